@@ -1,0 +1,171 @@
+"""CPU checks of the DEVICE arithmetic (rust-eth-kzg_b200/csrc/{mp,field,g1,g1_mul}.cuh) compiled with the
+PTX carry-chain primitives replaced by their host emulation (tests/host_emu/*.cpp).  The expected
+values come from Python big integers and the oracle's affine curve arithmetic (oracle/pyref.py).
+This is the only way to exercise the limb-level algorithms in the GPU-less build container; the
+same functions are re-checked on the real device by tests/test_gpu_primitives.py."""
+import ctypes
+import os
+import random
+import subprocess
+
+import pytest
+
+from oracle import pyref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "rust-eth-kzg_b200", "csrc")
+P, R = pyref.P, pyref.R
+
+
+def _build(name):
+    src = os.path.join(ROOT, "tests", "host_emu", name + ".cpp")
+    out = os.path.join(ROOT, "tests", "host_emu", name + ".so")
+    deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-w", "-x", "c++", "-std=c++17", "-shared", "-fPIC", "-I" + CSRC, "-o", out, src])
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def emu_field():
+    return _build("emu_field")
+
+
+@pytest.fixture(scope="module")
+def emu_g1():
+    return _build("emu_g1")
+
+
+def arr(x, n):
+    return (ctypes.c_uint32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
+
+
+def val(a):
+    return sum(int(v) << (32 * i) for i, v in enumerate(a))
+
+
+@pytest.mark.parametrize("mod,n,pre", [(P, 12, "fp"), (R, 8, "fr")])
+def test_field_ops(emu_field, mod, n, pre):
+    rng = random.Random(1)
+    Rm = 1 << (32 * n)
+    Ri = pow(Rm, -1, mod)
+    edge = [0, 1, 2, mod - 1, mod - 2, Rm % mod, (mod - 1) // 2, (mod + 1) // 2]
+    vals = edge + [rng.randrange(mod) for _ in range(200)]
+    out = (ctypes.c_uint32 * n)()
+    for a in vals:
+        for b in rng.sample(vals, 6) + edge:
+            getattr(emu_field, "emu_%s_mul" % pre)(arr(a, n), arr(b, n), out)
+            assert val(out) == a * b * Ri % mod
+            getattr(emu_field, "emu_%s_add" % pre)(arr(a, n), arr(b, n), out)
+            assert val(out) == (a + b) % mod
+            getattr(emu_field, "emu_%s_sub" % pre)(arr(a, n), arr(b, n), out)
+            assert val(out) == (a - b) % mod
+    for a in vals[1:30]:
+        getattr(emu_field, "emu_%s_inv" % pre)(arr(a, n), out)
+        assert val(out) == pow(a * Ri % mod, -1, mod) * Rm % mod
+    for a in [0, 1, R - 1, R, R + 1, 2**256 - 1]:
+        assert emu_field.emu_fr_ge_mod(arr(a, 8)) == (1 if a >= R else 0)
+    for a in [0, (P - 1) // 2, (P - 1) // 2 + 1, P - 1]:
+        assert emu_field.emu_fp_gt_half(arr(a, 12)) == (1 if a > (P - 1) // 2 else 0)
+
+
+def _pts(rng, n):
+    return [pyref.g1_mul(pyref.G1_GEN, rng.randrange(1, R)) for _ in range(n)]
+
+
+def test_g1_compress_roundtrip(emu_g1):
+    rng = random.Random(2)
+    out = ctypes.create_string_buffer(48)
+    for pt in _pts(rng, 8) + [None]:
+        b = pyref.g1_compress(pt)
+        assert emu_g1.emu_g1_decompress_roundtrip(b, out) == 0
+        assert out.raw == b
+    # malformed encodings: no compression flag, x >= p, not on curve, dirty infinity
+    bad = [bytes(48), b"\x9f" + b"\xff" * 47, b"\xc0" + b"\x00" * 46 + b"\x01", b"\xe0" + b"\x00" * 47]
+    x = 1
+    while True:  # find an x with no curve point
+        if pow((x**3 + 4) % P, (P - 1) // 2, P) != 1:
+            break
+        x += 1
+    bad.append(bytes([0x80]) + x.to_bytes(48, "big")[1:])
+    for b in bad:
+        assert emu_g1.emu_g1_decompress_roundtrip(b, out) != 0
+
+
+def test_g1_binops(emu_g1):
+    rng = random.Random(3)
+    pts = _pts(rng, 4)
+    out = ctypes.create_string_buffer(48)
+    cases = [(a, b) for a in pts[:3] for b in pts[:3]] + [(pts[0], None), (None, pts[1]), (None, None), (pts[0], pyref.g1_neg(pts[0]))]
+    for a, b in cases:
+        pa, pb = pyref.g1_compress(a), pyref.g1_compress(b)
+        s = pyref.g1_compress(pyref.g1_add(a, b))
+        d = pyref.g1_compress(pyref.g1_add(a, pyref.g1_neg(b)))
+        dbl = pyref.g1_compress(pyref.g1_add(a, a))
+        for op, exp in [(0, s), (1, d), (2, s), (3, s), (4, s), (5, d), (6, dbl), (7, dbl)]:
+            assert emu_g1.emu_g1_binop(op, pa, pb, out) == 0
+            assert out.raw == exp, (op, a is None, b is None)
+
+
+def test_g1_chains(emu_g1):
+    rng = random.Random(4)
+    out = ctypes.create_string_buffer(48)
+    for trial in range(3):
+        n = 10
+        pts = _pts(rng, n)
+        if trial == 1:  # force P+P, P-P and identity inside the chain
+            pts[3] = pts[2]; pts[5] = None; pts[1] = pts[0]
+        negs = [rng.randrange(2) for _ in range(n)]
+        if trial == 1:
+            negs[0], negs[1] = 0, 1   # P - P at the start -> identity accumulator
+            negs[2], negs[3] = 1, 1   # -P -P -> doubling
+        exp = None
+        for p, s in zip(pts, negs):
+            exp = pyref.g1_add(exp, pyref.g1_neg(p) if s else p)
+        buf = b"".join(pyref.g1_compress(p) for p in pts)
+        for mode in range(4):
+            assert emu_g1.emu_g1_chain(mode, n, buf, bytes(negs), out) == 0
+            assert out.raw == pyref.g1_compress(exp), (trial, mode)
+    # two equal half-chains (xyzz_add / jac_add doubling branch) and opposite half-chains (identity)
+    pts = _pts(rng, 3)
+    buf = b"".join(pyref.g1_compress(p) for p in pts + pts)
+    tot = None
+    for p in pts:
+        tot = pyref.g1_add(tot, p)
+    for mode in (2, 3):
+        assert emu_g1.emu_g1_chain(mode, 6, buf, bytes(6), out) == 0
+        assert out.raw == pyref.g1_compress(pyref.g1_add(tot, tot))
+        assert emu_g1.emu_g1_chain(mode, 6, buf, bytes([0, 0, 0, 1, 1, 1]), out) == 0
+        assert out.raw == pyref.g1_compress(None)
+
+
+def test_g1_scalar_mul(emu_g1):
+    rng = random.Random(5)
+    out = ctypes.create_string_buffer(48)
+    pt = _pts(rng, 1)[0]
+    pb = pyref.g1_compress(pt)
+    for k in [0, 1, 2, R - 1, rng.randrange(R), rng.randrange(2**256)]:
+        assert emu_g1.emu_g1_mul_u256(pb, arr(k, 8), out) == 0
+        assert out.raw == pyref.g1_compress(pyref.g1_mul(pt, k % R))
+    w128 = pyref.root_of_unity(128)
+    for e in [0, 1, 32, 63, 64, 127]:
+        assert emu_g1.emu_g1_mul_twiddle(pb, e, out) == 0
+        assert out.raw == pyref.g1_compress(pyref.g1_mul(pt, 2 * pow(w128, e, R) % R)), e
+
+
+def _booth_ref(s, t, w):
+    """literal transcription target: SURVEY.md Appendix A.4 closed form"""
+    v = ((s << 1) >> (t * w)) & ((1 << (w + 1)) - 1)
+    return ((v + 1) >> 1) - ((v >> w) << w)
+
+
+def test_booth_digits(emu_g1):
+    rng = random.Random(6)
+    for s in [0, 1, R - 1, 2**255 - 1, 2**256 - 1] + [rng.randrange(R) for _ in range(40)]:
+        for w in (4, 8, 9, 12, 13, 16):
+            nw = 255 // w + 1
+            ds = [emu_g1.emu_booth_digit(arr(s, 8), t, w) for t in range(nw + 1)]
+            assert ds == [_booth_ref(s, t, w) for t in range(nw + 1)]
+            if s < 2**255:
+                assert sum(d << (t * w) for t, d in enumerate(ds[:nw])) == s
+                assert all(abs(d) <= 1 << (w - 1) for d in ds)
