@@ -1,0 +1,130 @@
+/*
+ * C ABI of the B200-native KZG backend: libc_eth_kzg_b200.so.
+ *
+ * This is the drop-in boundary.  The first block reproduces, symbol for symbol, the header cbindgen
+ * generates from the reference's `bindings/c/src/lib.rs` (checked-in rendering:
+ * bindings/nim/nim_code/nim_eth_kzg/header.nim:5-140): same names, argument order, types, ownership
+ * and error behaviour, so the reference's C#/Nim/Go/Java shims link against this library unchanged.
+ * The second block is additive: batch entry points and device-pointer entry points that the
+ * reference does not have (its API is one blob per call).
+ *
+ * Ownership (bindings/c/src/pointer_utils.rs:53-62): every data buffer is caller-allocated; `out_cells`
+ * and `out_proofs` are arrays of 128 caller-owned pointers (2048 B / 48 B each).  The library owns only
+ * the context and error strings.  A failing call returns {Err, malloc'd message}; free it with
+ * eth_kzg_free_error_message.  Verification functions return Ok with *verified = false for a wrong
+ * proof and Err for malformed input (bindings/c/src/lib.rs:272-280).
+ */
+#ifndef C_ETH_KZG_B200_H
+#define C_ETH_KZG_B200_H
+
+#include <stdbool.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* bindings/c/src/lib.rs:41-44 (opaque) */
+typedef struct DASContext DASContext;
+
+/* bindings/c/src/lib.rs:118-123 */
+typedef enum CResultStatus {
+    Ok,
+    Err,
+} CResultStatus;
+
+/* bindings/c/src/lib.rs:128-132 */
+typedef struct CResult {
+    CResultStatus status;
+    char *error_msg;
+} CResult;
+
+/* bindings/c/src/lib.rs:79.  Builds the SRS-derived tables on the current CUDA device (override with
+ * EKZG_DEVICE).  use_precomp selects the fixed-base window width: false -> 8 bits, true -> the width in
+ * EKZG_FK20_WINDOW (default 8; wider windows trade HBM for fewer point additions per blob).
+ * Returns NULL if no CUDA device is usable: there is no CPU fallback. */
+DASContext *eth_kzg_das_context_new(bool use_precomp);
+
+/* bindings/c/src/lib.rs:109 (null-safe) */
+void eth_kzg_das_context_free(DASContext *ctx);
+
+/* bindings/c/src/lib.rs:171 (null-safe) */
+void eth_kzg_free_error_message(char *c_message);
+
+/* bindings/c/src/lib.rs:196  blob: 131072 B, out: 48 B */
+CResult eth_kzg_blob_to_kzg_commitment(const DASContext *ctx, const uint8_t *blob, uint8_t *out);
+
+/* bindings/c/src/lib.rs:226  out_cells: 128 x 2048 B, out_proofs: 128 x 48 B */
+CResult eth_kzg_compute_cells_and_kzg_proofs(const DASContext *ctx, const uint8_t *blob, uint8_t **out_cells,
+                                             uint8_t **out_proofs);
+
+/* bindings/c/src/lib.rs:255 */
+CResult eth_kzg_compute_cells(const DASContext *ctx, const uint8_t *blob, uint8_t **out_cells);
+
+/* bindings/c/src/lib.rs:309 */
+CResult eth_kzg_verify_cell_kzg_proof_batch(const DASContext *ctx, uint64_t commitments_length,
+                                            const uint8_t *const *commitments, uint64_t cell_indices_length,
+                                            const uint64_t *cell_indices, uint64_t cells_length,
+                                            const uint8_t *const *cells, uint64_t proofs_length,
+                                            const uint8_t *const *proofs, bool *verified);
+
+/* bindings/c/src/lib.rs:366 */
+CResult eth_kzg_recover_cells_and_proofs(const DASContext *ctx, uint64_t cells_length, const uint8_t *const *cells,
+                                         uint64_t cell_indices_length, const uint64_t *cell_indices, uint8_t **out_cells,
+                                         uint8_t **out_proofs);
+
+/* bindings/c/src/lib.rs:395-405 */
+uint64_t eth_kzg_constant_bytes_per_cell(void);
+uint64_t eth_kzg_constant_bytes_per_proof(void);
+uint64_t eth_kzg_constant_cells_per_ext_blob(void);
+
+/* bindings/c/src/lib.rs:423  z: 32 B, out_proof: 48 B, out_y: 32 B */
+CResult eth_kzg_compute_kzg_proof(const DASContext *ctx, const uint8_t *blob, const uint8_t *z, uint8_t *out_proof,
+                                  uint8_t *out_y);
+
+/* bindings/c/src/lib.rs:451 */
+CResult eth_kzg_compute_blob_kzg_proof(const DASContext *ctx, const uint8_t *blob, const uint8_t *commitment,
+                                       uint8_t *out_proof);
+
+/* bindings/c/src/lib.rs:480 */
+CResult eth_kzg_verify_kzg_proof(const DASContext *ctx, const uint8_t *commitment, const uint8_t *z, const uint8_t *y,
+                                 const uint8_t *proof, bool *verified);
+
+/* bindings/c/src/lib.rs:510 */
+CResult eth_kzg_verify_blob_kzg_proof(const DASContext *ctx, const uint8_t *blob, const uint8_t *commitment,
+                                      const uint8_t *proof, bool *verified);
+
+/* bindings/c/src/lib.rs:546 */
+CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext *ctx, uint64_t blobs_length, const uint8_t *const *blobs,
+                                            uint64_t commitments_length, const uint8_t *const *commitments,
+                                            uint64_t proofs_length, const uint8_t *const *proofs, bool *verified);
+
+/* ------------------------------------------------------------------------------------------------
+ * Additive B200 entry points (not in the reference; SURVEY.md §8b "Gap vs BASELINE.json configs").
+ * ---------------------------------------------------------------------------------------------- */
+
+/* n independent blobs in one call, HOST buffers, contiguous: blobs = n*131072 B, out_cells = n*128*2048 B,
+ * out_proofs = n*128*48 B.  blob_status[i] (optional, may be NULL) is 0 for a valid blob and 1 for a
+ * non-canonical one, whose outputs are left unspecified; the call returns Err iff any blob is invalid.
+ * Internally the batch is streamed through the device in chunks with copies overlapped with compute.
+ * Batch form of eip7594/src/prover.rs:117-134. */
+CResult eth_kzg_b200_compute_cells_and_kzg_proofs_batch(const DASContext *ctx, uint64_t n, const uint8_t *blobs,
+                                                        uint8_t *out_cells, uint8_t *out_proofs, uint8_t *blob_status);
+
+/* Same computation on buffers that already live on the context's device (layout as above, 16-byte aligned);
+ * d_status is n uint32 (0 ok / 1 invalid blob).  Runs asynchronously on `cuda_stream` (a cudaStream_t; 0 for the
+ * default stream); no host synchronisation.  d_cells may be NULL to skip cell output. */
+CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext *ctx, uint64_t n, const void *d_blobs,
+                                                         void *d_cells, void *d_proofs, void *d_status, void *cuda_stream);
+
+/* CUDA device ordinal the context lives on, fixed-base window width, and bytes of HBM its tables occupy. */
+int eth_kzg_b200_context_device(const DASContext *ctx);
+int eth_kzg_b200_context_window(const DASContext *ctx);
+uint64_t eth_kzg_b200_context_table_bytes(const DASContext *ctx);
+/* kernel launches issued by one device batch call (for launch accounting in benchmarks) */
+int eth_kzg_b200_launches_per_batch(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C_ETH_KZG_B200_H */

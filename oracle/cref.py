@@ -138,3 +138,21 @@ def verify_cell_kzg_proof_batch(commitments, cell_indices, cells, proofs):
     _chk(lib().okzg_verify_cell_kzg_proof_batch(len(commitments), b"".join(commitments), len(cell_indices), idx,
                                                  len(cells), b"".join(cells), len(proofs), b"".join(proofs), C.byref(ok)))
     return bool(ok.value)
+
+
+def fk20_stages(blob):
+    """(scalars[128][64] ints, msm[128] compressed R_j, h[64] compressed) of one blob -- stage parity hook"""
+    sc = C.create_string_buffer(128 * 64 * 32)
+    msm = C.create_string_buffer(128 * 48)
+    h = C.create_string_buffer(64 * 48)
+    _chk(lib().okzg_test_fk20_stages(bytes(blob), sc, msm, h))
+    scalars = [[int.from_bytes(sc.raw[32 * (j * 64 + k):32 * (j * 64 + k) + 32], "big") for k in range(64)] for j in range(128)]
+    return scalars, [msm.raw[48 * j:48 * j + 48] for j in range(128)], [h.raw[48 * i:48 * i + 48] for i in range(64)]
+
+
+def g1_mul(p48, k):
+    out = C.create_string_buffer(48)
+    rc = lib().okzg_test_g1_mul(bytes(p48), int(k).to_bytes(32, "big"), out)
+    if rc != 0:
+        raise OracleError("g1_mul rc=%d" % rc)
+    return out.raw

@@ -752,3 +752,30 @@ void okzg_test_fk20_msm(const uint8_t *scalars_be, uint8_t *out) {
         g1_t r; fixed_base_msm(&r, G.fk20_table + (size_t)j * 64 * PRECOMP_ENTRIES, s); g1_compress(out + 48 * j, &r);
     }
 }
+/* FK20 intermediates of one blob for stage-by-stage kernel parity (tests/test_gpu_stages.py):
+ * scalars: A_k[j] as BE32 at [(j*64+k)*32]; msm: 128 compressed R_j; h: 64 compressed h-commitments
+ * (fk20/batch_toeplitz.rs:94-124). */
+int okzg_test_fk20_stages(const uint8_t *blob, uint8_t *scalars, uint8_t *msm, uint8_t *h) {
+    fr_t *c = malloc(sizeof(fr_t) * N_BLOB);
+    if (!blob_to_scalars(c, blob)) { free(c); return OKZG_ERR_INPUT; }
+    scalars_to_coeffs(&G, c);
+    fr_t (*A)[128] = malloc(sizeof(fr_t) * 64 * 128);
+    for (int k = 0; k < 64; k++) {
+        fr_t *a = A[k];
+        for (int i = 0; i < 128; i++) fr_set_zero(&a[i]);
+        a[0] = c[4095 - k];
+        for (int i = 1; i < 64; i++) a[128 - i] = c[4095 - k - 64 * i];
+        fft_fr(&G.d128, a);
+    }
+    g1_t R[128];
+    for (int j = 0; j < 128; j++) {
+        fr_t s[64];
+        for (int k = 0; k < 64; k++) { s[k] = A[k][j]; fr_to_be(scalars + 32 * (j * 64 + k), &s[k]); }
+        fixed_base_msm(&R[j], G.fk20_table + (size_t)j * 64 * PRECOMP_ENTRIES, s);
+        g1_compress(msm + 48 * j, &R[j]);
+    }
+    ifft_g1_take_n(&G.d128, R, 64);
+    for (int i = 0; i < 64; i++) g1_compress(h + 48 * i, &R[i]);
+    free(A); free(c);
+    return OKZG_OK;
+}

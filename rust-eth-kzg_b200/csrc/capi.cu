@@ -1,0 +1,158 @@
+// extern "C" surface of libc_eth_kzg_b200.so (include/c_eth_kzg.h): pointer marshalling only, like the
+// reference's bindings/c/src/*.rs.  Every function binds the context's device, so calls may come from
+// any host thread (bindings/node calls from the libuv pool, SURVEY.md §8b "Threading").
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "../../include/c_eth_kzg.h"
+#include "kzg_runtime.h"
+
+using ekzg::Status;
+
+struct DASContext {
+    std::unique_ptr<ekzg::Context> inner;
+};
+
+static CResult c_ok() { return CResult{Ok, nullptr}; }
+static CResult c_err(const std::string& m) {
+    char* p = (char*)malloc(m.size() + 1);
+    if (p) memcpy(p, m.c_str(), m.size() + 1);
+    return CResult{Err, p};
+}
+static CResult to_c(const Status& s) { return s.ok ? c_ok() : c_err(s.msg); }
+static const ekzg::Context& cx(const DASContext* ctx) {
+    if (!ctx) {  // the reference asserts (bindings/c/src/lib.rs: `assert!(!ctx.is_null())`) and aborts
+        fprintf(stderr, "c_eth_kzg_b200: null DASContext\n");
+        abort();
+    }
+    return *ctx->inner;
+}
+
+extern "C" {
+
+DASContext* eth_kzg_das_context_new(bool use_precomp) {
+    std::unique_ptr<ekzg::Context> c;
+    Status s = ekzg::Context::create(use_precomp, &c);
+    if (!s.ok) {
+        fprintf(stderr, "c_eth_kzg_b200: context creation failed: %s\n", s.msg.c_str());
+        return nullptr;
+    }
+    DASContext* d = new DASContext();
+    d->inner = std::move(c);
+    return d;
+}
+
+void eth_kzg_das_context_free(DASContext* ctx) {
+    if (ctx) delete ctx;
+}
+
+void eth_kzg_free_error_message(char* c_message) {
+    if (c_message) free(c_message);
+}
+
+uint64_t eth_kzg_constant_bytes_per_cell(void) { return ekzg::BYTES_PER_CELL; }
+uint64_t eth_kzg_constant_bytes_per_proof(void) { return ekzg::BYTES_PER_G1; }
+uint64_t eth_kzg_constant_cells_per_ext_blob(void) { return ekzg::N_CELLS; }
+
+CResult eth_kzg_compute_cells_and_kzg_proofs(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells, uint8_t** out_proofs) {
+    std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32), proofs((size_t)ekzg::N_CELLS * 48);
+    Status s = cx(ctx).compute_cells_and_kzg_proofs_batch(1, blob, cells.data(), proofs.data(), nullptr, true);
+    if (!s.ok) return c_err(s.msg);
+    for (int i = 0; i < ekzg::N_CELLS; i++) {  // pointer_utils.rs:53-62 write_to_2d_slice
+        memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
+        memcpy(out_proofs[i], proofs.data() + (size_t)i * 48, 48);
+    }
+    return c_ok();
+}
+
+CResult eth_kzg_compute_cells(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells) {
+    std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32);
+    Status s = cx(ctx).compute_cells_and_kzg_proofs_batch(1, blob, cells.data(), nullptr, nullptr, false);
+    if (!s.ok) return c_err(s.msg);
+    for (int i = 0; i < ekzg::N_CELLS; i++) memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
+    return c_ok();
+}
+
+CResult eth_kzg_b200_compute_cells_and_kzg_proofs_batch(const DASContext* ctx, uint64_t n, const uint8_t* blobs, uint8_t* out_cells,
+                                                        uint8_t* out_proofs, uint8_t* blob_status) {
+    return to_c(cx(ctx).compute_cells_and_kzg_proofs_batch(n, blobs, out_cells, out_proofs, blob_status, out_proofs != nullptr));
+}
+
+CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext* ctx, uint64_t n, const void* d_blobs, void* d_cells,
+                                                         void* d_proofs, void* d_status, void* cuda_stream) {
+    const ekzg::Context& c = cx(ctx);
+    Status s = c.bind_device();
+    if (!s.ok) return c_err(s.msg);
+    if (n == 0) return c_ok();
+    if (n > (1u << 20)) return c_err("batch too large");
+    ekzg::Workspace* ws = c.acquire((int)n, false);
+    if (!ws) return c_err("device memory allocation failed");
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    s = c.fk20_device(*ws, (int)n, (const uint8_t*)d_blobs, (uint8_t*)d_cells, (uint8_t*)d_proofs, (uint32_t*)d_status, st);
+    // the scratch buffers are reused by the next call on this context: order later work after this batch
+    if (s.ok) {
+        cudaEventRecord(ws->done, st);
+        cudaStreamWaitEvent(ws->stream, ws->done, 0);
+    }
+    c.give_back(ws);
+    return to_c(s);
+}
+
+int eth_kzg_b200_context_device(const DASContext* ctx) { return cx(ctx).device(); }
+int eth_kzg_b200_context_window(const DASContext* ctx) { return cx(ctx).tables().w; }
+uint64_t eth_kzg_b200_context_table_bytes(const DASContext* ctx) { return cx(ctx).table_bytes(); }
+int eth_kzg_b200_launches_per_batch(void) { return ekzg::FK20_LAUNCHES_PER_BATCH + 1 /* status memset */; }
+
+// Stage dump of one blob for kernel-level parity tests: plain scalars [128][64][8 x u32 LE],
+// MSM outputs (natural j order) and h commitments as compressed points.  Synchronous; test hook.
+CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blob, uint32_t* out_scalars, uint8_t* out_msm, uint8_t* out_h) {
+    using namespace ekzg;
+    const Context& c = cx(ctx);
+    Status s = c.bind_device();
+    if (!s.ok) return c_err(s.msg);
+    Workspace* ws = c.acquire(1, true);
+    if (!ws) return c_err("allocation failed");
+    cudaStream_t st = ws->stream;
+    const DevTables& T = c.tables();
+    auto fail = [&](const char* m) { c.give_back(ws); return c_err(m); };
+    if (cudaMemcpyAsync(ws->d_blobs, blob, BYTES_PER_BLOB, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail("h2d");
+    cudaMemsetAsync(ws->d_status, 0, 4, st);
+    if (launch_blob_to_coeffs_cells(ws->d_blobs, ws->d_coeffs, ws->d_cells, ws->d_status, T, 1, true, st) != cudaSuccess) return fail("k1");
+    if (launch_toeplitz_scalars(ws->d_coeffs, ws->d_scalars, T, 1, st) != cudaSuccess) return fail("k2");
+    if (cudaMemcpyAsync(out_scalars, ws->d_scalars, 128 * 64 * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("d2h scalars");
+    if (launch_fk20_msm(ws->d_scalars, ws->d_pts, T, 1, st) != cudaSuccess) return fail("k4");
+    // MSM outputs sit at bit-reversed positions; compress all 128 then un-permute on the host
+    if (launch_g1_compress(ws->d_pts, ws->d_proofs, 128, 1, st) != cudaSuccess) return fail("k6");
+    uint8_t tmp[128 * 48];
+    if (cudaMemcpyAsync(tmp, ws->d_proofs, sizeof(tmp), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("d2h msm");
+    for (int sidx = 0; sidx <= 6; sidx++)
+        if (launch_g1_ntt_stage(ws->d_pts, T, 1, sidx, 0, st) != cudaSuccess) return fail("k5");
+    if (launch_g1_compress(ws->d_pts, ws->d_proofs, 64, 1, st) != cudaSuccess) return fail("k6b");
+    if (cudaMemcpyAsync(out_h, ws->d_proofs, 64 * 48, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("d2h h");
+    cudaError_t e = cudaStreamSynchronize(st);
+    c.give_back(ws);
+    if (e != cudaSuccess) return c_err(cudaGetErrorString(e));
+    for (int j = 0; j < 128; j++) {
+        int r = 0;
+        for (int b = 0; b < 7; b++) r |= ((j >> b) & 1) << (6 - b);
+        memcpy(out_msm + 48 * j, tmp + 48 * r, 48);
+    }
+    return c_ok();
+}
+
+// ---- not built yet in this round: fail loudly, never fall back to a CPU path ----
+static CResult not_yet(const char* what) { return c_err(std::string(what) + ": not implemented in this build of c_eth_kzg_b200"); }
+
+CResult eth_kzg_blob_to_kzg_commitment(const DASContext* ctx, const uint8_t*, uint8_t*) { cx(ctx); return not_yet("blob_to_kzg_commitment"); }
+CResult eth_kzg_verify_cell_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint64_t*, uint64_t,
+                                            const uint8_t* const*, uint64_t, const uint8_t* const*, bool*) { cx(ctx); return not_yet("verify_cell_kzg_proof_batch"); }
+CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint64_t*, uint8_t**,
+                                         uint8_t**) { cx(ctx); return not_yet("recover_cells_and_proofs"); }
+CResult eth_kzg_compute_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*) { cx(ctx); return not_yet("compute_kzg_proof"); }
+CResult eth_kzg_compute_blob_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, uint8_t*) { cx(ctx); return not_yet("compute_blob_kzg_proof"); }
+CResult eth_kzg_verify_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_kzg_proof"); }
+CResult eth_kzg_verify_blob_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_blob_kzg_proof"); }
+CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint8_t* const*, uint64_t,
+                                            const uint8_t* const*, bool*) { cx(ctx); return not_yet("verify_blob_kzg_proof_batch"); }
+
+}  // extern "C"

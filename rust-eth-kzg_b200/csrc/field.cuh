@@ -15,7 +15,7 @@
 namespace ekzg {
 
 template <class P>
-struct Fe {
+struct alignas(16) Fe {
     uint32_t v[P::N];
 };
 using Fp = Fe<FpParams>;
@@ -265,8 +265,8 @@ struct FpExpSqrt {  // (p+1)/4
     EKZG_HD uint32_t operator()(int i) const { return FpParams::exp_sqrt(i); }
 };
 
-EKZG_HD void fp_inv(Fp& out, const Fp& a) { fe_pow_limbs(out, a, FpExpInv(), 381); }
-EKZG_HD void fr_inv(Fr& out, const Fr& a) { fe_pow_limbs(out, a, FrExpInv(), 255); }
-EKZG_HD void fp_sqrt_candidate(Fp& out, const Fp& a) { fe_pow_limbs(out, a, FpExpSqrt(), 379); }
+EKZG_HD_CALL void fp_inv(Fp& out, const Fp& a) { fe_pow_limbs(out, a, FpExpInv(), 381); }
+EKZG_HD_CALL void fr_inv(Fr& out, const Fr& a) { fe_pow_limbs(out, a, FrExpInv(), 255); }
+EKZG_HD_CALL void fp_sqrt_candidate(Fp& out, const Fp& a) { fe_pow_limbs(out, a, FpExpSqrt(), 379); }
 
 }  // namespace ekzg

@@ -40,7 +40,7 @@ EKZG_HD void jac_from_affine(G1Jac& r, const G1Affine& p) {
 }
 
 // 2*P for affine P != identity  (mdbl-2008-s-1, a = 0)
-EKZG_HD void xyzz_dbl_affine(G1Xyzz& r, const G1Affine& p) {
+EKZG_HD_CALL void xyzz_dbl_affine(G1Xyzz& r, const G1Affine& p) {
     Fp u, v, w, s, m, t;
     fe_dbl(u, p.y);
     fe_sqr(v, u);
@@ -86,7 +86,7 @@ EKZG_HD void xyzz_madd(G1Xyzz& acc, const G1Affine& p_in, bool neg) {
 }
 
 // 2*P, general XYZZ  (dbl-2008-s-1, a = 0)
-EKZG_HD void xyzz_dbl(G1Xyzz& r, const G1Xyzz& p) {
+EKZG_HD_CALL void xyzz_dbl(G1Xyzz& r, const G1Xyzz& p) {
     if (xyzz_is_inf(p)) { xyzz_set_inf(r); return; }
     Fp u, v, w, s, m, t;
     fe_dbl(u, p.y);
@@ -106,7 +106,7 @@ EKZG_HD void xyzz_dbl(G1Xyzz& r, const G1Xyzz& p) {
 }
 
 // acc += q, both XYZZ  (add-2008-s: 12M + 2S)
-EKZG_HD void xyzz_add(G1Xyzz& acc, const G1Xyzz& q) {
+EKZG_HD_CALL void xyzz_add(G1Xyzz& acc, const G1Xyzz& q) {
     if (xyzz_is_inf(q)) return;
     if (xyzz_is_inf(acc)) { acc = q; return; }
     Fp u1, u2, s1, s2, pp, ppp, t;
@@ -148,7 +148,7 @@ EKZG_HD void jac_from_xyzz(G1Jac& r, const G1Xyzz& p) {
 }
 
 // 2*P Jacobian (dbl-2009-l, a = 0): 2M + 5S.  Identity stays identity (Z3 = 2*Y*0).
-EKZG_HD void jac_dbl(G1Jac& r, const G1Jac& p) {
+EKZG_HD_CALL void jac_dbl(G1Jac& r, const G1Jac& p) {
     Fp a, b, c, d, e, f;
     fe_sqr(a, p.x);
     fe_sqr(b, p.y);
@@ -166,7 +166,7 @@ EKZG_HD void jac_dbl(G1Jac& r, const G1Jac& p) {
 }
 
 // acc += q, both Jacobian  (add-2007-bl: 11M + 5S)
-EKZG_HD void jac_add(G1Jac& acc, const G1Jac& q) {
+EKZG_HD_CALL void jac_add(G1Jac& acc, const G1Jac& q) {
     if (jac_is_inf(q)) return;
     if (jac_is_inf(acc)) { acc = q; return; }
     Fp z1z1, z2z2, u1, u2, s1, s2, h, i, j, rr, v;
@@ -200,7 +200,7 @@ EKZG_HD void jac_neg(G1Jac& r, const G1Jac& p) { r.x = p.x; fe_neg(r.y, p.y); r.
 EKZG_HD void jac_cneg(G1Jac& r, const G1Jac& p, bool neg) { r.x = p.x; fe_cneg(r.y, p.y, neg); r.z = p.z; }
 
 // acc += (neg ? -P : P), P affine  (madd-2007-bl: 7M + 4S)
-EKZG_HD void jac_madd(G1Jac& acc, const G1Affine& p_in, bool neg) {
+EKZG_HD_CALL void jac_madd(G1Jac& acc, const G1Affine& p_in, bool neg) {
     if (g1a_is_inf(p_in)) return;
     G1Affine p;
     p.x = p_in.x;
@@ -250,7 +250,7 @@ EKZG_HD void jac_to_affine_with_inv(G1Affine& r, const G1Jac& p, const Fp& zinv)
 // serialize an affine point (Montgomery coordinates) to the 48-byte compressed wire format
 // (crates/serialization/src/lib.rs:84-86 -> blstrs to_compressed):
 // big-endian x; byte0 bit7 = compressed, bit6 = identity, bit5 = y > (p-1)/2.
-EKZG_HD void g1a_compress(uint8_t* out, const G1Affine& p) {
+EKZG_HD_CALL void g1a_compress(uint8_t* out, const G1Affine& p) {
     if (g1a_is_inf(p)) {
         out[0] = 0xc0;
         for (int i = 1; i < 48; i++) out[i] = 0;
@@ -283,7 +283,7 @@ EKZG_HD bool g1a_on_curve(const G1Affine& p) {
 }
 
 // parse 48 compressed bytes. returns 0 ok, 1 malformed / not on curve.  No subgroup check here.
-EKZG_HD int g1a_decompress(G1Affine& r, const uint8_t* in) {
+EKZG_HD_CALL int g1a_decompress(G1Affine& r, const uint8_t* in) {
     uint8_t b0 = in[0];
     if (!(b0 & 0x80)) return 1;  // uncompressed form not accepted for 48-byte input
     bool inf = b0 & 0x40, sign = b0 & 0x20;

@@ -45,7 +45,7 @@ EKZG_HD int booth_digit(const uint32_t* s, int t, int w) {
 }
 
 // k*P, k = k1 + k2*lambda given as signed radix-16 digits d[0..32] (k1) and d[33..65] (k2).
-EKZG_HD void jac_mul_glv16(G1Jac& out, const G1Jac& p, const int8_t* d) {
+EKZG_HD_CALL void jac_mul_glv16(G1Jac& out, const G1Jac& p, const int8_t* d) {
     G1Jac tbl[8];  // tbl[i] = (i+1)*P
     tbl[0] = p;
     jac_dbl(tbl[1], p);
@@ -80,7 +80,7 @@ EKZG_HD void jac_mul_glv16(G1Jac& out, const G1Jac& p, const int8_t* d) {
 }
 
 // k*P for a plain 256-bit little-endian scalar (unsigned 4-bit windows); setup paths only
-EKZG_HD void jac_mul_u256(G1Jac& out, const G1Jac& p, const uint32_t* k) {
+EKZG_HD_CALL void jac_mul_u256(G1Jac& out, const G1Jac& p, const uint32_t* k) {
     G1Jac tbl[15];
     tbl[0] = p;
     for (int i = 1; i < 15; i++) { tbl[i] = tbl[i - 1]; jac_add(tbl[i], p); }

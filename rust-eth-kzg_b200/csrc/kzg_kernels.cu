@@ -1,0 +1,513 @@
+// sm_100a kernels of the FK20 prover path (compute_cells_and_kzg_proofs) and the one-off table setup.
+// Launch wrappers at the bottom; the host runtime (kzg_runtime.cu) only sees kzg_kernels.h.
+//
+// Batch layout (B blobs per launch, everything resident in HBM):
+//   blobs   [B][131072]  bytes as on the wire
+//   coeffs  [B][4096]    Fr, Montgomery form (monomial coefficients, A.1 of SURVEY.md)
+//   cells   [B][8192*32] bytes as on the wire (cells 0..63 = the blob itself)
+//   scalars [128][64][B] plain 256-bit integers: scalar k of MSM j of blob b (blob fastest, so a warp
+//                        of 32 blobs working on the same MSM reads 1 KiB contiguous)
+//   pts     [128][B]     G1Jac, position-major / blob fastest (same reason)
+//   proofs  [B][128*48]  bytes as on the wire
+#include "kzg_kernels.h"
+#include "fr_ntt.cuh"
+
+namespace ekzg {
+
+__device__ __forceinline__ int rev_bits(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
+
+// ------------------------------------------------------------------------------------------------
+// setup: twiddle tables  tw[i] = base^i
+// ------------------------------------------------------------------------------------------------
+__global__ void k_powers(Fr* out, Fr base, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fr acc, b = base;
+    fe_set_one(acc);
+    for (int e = i; e; e >>= 1) {
+        if (e & 1) fe_mul(acc, acc, b);
+        fe_sqr(b, b);
+    }
+    st_vec(&out[i], acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  blob bytes -> coefficients (+ the upper 64 cells)
+//   reference: deserialize_blob_to_scalars (serialization/src/lib.rs:36-63), reverse_bit_order + ifft_scalars
+//   (fk20/prover.rs:177-180), compute_coset_evaluations (fk20/prover.rs:158-165), serialize (lib.rs:132-156).
+//   One CTA per blob, the 4096 elements stay in shared memory (128 KiB) from the wire format in to the
+//   wire format out.  The 8192-point extension is split by hand: its even outputs are the blob itself
+//   (cells 0..63 are a byte copy), its odd outputs are one 4096-point NTT of c[i]*omega_8192^i.
+// ------------------------------------------------------------------------------------------------
+constexpr int K1_THREADS = 1024;
+
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k_blob_to_coeffs_cells(const uint8_t* __restrict__ blobs, Fr* __restrict__ coeffs, uint8_t* __restrict__ cells,
+                       uint32_t* __restrict__ status, DevTables T, int want_cells) {
+    extern __shared__ uint32_t sm[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const uint8_t* blob = blobs + (size_t)b * BYTES_PER_BLOB;
+    const Fr r2 = fe_const_r2<FrParams>();
+    bool bad = false;
+    for (int i = tid; i < N_BLOB; i += K1_THREADS) {
+        Fr e = fr_load_be(blob + 32 * i);
+        bad |= fe_plain_ge_mod(e);
+        fe_mul(e, e, r2);
+        smem_st(sm, N_BLOB, i, e);
+    }
+    if (bad) atomicOr(&status[b], 1u);
+    __syncthreads();
+    // c = INTT_4096(BRP(e)): DIT on the array as it lies
+    ntt_dit_shared<12>(sm, N_BLOB, 1, T.tw4096_inv, tid, K1_THREADS);
+    const Fr ninv = fr_inv_4096();
+    Fr* cf = coeffs + (size_t)b * N_BLOB;
+    for (int i = tid; i < N_BLOB; i += K1_THREADS) {
+        Fr c = smem_ld(sm, N_BLOB, i);
+        fe_mul(c, c, ninv);
+        st_vec(&cf[i], c);
+        if (want_cells) {
+            Fr w = ld_vec(&T.tw8192[i]);
+            fe_mul(c, c, w);
+            smem_st(sm, N_BLOB, i, c);
+        }
+    }
+    if (!want_cells) return;
+    __syncthreads();
+    ntt_dif_shared<12>(sm, N_BLOB, 1, T.tw4096, tid, K1_THREADS);
+    uint8_t* out = cells + (size_t)b * (N_EXT * 32);
+    for (int i = tid; i < N_BLOB; i += K1_THREADS) {
+        Fr v = smem_ld(sm, N_BLOB, i);
+        fe_from_mont(v, v);
+        fr_store_be(out + (size_t)(N_BLOB + i) * 32, v);
+        // cells 0..63: BRP(NTT_4096(c)) == the blob's own field elements
+        const uint4* src = reinterpret_cast<const uint4*>(blob + 32 * i);
+        uint4* dst = reinterpret_cast<uint4*>(out + 32 * i);
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+}
+
+// coefficients -> all 128 cells (recovery path: Input::PolyCoeff, fk20/prover.rs:184-188 + 158-165)
+__global__ void __launch_bounds__(K1_THREADS, 1)
+k_coeffs_to_cells(const Fr* __restrict__ coeffs, uint8_t* __restrict__ cells, DevTables T) {
+    extern __shared__ uint32_t sm[];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const Fr* cf = coeffs + (size_t)b * N_BLOB;
+    uint8_t* out = cells + (size_t)b * (N_EXT * 32);
+    for (int halfsel = 0; halfsel < 2; halfsel++) {
+        for (int i = tid; i < N_BLOB; i += K1_THREADS) {
+            Fr c = ld_vec(&cf[i]);
+            if (halfsel) {
+                Fr w = ld_vec(&T.tw8192[i]);
+                fe_mul(c, c, w);
+            }
+            smem_st(sm, N_BLOB, i, c);
+        }
+        __syncthreads();
+        ntt_dif_shared<12>(sm, N_BLOB, 1, T.tw4096, tid, K1_THREADS);
+        for (int i = tid; i < N_BLOB; i += K1_THREADS) {
+            Fr v = smem_ld(sm, N_BLOB, i);
+            fe_from_mont(v, v);
+            fr_store_be(out + (size_t)(halfsel * N_BLOB + i) * 32, v);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  coefficients -> the 128x64 MSM scalars of a blob
+//   reference: compute_h_poly_commitments (fk20/h_poly.rs:36-53), CirculantMatrix::from_toeplitz
+//   (fk20/toeplitz.rs:132-144), the 64 fft_scalars(128) + transpose of sum_matrix_vector_mul
+//   (fk20/batch_toeplitz.rs:94-107).  a_k = [c[4095-k], 0^64, c[4095-k-64*63], ..., c[4095-k-64]].
+//   The 1/128 of the later G1 inverse NTT (domain.rs:172-194) is folded into the scalars here.
+//   One CTA handles K2_ROWS of the 64 rows of one blob.
+// ------------------------------------------------------------------------------------------------
+constexpr int K2_ROWS = 8;
+constexpr int K2_THREADS = K2_ROWS * 64;
+
+__global__ void __launch_bounds__(K2_THREADS)
+k_toeplitz_scalars(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars, DevTables T, int B) {
+    __shared__ uint32_t sm[8 * K2_ROWS * 128];
+    constexpr int STRIDE = K2_ROWS * 128;
+    const int b = blockIdx.x, k0 = blockIdx.y * K2_ROWS, tid = threadIdx.x;
+    const Fr* cf = coeffs + (size_t)b * N_BLOB;
+    const Fr inv128 = fr_inv_128();
+    for (int e = tid; e < K2_ROWS * 128; e += K2_THREADS) {
+        int q = e >> 7, i = e & 127, k = k0 + q;
+        Fr v;
+        fe_set_zero(v);
+        int src = -1;
+        if (i == 0) src = 4095 - k;
+        else if (i > 64) src = 4095 - k - 64 * (128 - i);
+        if (src >= 0) {
+            v = ld_vec(&cf[src]);
+            fe_mul(v, v, inv128);
+        }
+        smem_st(sm, STRIDE, e, v);
+    }
+    __syncthreads();
+    ntt_dif_shared<7>(sm, STRIDE, K2_ROWS, T.tw128, tid, K2_THREADS);
+    // array position p of row q holds A_k[rev7(p)]; write plain integers to scalars[j][k][b]
+    for (int e = tid; e < K2_ROWS * 128; e += K2_THREADS) {
+        int q = e >> 7, p = e & 127, k = k0 + q, j = rev_bits(p, 7);
+        Fr v = smem_ld(sm, STRIDE, e);
+        fe_from_mont(v, v);
+        uint32_t* dst = scalars + ((size_t)(j * FK20_POINTS + k) * B + b) * 8;
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        d4[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+        d4[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  the 128 fixed-base MSMs of every blob   (HOT LOOP #1)
+//   reference: FixedBaseMSMPrecompWindow::msm (fixed_base_msm_window.rs:102-168) with
+//   multi_batch_addition_binary_tree_stride (batch_addition.rs:142-232).
+//   One thread per (MSM j, blob b, slice of the 64 points): it walks its points and windows, turns each
+//   window into a signed Booth digit, gathers the table entry and accumulates in XYZZ coordinates
+//   (8M+2S per entry, no doublings at all because every window has its own table slice).  Lanes of a
+//   warp are 32 blobs on the same MSM, so table gathers hit the same few KiB and scalar loads coalesce.
+//   The slices of one (j, b) are combined through shared memory; the sum is written as a Jacobian point
+//   at the BIT-REVERSED position so the inverse G1 NTT can run decimation-in-time without a shuffle.
+// ------------------------------------------------------------------------------------------------
+template <int NSLICE>
+__global__ void __launch_bounds__(128)
+k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, DevTables T, int B) {
+    // block = 128 threads = NSLICE slices x (128/NSLICE) blobs of one MSM j
+    constexpr int BLOBS_PER_CTA = 128 / NSLICE;
+    constexpr int KPER = FK20_POINTS / NSLICE;
+    const int j = blockIdx.y;
+    const int lane_b = threadIdx.x % BLOBS_PER_CTA, slice = threadIdx.x / BLOBS_PER_CTA;
+    const int b = blockIdx.x * BLOBS_PER_CTA + lane_b;
+    const bool active = b < B;
+    G1Xyzz acc;
+    xyzz_set_inf(acc);
+    if (active) {
+        const int w = T.w, nw = T.nw;
+        for (int kk = 0; kk < KPER; kk++) {
+            const int k = slice * KPER + kk;
+            const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)(j * FK20_POINTS + k) * B + b) * 8);
+            uint4 s0 = sp[0], s1 = sp[1];
+            uint32_t s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const G1Affine* tb = T.fk20_table + fk20_index(T, j, k, 0, 0);
+            for (int t = 0; t < nw; t++) {
+                int d = booth_digit(s, t, w);
+                if (d != 0) {
+                    int m = (d < 0 ? -d : d) - 1;
+                    G1Affine e = ld_vec(&tb[(size_t)t * T.half + m]);
+                    xyzz_madd(acc, e, d < 0);
+                }
+            }
+        }
+    }
+    __shared__ G1Xyzz red[NSLICE > 1 ? 128 : 1];
+    if (NSLICE > 1) {
+        for (int step = NSLICE / 2; step >= 1; step >>= 1) {
+            if (slice >= step && slice < 2 * step) red[threadIdx.x] = acc;
+            __syncthreads();
+            if (slice < step) xyzz_add(acc, red[threadIdx.x + step * BLOBS_PER_CTA]);
+            __syncthreads();
+        }
+    }
+    if (active && slice == 0) {
+        G1Jac r;
+        jac_from_xyzz(r, acc);
+        st_vec(&pts[(size_t)rev_bits(j, 7) * B + b], r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  G1 NTT stages  (HOT LOOP #2)
+//   reference: Domain::ifft_g1_take_n / fft_g1 (polynomial/src/domain.rs:149-194) over the generic
+//   butterfly `dit` (fft.rs:164-177) whose `*b * twiddle` is a full scalar multiplication.
+//   One thread per (butterfly, blob), blob fastest: a warp is the same butterfly of 32 blobs, so the
+//   twiddle (hence the GLV digit string) is warp-uniform and trivial twiddles skip whole warps.
+//   mode 0: inverse DIT stage `st` (input bit-reversed, written that way by K4).  The last stage only
+//           produces the 64 kept outputs (ifft_g1_take_n(.., 64)); the 1/128 is already in the scalars.
+//   mode 1: forward DIF stage on (h || O^64): the first stage (st = 6) is h[i] -> (h[i], w^i h[i]).
+//           The output of the last stage is in bit-reversed order = proof order (fk20/prover.rs:222).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_g1_ntt_stage(G1Jac* __restrict__ pts, DevTables T, int B, int st, int mode) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= 64 * B) return;
+    const int t = gid / B, b = gid - t * B;
+    const int len = 1 << st;
+    const int pos = t & (len - 1);
+    const int i = ((t >> st) << (st + 1)) + pos, j = i + len;
+    const int e = pos << (6 - st);  // twiddle exponent of omega_128
+    G1Jac* pi = &pts[(size_t)i * B + b];
+    G1Jac* pj = &pts[(size_t)j * B + b];
+    if (mode == 0) {
+        G1Jac u = ld_vec(pi), v = ld_vec(pj);
+        if (e != 0 && !jac_is_inf(v)) jac_mul_glv16(v, v, T.glv_digits + 66 * ((128 - e) & 127));
+        G1Jac s = u;
+        jac_add(s, v);
+        st_vec(pi, s);
+        if (st != 6) {
+            jac_neg(v, v);
+            jac_add(u, v);
+            st_vec(pj, u);
+        }
+    } else {
+        if (st == 6) {
+            G1Jac u = ld_vec(pi);
+            if (e != 0 && !jac_is_inf(u)) jac_mul_glv16(u, u, T.glv_digits + 66 * e);
+            st_vec(pj, u);
+        } else {
+            G1Jac u = ld_vec(pi), v = ld_vec(pj);
+            G1Jac s = u;
+            jac_add(s, v);
+            jac_neg(v, v);
+            jac_add(u, v);
+            if (e != 0 && !jac_is_inf(u)) jac_mul_glv16(u, u, T.glv_digits + 66 * e);
+            st_vec(pi, s);
+            st_vec(pj, u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  Jacobian -> affine -> 48-byte compressed
+//   reference: g1_batch_normalize (bls12_381/src/lib.rs:56-104) + serialize_g1_compressed
+//   (serialization/src/lib.rs:84-86, 138).  One thread per point, blob-fastest input.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_g1_compress(const G1Jac* __restrict__ pts, uint8_t* __restrict__ out, int npos, int B) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= npos * B) return;
+    const int p = gid / B, b = gid - p * B;
+    G1Jac q = ld_vec(&pts[(size_t)p * B + b]);
+    G1Affine a;
+    if (jac_is_inf(q)) {
+        g1a_set_inf(a);
+    } else {
+        Fp zi;
+        fp_inv(zi, q.z);
+        jac_to_affine_with_inv(a, q, zi);
+    }
+    uint8_t buf[48];
+    g1a_compress(buf, a);
+    uint8_t* dst = out + ((size_t)b * npos + p) * BYTES_PER_G1;
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(buf);
+    (void)w;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        uint4 v;
+        v.x = buf[16 * c + 0] | (buf[16 * c + 1] << 8) | (buf[16 * c + 2] << 16) | ((uint32_t)buf[16 * c + 3] << 24);
+        v.y = buf[16 * c + 4] | (buf[16 * c + 5] << 8) | (buf[16 * c + 6] << 16) | ((uint32_t)buf[16 * c + 7] << 24);
+        v.z = buf[16 * c + 8] | (buf[16 * c + 9] << 8) | (buf[16 * c + 10] << 16) | ((uint32_t)buf[16 * c + 11] << 24);
+        v.w = buf[16 * c + 12] | (buf[16 * c + 13] << 8) | (buf[16 * c + 14] << 16) | ((uint32_t)buf[16 * c + 15] << 24);
+        d4[c] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// setup kernels
+// ------------------------------------------------------------------------------------------------
+// 48-byte compressed points -> affine Montgomery; status[i] != 0 on malformed input.
+__global__ void k_g1_decompress(const uint8_t* __restrict__ in, G1Affine* __restrict__ out, uint32_t* __restrict__ status, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[48];
+    for (int c = 0; c < 48; c++) buf[c] = in[(size_t)i * 48 + c];
+    G1Affine a;
+    int rc = g1a_decompress(a, buf);
+    if (rc) { g1a_set_inf(a); status[i] = 1; }
+    st_vec(&out[i], a);
+}
+
+// FK20 setup, step 1 (fk20/prover.rs:88-104): lay the 64 strided SRS vectors V_k out as the lower half of
+// a 128-point G1 NTT input, "blob" index := k.   pts[m][k] = srs[4031 - (k + 64 m)], m < 63; identity else.
+__global__ void k_fk20_setup_vectors(const G1Affine* __restrict__ srs, G1Jac* __restrict__ pts) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= 128 * 64) return;
+    int m = gid / 64, k = gid % 64;
+    G1Jac r;
+    jac_set_inf(r);
+    int idx = k + 64 * m;
+    if (m < 63 && idx < 4032) {
+        G1Affine a = ld_vec(&srs[4031 - idx]);
+        jac_from_affine(r, a);
+    }
+    st_vec(&pts[(size_t)m * 64 + k], r);
+}
+
+// FK20 setup, step 2: per base point P = F_k[j] (at pts[rev7(j)][k] after the DIF NTT) the window
+// bases Q_t = 2^(t*w) P, normalised to affine with one shared inversion per thread.
+constexpr int MAX_NW = 64;
+__global__ void __launch_bounds__(64)
+k_fk20_window_bases(const G1Jac* __restrict__ pts, G1Affine* __restrict__ qaff, int w, int nw) {
+    int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= FK20_MSMS * FK20_POINTS) return;
+    int j = gid / FK20_POINTS, k = gid % FK20_POINTS;
+    G1Jac p = ld_vec(&pts[(size_t)rev_bits(j, 7) * 64 + k]);
+    G1Affine* dst = qaff + (size_t)gid * nw;
+    G1Jac qs[MAX_NW];
+    Fp prefix[MAX_NW];
+    G1Jac q = p;
+    Fp run;
+    fe_set_one(run);
+    for (int t = 0; t < nw; t++) {
+        if (t) for (int s = 0; s < w; s++) jac_dbl(q, q);
+        qs[t] = q;
+        prefix[t] = run;          // product of z_0..z_{t-1}
+        fe_mul(run, run, q.z);
+    }
+    Fp inv;
+    fp_inv(inv, run);             // 1 / prod z_u   (all z_u != 0: P has prime order)
+    for (int t = nw - 1; t >= 0; t--) {
+        Fp zi;
+        fe_mul(zi, inv, prefix[t]);   // 1/z_t
+        fe_mul(inv, inv, qs[t].z);    // drop z_t
+        G1Affine a;
+        jac_to_affine_with_inv(a, qs[t], zi);
+        st_vec(&dst[t], a);
+    }
+}
+
+// FK20 setup, step 3 (fixed_base_msm_window.rs:69-82 precompute_points, once per window):
+// table[(j,k,t)][m] = (m+1) * Q_t for m < half, affine.  One thread per chunk of CH consecutive m.
+constexpr int TBL_CH = 16;
+__global__ void __launch_bounds__(128)
+k_fk20_table_fill(const G1Affine* __restrict__ qaff, G1Affine* __restrict__ table, int half, size_t nbases) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunks = (half + TBL_CH - 1) / TBL_CH;
+    if (gid >= nbases * chunks) return;
+    const size_t base = gid / chunks;
+    const int c = (int)(gid % chunks);
+    const G1Affine q = ld_vec(&qaff[base]);
+    // start = (c*CH + 1) * Q
+    G1Jac acc;
+    jac_set_inf(acc);
+    uint32_t mult = (uint32_t)c * TBL_CH + 1;
+    for (int bit = 31 - __clz(mult); bit >= 0; bit--) {
+        jac_dbl(acc, acc);
+        if ((mult >> bit) & 1) jac_madd(acc, q, false);
+    }
+    G1Jac buf[TBL_CH];
+    Fp prefix[TBL_CH];
+    Fp run;
+    fe_set_one(run);
+    const int cnt = min(TBL_CH, half - c * TBL_CH);
+    for (int i = 0; i < cnt; i++) {
+        if (i) jac_madd(acc, q, false);
+        buf[i] = acc;
+        prefix[i] = run;
+        fe_mul(run, run, acc.z);
+    }
+    Fp inv;
+    fp_inv(inv, run);
+    G1Affine* dst = table + base * half + (size_t)c * TBL_CH;
+    for (int i = cnt - 1; i >= 0; i--) {
+        Fp zi;
+        fe_mul(zi, inv, prefix[i]);
+        fe_mul(inv, inv, buf[i].z);
+        G1Affine a;
+        jac_to_affine_with_inv(a, buf[i], zi);
+        st_vec(&dst[i], a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers
+// ------------------------------------------------------------------------------------------------
+#define EKZG_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st) {
+    Fr b;
+    for (int i = 0; i < 8; i++) b.v[i] = base_mont[i];
+    k_powers<<<(n + 127) / 128, 128, 0, st>>>(out, b, n);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t kernels_init() {
+    cudaError_t e = cudaFuncSetAttribute(k_blob_to_coeffs_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * N_BLOB * 4);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_coeffs_to_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * N_BLOB * 4);
+}
+
+cudaError_t launch_blob_to_coeffs_cells(const uint8_t* blobs, Fr* coeffs, uint8_t* cells, uint32_t* status, const DevTables& T,
+                                        int B, bool want_cells, cudaStream_t st) {
+    k_blob_to_coeffs_cells<<<B, K1_THREADS, 8 * N_BLOB * 4, st>>>(blobs, coeffs, cells, status, T, want_cells ? 1 : 0);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_coeffs_to_cells(const Fr* coeffs, uint8_t* cells, const DevTables& T, int B, cudaStream_t st) {
+    k_coeffs_to_cells<<<B, K1_THREADS, 8 * N_BLOB * 4, st>>>(coeffs, cells, T);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st) {
+    k_toeplitz_scalars<<<dim3(B, FK20_POINTS / K2_ROWS), K2_THREADS, 0, st>>>(coeffs, scalars, T, B);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_fk20_msm(const uint32_t* scalars, G1Jac* pts, const DevTables& T, int B, cudaStream_t st) {
+    // fewer blobs per launch -> more slices per MSM so the machine still fills
+    if (B >= 512) {
+        k_fk20_msm<4><<<dim3((B + 31) / 32, FK20_MSMS), 128, 0, st>>>(scalars, pts, T, B);
+    } else {
+        k_fk20_msm<16><<<dim3((B + 7) / 8, FK20_MSMS), 128, 0, st>>>(scalars, pts, T, B);
+    }
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_g1_ntt_stage(G1Jac* pts, const DevTables& T, int B, int stage, int mode, cudaStream_t st) {
+    int n = 64 * B;
+    k_g1_ntt_stage<<<(n + 127) / 128, 128, 0, st>>>(pts, T, B, stage, mode);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_fk20_g1_ntts(G1Jac* pts, const DevTables& T, int B, cudaStream_t st) {
+    for (int s = 0; s <= 6; s++) {
+        cudaError_t e = launch_g1_ntt_stage(pts, T, B, s, 0, st);
+        if (e != cudaSuccess) return e;
+    }
+    for (int s = 6; s >= 0; s--) {
+        cudaError_t e = launch_g1_ntt_stage(pts, T, B, s, 1, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launch_g1_compress(const G1Jac* pts, uint8_t* out, int npos, int B, cudaStream_t st) {
+    int n = npos * B;
+    k_g1_compress<<<(n + 127) / 128, 128, 0, st>>>(pts, out, npos, B);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_g1_decompress(const uint8_t* in, G1Affine* out, uint32_t* status, int n, cudaStream_t st) {
+    k_g1_decompress<<<(n + 63) / 64, 64, 0, st>>>(in, out, status, n);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+cudaError_t launch_fk20_setup(const G1Affine* srs, G1Jac* pts_scratch /*128*64*/, G1Affine* qaff /*8192*nw*/, G1Affine* table,
+                              const DevTables& T, cudaStream_t st) {
+    if (T.nw > MAX_NW) return cudaErrorInvalidValue;
+    k_fk20_setup_vectors<<<(128 * 64 + 127) / 128, 128, 0, st>>>(srs, pts_scratch);
+    EKZG_LAUNCH_CHECK();
+    for (int s = 6; s >= 0; s--) {
+        cudaError_t e = launch_g1_ntt_stage(pts_scratch, T, 64, s, 1, st);
+        if (e != cudaSuccess) return e;
+    }
+    k_fk20_window_bases<<<(FK20_MSMS * FK20_POINTS + 63) / 64, 64, 0, st>>>(pts_scratch, qaff, T.w, T.nw);
+    EKZG_LAUNCH_CHECK();
+    size_t nbases = (size_t)FK20_MSMS * FK20_POINTS * T.nw;
+    int chunks = (T.half + TBL_CH - 1) / TBL_CH;
+    size_t nthreads = nbases * chunks;
+    k_fk20_table_fill<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(qaff, table, T.half, nbases);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace ekzg

@@ -1,0 +1,24 @@
+// Host-visible launch wrappers for the kernels in kzg_kernels.cu / kzg_kernels_*.cu.
+#pragma once
+#include "kzg_device.cuh"
+
+namespace ekzg {
+
+cudaError_t kernels_init();
+cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st);
+cudaError_t launch_blob_to_coeffs_cells(const uint8_t* blobs, Fr* coeffs, uint8_t* cells, uint32_t* status, const DevTables& T,
+                                        int B, bool want_cells, cudaStream_t st);
+cudaError_t launch_coeffs_to_cells(const Fr* coeffs, uint8_t* cells, const DevTables& T, int B, cudaStream_t st);
+cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st);
+cudaError_t launch_fk20_msm(const uint32_t* scalars, G1Jac* pts, const DevTables& T, int B, cudaStream_t st);
+cudaError_t launch_g1_ntt_stage(G1Jac* pts, const DevTables& T, int B, int stage, int mode, cudaStream_t st);
+cudaError_t launch_fk20_g1_ntts(G1Jac* pts, const DevTables& T, int B, cudaStream_t st);
+cudaError_t launch_g1_compress(const G1Jac* pts, uint8_t* out, int npos, int B, cudaStream_t st);
+cudaError_t launch_g1_decompress(const uint8_t* in, G1Affine* out, uint32_t* status, int n, cudaStream_t st);
+cudaError_t launch_fk20_setup(const G1Affine* srs, G1Jac* pts_scratch, G1Affine* qaff, G1Affine* table, const DevTables& T,
+                              cudaStream_t st);
+
+// number of kernel launches one compute_cells_and_kzg_proofs batch issues (for bench.py's gpu_launches)
+constexpr int FK20_LAUNCHES_PER_BATCH = 1 /*K1*/ + 1 /*K2*/ + 1 /*K4*/ + 14 /*K5*/ + 1 /*K6*/;
+
+}  // namespace ekzg

@@ -1,0 +1,275 @@
+// Host runtime of the B200 KZG backend (see kzg_runtime.h).
+#include "kzg_runtime.h"
+#include <cstdlib>
+#include <cstring>
+#include "fr_consts.cuh"
+
+// The ceremony output (crates/trusted_setup/data/trusted_setup_4096.json, repacked by
+// tools/convert_trusted_setup.py) is linked into the library, like the reference embeds its JSON
+// (crates/trusted_setup/src/lib.rs:5).
+extern "C" {
+extern const unsigned char ekzg_trusted_setup_start[];
+extern const unsigned char ekzg_trusted_setup_end[];
+}
+
+namespace ekzg {
+
+int chunk_capacity() {
+    const char* e = getenv("EKZG_CHUNK");
+    int c = e ? atoi(e) : 256;
+    if (c < 1) c = 1;
+    if (c > 4096) c = 4096;
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------------
+Status Workspace::alloc(int cap, bool with_io) {
+    capacity = cap;
+    EKZG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    EKZG_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    EKZG_CUDA(cudaMalloc(&d_coeffs, (size_t)cap * N_BLOB * sizeof(Fr)));
+    EKZG_CUDA(cudaMalloc(&d_scalars, (size_t)cap * FK20_MSMS * FK20_POINTS * 32));
+    EKZG_CUDA(cudaMalloc(&d_pts, (size_t)cap * 128 * sizeof(G1Jac)));
+    if (with_io) {
+        EKZG_CUDA(cudaMalloc(&d_blobs, (size_t)cap * BYTES_PER_BLOB));
+        EKZG_CUDA(cudaMalloc(&d_cells, (size_t)cap * N_EXT * 32));
+        EKZG_CUDA(cudaMalloc(&d_proofs, (size_t)cap * N_CELLS * BYTES_PER_G1));
+        EKZG_CUDA(cudaMalloc(&d_status, (size_t)cap * sizeof(uint32_t)));
+        EKZG_CUDA(cudaMallocHost(&h_blobs, (size_t)cap * BYTES_PER_BLOB));
+        EKZG_CUDA(cudaMallocHost(&h_cells, (size_t)cap * N_EXT * 32));
+        EKZG_CUDA(cudaMallocHost(&h_proofs, (size_t)cap * N_CELLS * BYTES_PER_G1));
+        EKZG_CUDA(cudaMallocHost(&h_status, (size_t)cap * sizeof(uint32_t)));
+    }
+    return Status::Ok();
+}
+
+void Workspace::release() {
+    cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_proofs); cudaFree(d_status);
+    cudaFreeHost(h_blobs); cudaFreeHost(h_cells); cudaFreeHost(h_proofs); cudaFreeHost(h_status);
+    if (done) cudaEventDestroy(done);
+    if (stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+Status Context::bind_device() const {
+    EKZG_CUDA(cudaSetDevice(device_));
+    return Status::Ok();
+}
+
+Status Context::create(bool use_precomp, std::unique_ptr<Context>* out) {
+    std::unique_ptr<Context> c(new Context());
+    Status s = c->init(use_precomp);
+    if (!s.ok) return s;
+    *out = std::move(c);
+    return Status::Ok();
+}
+
+Context::~Context() {
+    cudaSetDevice(device_);
+    for (Workspace* w : pool_) { w->release(); delete w; }
+    for (void* p : allocs_) cudaFree(p);
+}
+
+template <class T>
+static Status dev_alloc(std::vector<void*>& allocs, T** p, size_t count) {
+    void* q = nullptr;
+    EKZG_CUDA(cudaMalloc(&q, count * sizeof(T)));
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return Status::Ok();
+}
+#define EKZG_TRY(expr) do { ::ekzg::Status s_ = (expr); if (!s_.ok) return s_; } while (0)
+
+Status Context::init(bool use_precomp) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return Status::Error("no CUDA device: this backend has no CPU fallback");
+    if (const char* e = getenv("EKZG_DEVICE")) {
+        device_ = atoi(e);
+        EKZG_CUDA(cudaSetDevice(device_));
+    } else {
+        EKZG_CUDA(cudaGetDevice(&device_));
+    }
+    cudaDeviceProp prop;
+    EKZG_CUDA(cudaGetDeviceProperties(&prop, device_));
+    if (prop.major < 10) return Status::Error(std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
+    EKZG_CUDA(kernels_init());
+
+    int w = 8;
+    if (use_precomp) {
+        if (const char* e = getenv("EKZG_FK20_WINDOW")) w = atoi(e);
+    }
+    if (w < 4 || w > 16) return Status::Error("EKZG_FK20_WINDOW must be in [4, 16]");
+    T_.w = w;
+    T_.nw = 255 / w + 1;
+    T_.half = 1 << (w - 1);
+
+    cudaStream_t st = 0;
+    // twiddles
+    Fr *tw4096, *tw4096_inv, *tw8192, *tw8192_inv, *tw128, *tw64_inv;
+    EKZG_TRY(dev_alloc(allocs_, &tw4096, 2048));
+    EKZG_TRY(dev_alloc(allocs_, &tw4096_inv, 2048));
+    EKZG_TRY(dev_alloc(allocs_, &tw8192, 4096));
+    EKZG_TRY(dev_alloc(allocs_, &tw8192_inv, 4096));
+    EKZG_TRY(dev_alloc(allocs_, &tw128, 64));
+    EKZG_TRY(dev_alloc(allocs_, &tw64_inv, 32));
+    EKZG_CUDA(launch_powers(tw4096, fr_omega_4096().v, 2048, st));
+    EKZG_CUDA(launch_powers(tw4096_inv, fr_omega_4096_inv().v, 2048, st));
+    EKZG_CUDA(launch_powers(tw8192, fr_omega_8192().v, 4096, st));
+    EKZG_CUDA(launch_powers(tw8192_inv, fr_omega_8192_inv().v, 4096, st));
+    EKZG_CUDA(launch_powers(tw128, fr_omega_128().v, 64, st));
+    EKZG_CUDA(launch_powers(tw64_inv, fr_omega_64_inv().v, 32, st));
+    T_.tw4096 = tw4096; T_.tw4096_inv = tw4096_inv; T_.tw8192 = tw8192; T_.tw8192_inv = tw8192_inv;
+    T_.tw128 = tw128; T_.tw64_inv = tw64_inv;
+    int8_t* glv;
+    EKZG_TRY(dev_alloc(allocs_, &glv, 128 * 66));
+    EKZG_CUDA(cudaMemcpy(glv, GLV_TWIDDLE_DIGITS_HOST, 128 * 66, cudaMemcpyHostToDevice));
+    T_.glv_digits = glv;
+
+    // trusted setup
+    const unsigned char* ts = ekzg_trusted_setup_start;
+    size_t ts_len = (size_t)(ekzg_trusted_setup_end - ekzg_trusted_setup_start);
+    if (ts_len < 16 || memcmp(ts, "EKZGTS01", 8) != 0) return Status::Error("embedded trusted setup: bad magic");
+    uint32_t n_g1, n_g2;
+    memcpy(&n_g1, ts + 8, 4);
+    memcpy(&n_g2, ts + 12, 4);
+    if (n_g1 != 4096 || n_g2 != 65 || ts_len != 16 + (size_t)48 * 2 * n_g1 + (size_t)96 * n_g2)
+        return Status::Error("embedded trusted setup: unexpected size");
+    uint8_t* d_bytes = nullptr;
+    uint32_t* d_st = nullptr;
+    EKZG_CUDA(cudaMalloc(&d_bytes, (size_t)48 * 2 * n_g1));
+    EKZG_CUDA(cudaMalloc(&d_st, sizeof(uint32_t) * 2 * n_g1));
+    EKZG_CUDA(cudaMemset(d_st, 0, sizeof(uint32_t) * 2 * n_g1));
+    EKZG_CUDA(cudaMemcpy(d_bytes, ts + 16, (size_t)48 * 2 * n_g1, cudaMemcpyHostToDevice));
+    G1Affine* srs;
+    EKZG_TRY(dev_alloc(allocs_, &srs, 2 * (size_t)n_g1));
+    EKZG_CUDA(launch_g1_decompress(d_bytes, srs, d_st, 2 * n_g1, st));
+    std::vector<uint32_t> hst(2 * n_g1);
+    EKZG_CUDA(cudaMemcpy(hst.data(), d_st, sizeof(uint32_t) * 2 * n_g1, cudaMemcpyDeviceToHost));
+    cudaFree(d_bytes);
+    cudaFree(d_st);
+    for (uint32_t v : hst)
+        if (v) return Status::Error("embedded trusted setup: a G1 point failed to decompress");
+    T_.srs_g1 = srs;
+    T_.srs_g1_lagrange = srs + n_g1;
+
+    // FK20 tables
+    size_t nbases = (size_t)FK20_MSMS * FK20_POINTS * T_.nw;
+    size_t nentries = nbases * T_.half;
+    G1Affine* table;
+    EKZG_TRY(dev_alloc(allocs_, &table, nentries));
+    table_bytes_ = nentries * sizeof(G1Affine);
+    G1Jac* scratch = nullptr;
+    G1Affine* qaff = nullptr;
+    EKZG_CUDA(cudaMalloc(&scratch, (size_t)128 * 64 * sizeof(G1Jac)));
+    EKZG_CUDA(cudaMalloc(&qaff, nbases * sizeof(G1Affine)));
+    T_.fk20_table = table;
+    EKZG_CUDA(launch_fk20_setup(T_.srs_g1, scratch, qaff, table, T_, st));
+    EKZG_CUDA(cudaDeviceSynchronize());
+    cudaFree(scratch);
+    cudaFree(qaff);
+    return Status::Ok();
+}
+
+Workspace* Context::acquire(int min_capacity, bool with_io) const {
+    {
+        std::lock_guard<std::mutex> g(pool_mu_);
+        for (size_t i = 0; i < pool_.size(); i++) {
+            Workspace* w = pool_[i];
+            if (w->capacity >= min_capacity && (!with_io || w->d_blobs)) {
+                pool_.erase(pool_.begin() + i);
+                return w;
+            }
+        }
+    }
+    Workspace* w = new Workspace();
+    Status s = w->alloc(min_capacity, with_io);
+    if (!s.ok) { w->release(); delete w; return nullptr; }
+    return w;
+}
+
+void Context::give_back(Workspace* ws) const {
+    std::lock_guard<std::mutex> g(pool_mu_);
+    pool_.push_back(ws);
+}
+
+// ------------------------------------------------------------------------------------------------
+Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells*/, uint8_t* d_proofs, cudaStream_t stream) const {
+    EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, n, stream));
+    EKZG_CUDA(launch_fk20_msm(ws.d_scalars, ws.d_pts, T_, n, stream));
+    EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, T_, n, stream));
+    EKZG_CUDA(launch_g1_compress(ws.d_pts, d_proofs, N_CELLS, n, stream));
+    return Status::Ok();
+}
+
+Status Context::fk20_device(Workspace& ws, int n, const uint8_t* d_blobs, uint8_t* d_cells, uint8_t* d_proofs, uint32_t* d_status,
+                            cudaStream_t stream) const {
+    if (n > ws.capacity) return Status::Error("workspace too small");
+    EKZG_CUDA(cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n, stream));
+    EKZG_CUDA(launch_blob_to_coeffs_cells(d_blobs, ws.d_coeffs, d_cells, d_status, T_, n, d_cells != nullptr, stream));
+    if (d_proofs) EKZG_TRY(fk20_from_coeffs_device(ws, n, d_cells, d_proofs, stream));
+    return Status::Ok();
+}
+
+Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* blobs, uint8_t* cells, uint8_t* proofs,
+                                                   uint8_t* blob_status, bool want_proofs) const {
+    if (n == 0) return Status::Ok();
+    EKZG_TRY(bind_device());
+    const int cap = (int)std::min<uint64_t>(n, (uint64_t)chunk_capacity());
+    const uint64_t nchunks = (n + cap - 1) / cap;
+    Workspace* W[2] = {acquire(cap, true), nchunks > 1 ? acquire(cap, true) : nullptr};
+    if (!W[0] || (nchunks > 1 && !W[1])) {
+        for (Workspace* w : W) if (w) give_back(w);
+        return Status::Error("device/pinned memory allocation failed");
+    }
+    bool any_bad = false;
+    Status result = Status::Ok();
+    uint64_t pending_first[2] = {0, 0};
+    int pending_cnt[2] = {0, 0};
+    auto drain = [&](int slot) -> Status {
+        Workspace& ws = *W[slot];
+        if (!pending_cnt[slot]) return Status::Ok();
+        EKZG_CUDA(cudaEventSynchronize(ws.done));
+        const uint64_t first = pending_first[slot];
+        const int cnt = pending_cnt[slot];
+        if (cells) memcpy(cells + first * (N_EXT * 32), ws.h_cells, (size_t)cnt * N_EXT * 32);
+        if (want_proofs) memcpy(proofs + first * (N_CELLS * BYTES_PER_G1), ws.h_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1);
+        for (int i = 0; i < cnt; i++) {
+            if (ws.h_status[i]) any_bad = true;
+            if (blob_status) blob_status[first + i] = ws.h_status[i] ? 1 : 0;
+        }
+        pending_cnt[slot] = 0;
+        return Status::Ok();
+    };
+    for (uint64_t c = 0; c < nchunks && result.ok; c++) {
+        const int slot = (int)(c & 1);
+        Workspace& ws = *W[slot];
+        result = drain(slot);
+        if (!result.ok) break;
+        const uint64_t first = c * cap;
+        const int cnt = (int)std::min<uint64_t>(cap, n - first);
+        memcpy(ws.h_blobs, blobs + first * BYTES_PER_BLOB, (size_t)cnt * BYTES_PER_BLOB);
+        cudaError_t e = cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)cnt * BYTES_PER_BLOB, cudaMemcpyHostToDevice, ws.stream);
+        if (e != cudaSuccess) { result = Status::Error(cudaGetErrorString(e)); break; }
+        result = fk20_device(ws, cnt, ws.d_blobs, cells ? ws.d_cells : nullptr, want_proofs ? ws.d_proofs : nullptr, ws.d_status, ws.stream);
+        if (!result.ok) break;
+        if (cells) cudaMemcpyAsync(ws.h_cells, ws.d_cells, (size_t)cnt * N_EXT * 32, cudaMemcpyDeviceToHost, ws.stream);
+        if (want_proofs) cudaMemcpyAsync(ws.h_proofs, ws.d_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1, cudaMemcpyDeviceToHost, ws.stream);
+        cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ws.stream);
+        e = cudaEventRecord(ws.done, ws.stream);
+        if (e != cudaSuccess) { result = Status::Error(cudaGetErrorString(e)); break; }
+        pending_first[slot] = first;
+        pending_cnt[slot] = cnt;
+    }
+    for (int slot = 0; slot < 2; slot++) {
+        if (!W[slot]) continue;
+        if (result.ok) result = drain(slot);
+        else cudaStreamSynchronize(W[slot]->stream);
+        give_back(W[slot]);
+    }
+    if (!result.ok) return result;
+    if (any_bad) return Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus");
+    return Status::Ok();
+}
+
+}  // namespace ekzg

@@ -1,0 +1,89 @@
+// Host runtime: context (per-device tables), workspaces (per-call device + pinned staging buffers),
+// and the batch pipeline that replaces the reference's maybe_rayon fan-out (crates/maybe_rayon) with
+// a GPU batch scheduler: many blobs per kernel launch, copies overlapped with compute on two streams.
+#pragma once
+#include <cuda_runtime.h>
+#include <condition_variable>
+#include <cstdint>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "kzg_kernels.h"
+
+namespace ekzg {
+
+struct Status {
+    bool ok = true;
+    std::string msg;
+    static Status Ok() { return Status(); }
+    static Status Error(const std::string& m) { Status s; s.ok = false; s.msg = m; return s; }
+};
+
+#define EKZG_CUDA(expr)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t e_ = (expr);                                                                                \
+        if (e_ != cudaSuccess) return ::ekzg::Status::Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
+    } while (0)
+
+// Device + pinned buffers for one in-flight chunk of up to `capacity` blobs.
+struct Workspace {
+    int capacity = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    // device
+    uint8_t* d_blobs = nullptr;
+    Fr* d_coeffs = nullptr;
+    uint8_t* d_cells = nullptr;
+    uint32_t* d_scalars = nullptr;
+    G1Jac* d_pts = nullptr;
+    uint8_t* d_proofs = nullptr;
+    uint32_t* d_status = nullptr;
+    // pinned host staging (the ABI hands us scattered caller buffers)
+    uint8_t* h_blobs = nullptr;
+    uint8_t* h_cells = nullptr;
+    uint8_t* h_proofs = nullptr;
+    uint32_t* h_status = nullptr;
+    Status alloc(int cap, bool with_io);
+    void release();
+};
+
+class Context {
+public:
+    static Status create(bool use_precomp, std::unique_ptr<Context>* out);
+    ~Context();
+
+    int device() const { return device_; }
+    const DevTables& tables() const { return T_; }
+    uint64_t table_bytes() const { return table_bytes_; }
+
+    // Everything on device, asynchronous on `stream`; scratch comes from `ws` (capacity >= n).
+    Status fk20_device(Workspace& ws, int n, const uint8_t* d_blobs, uint8_t* d_cells, uint8_t* d_proofs, uint32_t* d_status,
+                       cudaStream_t stream) const;
+    // same, starting from coefficients already in ws.d_coeffs (recovery path)
+    Status fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* d_cells, uint8_t* d_proofs, cudaStream_t stream) const;
+
+    // Host buffers, contiguous; chunks the batch through two workspaces.
+    Status compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* blobs, uint8_t* cells, uint8_t* proofs,
+                                              uint8_t* blob_status, bool want_proofs) const;
+
+    // workspace pool (calls are re-entrant: concurrent callers each borrow their own workspaces)
+    Workspace* acquire(int min_capacity, bool with_io) const;
+    void give_back(Workspace* ws) const;
+
+    Status bind_device() const;
+
+private:
+    Context() = default;
+    Status init(bool use_precomp);
+    int device_ = 0;
+    DevTables T_{};
+    std::vector<void*> allocs_;
+    uint64_t table_bytes_ = 0;
+    mutable std::mutex pool_mu_;
+    mutable std::vector<Workspace*> pool_;
+};
+
+int chunk_capacity();
+
+}  // namespace ekzg

@@ -1,0 +1,114 @@
+"""GPU parity tests of the hot path (compute_cells_and_kzg_proofs) through the C ABI, against
+(1) the reference's consensus vectors (tests/golden, from test_vectors/compute_cells_and_kzg_proofs),
+(2) the CPU oracle on seeded synthetic + edge blobs, stage by stage and end to end,
+(3) size-independent properties at the full batch size of BASELINE.json config #3.
+Bit-exact everywhere: this is integer arithmetic."""
+import hashlib
+
+import pytest
+
+from tests import vectors
+
+pytestmark = pytest.mark.gpu
+
+R = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def _synth(pkg):
+    import importlib
+    return importlib.import_module("eth_kzg_b200.synthetic")
+
+
+def test_fk20_stages_match_oracle(das_ctx, pkg):
+    """scalars (Toeplitz NTT), MSM outputs and h commitments of one blob vs the oracle's intermediates.
+    The device folds the 1/128 of the inverse G1 NTT into the scalars, so scalars and MSM outputs are
+    compared after scaling the oracle's by 128^-1."""
+    from oracle import cref
+    blob = _synth(pkg).blob(7)
+    sc, msm, h = das_ctx.debug_fk20_stages(blob)
+    osc, omsm, oh = cref.fk20_stages(blob)
+    inv128 = pow(128, -1, R)
+    bad = [(j, k) for j in range(128) for k in range(64) if sc[j][k] != osc[j][k] * inv128 % R]
+    assert not bad, "scalar mismatches (first 5): %r" % bad[:5]
+    badm = [j for j in range(128) if msm[j] != cref.g1_mul(omsm[j], inv128)]
+    assert not badm, "MSM mismatches at j = %r" % badm[:10]
+    badh = [i for i in range(64) if h[i] != oh[i]]
+    assert not badh, "h mismatches at i = %r" % badh[:10]
+
+
+@pytest.mark.parametrize("name,inp,expected", [pytest.param(n, i, o, id=n) for n, i, o in vectors.load("compute_cells_and_kzg_proofs")])
+def test_consensus_vectors(das_ctx, pkg, name, inp, expected):
+    """crates/eip7594/tests/compute_cells_and_kzg_proofs.rs: byte-exact cells+proofs, `output: null` <=> Err"""
+    try:
+        cells, proofs = das_ctx.compute_cells_and_kzg_proofs(inp["blob"])
+        got = [cells, proofs]
+    except pkg.KzgError:
+        got = None
+    if expected is not None:
+        expected = [list(expected[0]), list(expected[1])]
+    assert got == expected
+
+
+@pytest.mark.parametrize("name,inp,expected", [pytest.param(n, i, o, id=n) for n, i, o in vectors.load("compute_cells_and_kzg_proofs")])
+def test_consensus_vectors_compute_cells(das_ctx, pkg, name, inp, expected):
+    try:
+        got = das_ctx.compute_cells(inp["blob"])
+    except pkg.KzgError:
+        got = None
+    assert got == (list(expected[0]) if expected is not None else None)
+
+
+def test_batch_matches_oracle(das_ctx, pkg):
+    """ragged batch (not a multiple of the warp or chunk size) of synthetic + edge blobs vs the oracle"""
+    from oracle import cref
+    syn = _synth(pkg)
+    blobs = syn.edge_blobs() + [syn.blob(i) for i in range(33)]
+    n = len(blobs)
+    cells, proofs, status = das_ctx.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n)
+    assert status == [0] * n
+    ocells, oproofs = cref.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n)
+    for i in range(n):
+        assert cells[i * 262144:(i + 1) * 262144] == ocells[i * 262144:(i + 1) * 262144], "cells of blob %d" % i
+        assert proofs[i * 6144:(i + 1) * 6144] == oproofs[i * 6144:(i + 1) * 6144], "proofs of blob %d" % i
+    # the constant blob: every proof is the identity
+    assert proofs[2 * 6144:3 * 6144] == (b"\xc0" + bytes(47)) * 128
+
+
+def test_batch_invalid_blob_is_isolated(das_ctx, pkg):
+    """one non-canonical element poisons only its own blob; the call reports Err like the reference"""
+    syn = _synth(pkg)
+    good = syn.blob(1)
+    bad = bytearray(syn.blob(2))
+    bad[32 * 100:32 * 101] = R.to_bytes(32, "big")
+    cells, proofs, status = das_ctx.compute_cells_and_kzg_proofs_batch(good + bytes(bad) + good, 3)
+    assert status == [0, 1, 0]
+    assert cells[:262144] == cells[2 * 262144:] and proofs[:6144] == proofs[2 * 6144:]
+    c1, p1 = das_ctx.compute_cells_and_kzg_proofs(good)
+    assert b"".join(c1) == cells[:262144] and b"".join(p1) == proofs[:6144]
+    with pytest.raises(pkg.KzgError):
+        das_ctx.compute_cells_and_kzg_proofs(bytes(bad))
+
+
+def test_full_size_batch_properties(das_ctx, pkg):
+    """BASELINE config #3 size (1024 blobs): properties that need no oracle run --
+    cells 0..63 reproduce the blob; the batch is a permutation-equivariant map (blob order does not
+    matter); results equal the single-blob ABI on sampled blobs; checksum is stable across chunkings."""
+    syn = _synth(pkg)
+    n = 1024
+    base = [syn.blob(i) for i in range(64)]
+    blobs = [base[(i * 37) % 64] for i in range(n)]
+    cells, proofs, status = das_ctx.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n)
+    assert status == [0] * n
+    first = {}
+    for i in range(n):
+        c = cells[i * 262144:(i + 1) * 262144]
+        p = proofs[i * 6144:(i + 1) * 6144]
+        assert c[:131072] == blobs[i]
+        key = (i * 37) % 64
+        if key in first:
+            assert first[key] == (hashlib.sha256(c).digest(), p), "blob %d differs from its duplicate" % i
+        else:
+            first[key] = (hashlib.sha256(c).digest(), p)
+    for key in (0, 17, 63):
+        c1, p1 = das_ctx.compute_cells_and_kzg_proofs(base[key])
+        assert first[key] == (hashlib.sha256(b"".join(c1)).digest(), b"".join(p1))
