@@ -1,0 +1,289 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: compute_cells_and_kzg_proofs, blobs/s (BASELINE.json metric, config #3).
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port on the box's host cores
+
+A step = one pass of the hot path over one batch of 1024 synthetic blobs PER GPU (weak scaling: blobs are
+independent, every rank works on its own shard, no data-path collective -- SURVEY.md §8e).
+  value  : blobs/s with the batch already resident in HBM (device-pointer entry point), CUDA-event timed,
+           max over ranks.
+  e2e    : blobs/s through the public host-buffer C-ABI call (eth_kzg_b200_compute_cells_and_kzg_proofs_batch):
+           pinned host input -> H2D -> kernels -> D2H -> host output, all inside the timed region.
+  roofline / roofline_imad / stages: per-stage device times measured live with CUDA events on the launching stream.
+Prints ONE JSON line on rank 0."""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOBS_PER_GPU = 1024
+BYTES_PER_BLOB = 131072
+CELLS_BYTES = 128 * 2048
+PROOFS_BYTES = 128 * 48
+METRIC = "blobs/sec compute_cells_and_kzg_proofs"
+
+# Work model of OUR algorithm per blob, used for the integer-issue roofline:
+#   K4: 128*64 scalars * nw windows table additions, XYZZ mixed add = 10 Fp mul
+#   K5: 642 scalar multiplications by 128th roots of unity (GLV, 132 dbl*7 + ~66 add*16 + table 76 + endo) + 1664 point adds
+FP_MUL_IMAD = 300          # IMAD.WIDE(.X) instructions per 12-limb Montgomery multiplication (12*(2*12+1))
+IMAD_WIDE_PEAK = 9.13e12   # measured on this pool's B200 by tools/gpu_probe.cu (carry-chained IMAD.WIDE, all SMs)
+
+
+def synth_blobs(n, first=0):
+    import __graft_entry__
+    __graft_entry__.load_package()
+    import importlib
+    syn = importlib.import_module("eth_kzg_b200.synthetic")
+    return syn.blobs(n, first)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(sample_blobs, threads=0):
+    """the oracle port (oracle/src/kzg.c, the reference's algorithm restated in C + OpenMP) on the host cores"""
+    from oracle import cref
+    cref.build()
+    nthreads = threads or cref.num_threads()
+    blobs = synth_blobs(sample_blobs)
+    cref.compute_cells_and_kzg_proofs_batch(blobs[:BYTES_PER_BLOB * min(2, sample_blobs)], min(2, sample_blobs), nthreads)  # builds tables
+    t0 = time.perf_counter()
+    cref.compute_cells_and_kzg_proofs_batch(blobs, sample_blobs, nthreads)
+    dt = time.perf_counter() - t0
+    return {"value": sample_blobs / dt, "unit": "blobs/s", "cores": nthreads, "kind": "port",
+            "sample": "%d synthetic blobs of the same generator, one blob per OpenMP thread, %.1f s" % (sample_blobs, dt)}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import cref
+    cref.build()
+    cores = cref.num_threads()
+    sample = max(cores, 8) * 2          # blobs per step: bounded sample of the 1024-blob workload
+    blobs = synth_blobs(sample)
+    cref.compute_cells_and_kzg_proofs_batch(blobs[:BYTES_PER_BLOB], 1, cores)
+    for _ in range(args.warmup):
+        cref.compute_cells_and_kzg_proofs_batch(blobs, sample, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cref.compute_cells_and_kzg_proofs_batch(blobs, sample, cores)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "blobs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 limbs (Fp 6x64, Fr 4x64 Montgomery)", "data": "synthetic",
+            "config": {"workload": "compute_cells_and_kzg_proofs, bounded sample of %d of the 1024 synthetic blobs per step" % sample,
+                       "note": "reference's Rust/blst build is not compilable here (no cargo); this is the C restatement of the same algorithm (oracle/)"},
+            "cpu_baseline": {"value": v, "unit": "blobs/s", "cores": cores, "kind": "port", "sample": "%d blobs x %d steps" % (sample, args.steps)},
+            "e2e": {"value": v, "unit": "blobs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blobs", type=int, default=BLOBS_PER_GPU, help="blobs per GPU per step")
+    ap.add_argument("--precomp", type=int, default=1, help="use_precomp flag of the context (window from EKZG_FK20_WINDOW)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import __graft_entry__
+    pkg = __graft_entry__.load_package()
+    ctx = pkg.DASContext(use_precomp=bool(args.precomp))
+    n = args.blobs
+    # this rank's shard of the job: independent blobs, different on every rank
+    host_blobs = synth_blobs(n, first=rank * n)
+    h_in = torch.frombuffer(bytearray(host_blobs), dtype=torch.uint8).pin_memory()
+    d_in = h_in.cuda()
+    d_cells = torch.empty(n * CELLS_BYTES, dtype=torch.uint8, device="cuda")
+    d_proofs = torch.empty(n * PROOFS_BYTES, dtype=torch.uint8, device="cuda")
+    d_status = torch.zeros(n, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def device_step():
+        ctx.compute_cells_and_kzg_proofs_device(n, d_in.data_ptr(), d_cells.data_ptr(), d_proofs.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    assert int(d_status.sum().item()) == 0
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.set_profiling(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    e1.record(stream)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    nb, stage_ms = ctx.collect_stage_times()
+    ctx.set_profiling(False)
+
+    # end to end through the host-buffer ABI call: pinned input, H2D + kernels + D2H inside the timed region
+    lib = pkg.load_library()
+    h_cells = torch.empty(n * CELLS_BYTES, dtype=torch.uint8).pin_memory()
+    h_proofs = torch.empty(n * PROOFS_BYTES, dtype=torch.uint8).pin_memory()
+    h_status = torch.zeros(n, dtype=torch.uint8).pin_memory()
+
+    def e2e_step():
+        res = lib.eth_kzg_b200_compute_cells_and_kzg_proofs_batch(ctypes.c_void_p(ctx.handle), ctypes.c_uint64(n), ctypes.c_void_p(h_in.data_ptr()),
+                                                                  ctypes.c_void_p(h_cells.data_ptr()), ctypes.c_void_p(h_proofs.data_ptr()),
+                                                                  ctypes.c_void_p(h_status.data_ptr()))
+        assert res.status == 0
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000
+    clocks = sampler.stop() if rank == 0 else None
+    # parity spot check inside the bench: device-resident and host paths agree
+    assert torch.equal(h_proofs.cuda(), d_proofs) and torch.equal(h_cells.cuda(), d_cells), "device and host paths disagree"
+
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_blobs = n * world * args.steps
+    value = total_blobs / (dev_ms / 1000)
+    e2e = total_blobs / (e2e_ms / 1000)
+    w, nw = ctx.window, 255 // ctx.window + 1
+    names = ["K1_blob_to_coeffs_cells", "K2_toeplitz_scalars", "K4_fk20_msm", "K5_g1_ntt", "K6_compress"]
+    stages = {nm: ms / max(nb, 1) for nm, ms in zip(names, stage_ms)}
+    tot = sum(stages.values()) or 1.0
+    # dominant kernel = K4 (one launch per batch).  HBM view: table gathers + scalar reads + point writes.
+    msm_ms = stages["K4_fk20_msm"]
+    msm_bytes = n * (128 * 64 * nw * 96 + 128 * 64 * 32 + 128 * 144)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = msm_bytes / (msm_ms / 1000) / 1e9 if msm_ms else 0.0
+    msm_mul = n * 128 * 64 * nw * 10
+    ntt_mul = n * (642 * (132 * 7 + 66 * 16 + 76 + 33) + 1664 * 16)
+    roofline = {"bound": "hbm", "kernel": "k_fk20_msm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "note": "table gathers are L2/HBM-trivial; the kernel is integer-issue bound, see roofline_imad"}
+    roofline_imad = {
+        "bound": "imad", "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE/s", "peak_source": "tools/gpu_probe.cu carry-chain microbenchmark on this pool",
+        "k_fk20_msm": {"fp_mul_per_launch": msm_mul, "achieved": msm_mul * FP_MUL_IMAD / (msm_ms / 1000) / 1e12 if msm_ms else 0.0},
+        "k_g1_ntt_stage(x14)": {"fp_mul_per_batch": ntt_mul, "achieved": ntt_mul * FP_MUL_IMAD / (stages["K5_g1_ntt"] / 1000) / 1e12 if stages["K5_g1_ntt"] else 0.0},
+    }
+    for k in ("k_fk20_msm", "k_g1_ntt_stage(x14)"):
+        roofline_imad[k]["frac"] = roofline_imad[k]["achieved"] * 1e12 / IMAD_WIDE_PEAK
+    line = {
+        "metric": METRIC, "value": value, "unit": "blobs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 limbs (Fp 12x32, Fr 8x32 Montgomery, IMAD.WIDE carry chains)", "data": "synthetic",
+        "config": {"workload": "compute_cells_and_kzg_proofs, batch of %d synthetic blobs per GPU (BASELINE config #3), mainnet trusted setup" % n,
+                   "blobs_per_gpu_per_step": n, "fk20_window_bits": w, "fk20_table_gib": ctx.table_bytes / 2**30,
+                   "l2": "inputs (%.0f MB) + tables exceed the 126 MB L2; no explicit flush" % (n * BYTES_PER_BLOB / 1e6),
+                   "sharding": "independent blobs per rank, tables replicated, no collective"},
+        "e2e": {"value": e2e, "unit": "blobs/s", "h2d_bytes_per_step": n * BYTES_PER_BLOB, "d2h_bytes_per_step": n * (CELLS_BYTES + PROOFS_BYTES + 4),
+                "ms_per_step": e2e_ms / args.steps, "api": "eth_kzg_b200_compute_cells_and_kzg_proofs_batch (host buffers)"},
+        "gpu_launches": args.steps * lib.eth_kzg_b200_launches_per_batch(),
+        "clocks": clocks, "roofline": roofline, "roofline_imad": roofline_imad,
+        "stages_ms_per_step": stages, "stage_share": {k: v / tot for k, v in stages.items()},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            line["cpu_baseline"] = cpu_baseline(int(os.environ.get("EKZG_CPU_SAMPLE", "0")) or max((os.cpu_count() or 8), 8) * 2)
+        except Exception as ex:  # the checker failing must not hide the GPU number
+            line["cpu_baseline"] = {"value": None, "unit": "blobs/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

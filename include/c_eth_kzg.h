@@ -124,6 +124,19 @@ uint64_t eth_kzg_b200_context_table_bytes(const DASContext *ctx);
 /* kernel launches issued by one device batch call (for launch accounting in benchmarks) */
 int eth_kzg_b200_launches_per_batch(void);
 
+
+/* Per-stage device timing of the FK20 pipeline (CUDA events on the launching stream), for benchmarks.
+ * Stages: 0 blob->coefficients/cells, 1 Toeplitz scalars, 2 fixed-base MSMs, 3 G1 NTTs, 4 compress.
+ * collect() adds the elapsed milliseconds of all finished batches to ms_out[5] and returns their count.
+ * Single-threaded use only. */
+void eth_kzg_b200_set_profiling(const DASContext *ctx, bool on);
+int eth_kzg_b200_collect_stage_times(const DASContext *ctx, double *ms_out);
+
+/* Test hook: FK20 intermediates of one blob (plain scalars [128][64][8 x u32 LE], 128 compressed MSM
+ * outputs in natural order, 64 compressed h commitments).  Synchronous. */
+CResult eth_kzg_b200_debug_fk20_stages(const DASContext *ctx, const uint8_t *blob, uint32_t *out_scalars, uint8_t *out_msm,
+                                       uint8_t *out_h);
+
 #ifdef __cplusplus
 }
 #endif

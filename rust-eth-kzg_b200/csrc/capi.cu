@@ -103,6 +103,12 @@ int eth_kzg_b200_context_window(const DASContext* ctx) { return cx(ctx).tables()
 uint64_t eth_kzg_b200_context_table_bytes(const DASContext* ctx) { return cx(ctx).table_bytes(); }
 int eth_kzg_b200_launches_per_batch(void) { return ekzg::FK20_LAUNCHES_PER_BATCH + 1 /* status memset */; }
 
+void eth_kzg_b200_set_profiling(const DASContext* ctx, bool on) { cx(ctx).set_profiling(on); }
+int eth_kzg_b200_collect_stage_times(const DASContext* ctx, double* ms_out) {
+    for (int i = 0; i < ekzg::Context::N_STAGES; i++) ms_out[i] = 0;
+    return cx(ctx).collect_stage_times(ms_out);
+}
+
 // Stage dump of one blob for kernel-level parity tests: plain scalars [128][64][8 x u32 LE],
 // MSM outputs (natural j order) and h commitments as compressed points.  Synchronous; test hook.
 CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blob, uint32_t* out_scalars, uint8_t* out_msm, uint8_t* out_h) {

@@ -194,11 +194,39 @@ void Context::give_back(Workspace* ws) const {
 }
 
 // ------------------------------------------------------------------------------------------------
+void Context::set_profiling(bool on) const {
+    profiling_ = on;
+    if (!on) {
+        for (auto& v : prof_events_) for (cudaEvent_t e : v) cudaEventDestroy(e);
+        prof_events_.clear();
+    }
+}
+
+int Context::collect_stage_times(double* ms) const {
+    int n = 0;
+    for (auto& v : prof_events_) {
+        if (cudaEventSynchronize(v.back()) != cudaSuccess) continue;
+        for (int s = 0; s < N_STAGES; s++) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, v[s], v[s + 1]) == cudaSuccess) ms[s] += t;
+        }
+        n++;
+        for (cudaEvent_t e : v) cudaEventDestroy(e);
+    }
+    prof_events_.clear();
+    return n;
+}
+
 Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells*/, uint8_t* d_proofs, cudaStream_t stream) const {
+    std::vector<cudaEvent_t>* ev = (profiling_ && !prof_events_.empty()) ? &prof_events_.back() : nullptr;
     EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, n, stream));
+    if (ev) cudaEventRecord((*ev)[2], stream);
     EKZG_CUDA(launch_fk20_msm(ws.d_scalars, ws.d_pts, T_, n, stream));
+    if (ev) cudaEventRecord((*ev)[3], stream);
     EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, T_, n, stream));
+    if (ev) cudaEventRecord((*ev)[4], stream);
     EKZG_CUDA(launch_g1_compress(ws.d_pts, d_proofs, N_CELLS, n, stream));
+    if (ev) cudaEventRecord((*ev)[5], stream);
     return Status::Ok();
 }
 
@@ -206,7 +234,14 @@ Status Context::fk20_device(Workspace& ws, int n, const uint8_t* d_blobs, uint8_
                             cudaStream_t stream) const {
     if (n > ws.capacity) return Status::Error("workspace too small");
     EKZG_CUDA(cudaMemsetAsync(d_status, 0, sizeof(uint32_t) * n, stream));
+    if (profiling_ && d_proofs) {
+        std::vector<cudaEvent_t> v(N_STAGES + 1);
+        for (auto& e : v) EKZG_CUDA(cudaEventCreate(&e));
+        prof_events_.push_back(v);
+        cudaEventRecord(v[0], stream);
+    }
     EKZG_CUDA(launch_blob_to_coeffs_cells(d_blobs, ws.d_coeffs, d_cells, d_status, T_, n, d_cells != nullptr, stream));
+    if (profiling_ && d_proofs) cudaEventRecord(prof_events_.back()[1], stream);
     if (d_proofs) EKZG_TRY(fk20_from_coeffs_device(ws, n, d_cells, d_proofs, stream));
     return Status::Ok();
 }

@@ -73,6 +73,14 @@ public:
 
     Status bind_device() const;
 
+    // Optional per-stage timing of fk20_device with CUDA events on the launching stream (bench.py's
+    // live roofline figures).  Stages: 0 K1 blob->coeffs/cells, 1 K2 toeplitz scalars, 2 K4 MSM,
+    // 3 K5 G1 NTTs, 4 K6 compress.  Not thread-safe: enable only from a single-threaded benchmark.
+    static constexpr int N_STAGES = 5;
+    void set_profiling(bool on) const;
+    // accumulates finished batches into ms[N_STAGES], returns the number of batches accumulated
+    int collect_stage_times(double* ms) const;
+
 private:
     Context() = default;
     Status init(bool use_precomp);
@@ -80,6 +88,8 @@ private:
     DevTables T_{};
     std::vector<void*> allocs_;
     uint64_t table_bytes_ = 0;
+    mutable bool profiling_ = false;
+    mutable std::vector<std::vector<cudaEvent_t>> prof_events_;  // one vector of N_STAGES+1 events per batch
     mutable std::mutex pool_mu_;
     mutable std::vector<Workspace*> pool_;
 };

@@ -231,6 +231,15 @@ class DASContext:
         _check(self._lib, self._lib.eth_kzg_b200_compute_cells_and_kzg_proofs_device(
             C.c_void_p(self._ctx), C.c_uint64(n), C.c_void_p(d_blobs), C.c_void_p(d_cells), C.c_void_p(d_proofs), C.c_void_p(d_status), C.c_void_p(stream)))
 
+    def set_profiling(self, on):
+        self._lib.eth_kzg_b200_set_profiling(C.c_void_p(self._ctx), C.c_bool(bool(on)))
+
+    def collect_stage_times(self):
+        """-> (batches, [ms per stage: K1 coeffs/cells, K2 scalars, K4 MSM, K5 G1 NTT, K6 compress])"""
+        ms = (C.c_double * 5)()
+        n = self._lib.eth_kzg_b200_collect_stage_times(C.c_void_p(self._ctx), ms)
+        return n, list(ms)
+
     def debug_fk20_stages(self, blob):
         sc = (C.c_uint32 * (128 * 64 * 8))()
         msm = C.create_string_buffer(128 * 48)

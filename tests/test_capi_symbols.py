@@ -1,0 +1,58 @@
+"""CPU-side boundary checks: the C-ABI library loads without a GPU and exports every symbol
+include/c_eth_kzg.h declares (no compute calls here); context creation fails loudly without a device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib(pkg):
+    path = pkg.library_path()
+    if not os.path.exists(path):
+        pkg.build_library()
+    return ctypes.CDLL(path)
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "c_eth_kzg.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(eth_kzg_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported(lib):
+    syms = _declared_symbols()
+    # the 13 functions + 3 constants of bindings/c/src/lib.rs:79-569 must all be there
+    reference = ["eth_kzg_das_context_new", "eth_kzg_das_context_free", "eth_kzg_free_error_message", "eth_kzg_blob_to_kzg_commitment",
+                 "eth_kzg_compute_cells_and_kzg_proofs", "eth_kzg_compute_cells", "eth_kzg_verify_cell_kzg_proof_batch",
+                 "eth_kzg_recover_cells_and_proofs", "eth_kzg_compute_kzg_proof", "eth_kzg_compute_blob_kzg_proof", "eth_kzg_verify_kzg_proof",
+                 "eth_kzg_verify_blob_kzg_proof", "eth_kzg_verify_blob_kzg_proof_batch", "eth_kzg_constant_bytes_per_cell",
+                 "eth_kzg_constant_bytes_per_proof", "eth_kzg_constant_cells_per_ext_blob"]
+    assert set(reference) <= set(syms)
+    for s in syms:
+        assert hasattr(lib, s), "missing export: " + s
+
+
+def test_constants(lib):
+    for name, v in (("eth_kzg_constant_bytes_per_cell", 2048), ("eth_kzg_constant_bytes_per_proof", 48), ("eth_kzg_constant_cells_per_ext_blob", 128)):
+        f = getattr(lib, name)
+        f.restype = ctypes.c_uint64
+        assert f() == v
+
+
+def test_null_safe_frees(lib):
+    lib.eth_kzg_das_context_free.argtypes = [ctypes.c_void_p]
+    lib.eth_kzg_free_error_message.argtypes = [ctypes.c_void_p]
+    lib.eth_kzg_das_context_free(None)      # bindings/c/src/lib.rs:109 null-safe
+    lib.eth_kzg_free_error_message(None)    # bindings/c/src/lib.rs:171 null-safe
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.KzgError):
+        pkg.DASContext()
