@@ -117,6 +117,14 @@ CResult eth_kzg_b200_compute_cells_and_kzg_proofs_batch(const DASContext *ctx, u
 CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext *ctx, uint64_t n, const void *d_blobs,
                                                          void *d_cells, void *d_proofs, void *d_status, void *cuda_stream);
 
+/* Batch forms of eth_kzg_blob_to_kzg_commitment / eth_kzg_compute_blob_kzg_proof (BASELINE.json config #2):
+ * contiguous HOST buffers, n*131072 B of blobs (and n*48 B of commitments) in, n*48 B out.  item_status[i]
+ * (optional): 0 ok, 1 invalid blob, 2 invalid commitment.  Err iff any item is invalid. */
+CResult eth_kzg_b200_blob_to_kzg_commitment_batch(const DASContext *ctx, uint64_t n, const uint8_t *blobs, uint8_t *out,
+                                                  uint8_t *item_status);
+CResult eth_kzg_b200_compute_blob_kzg_proof_batch(const DASContext *ctx, uint64_t n, const uint8_t *blobs,
+                                                  const uint8_t *commitments, uint8_t *out_proofs, uint8_t *item_status);
+
 /* CUDA device ordinal the context lives on, fixed-base window width, and bytes of HBM its tables occupy. */
 int eth_kzg_b200_context_device(const DASContext *ctx);
 int eth_kzg_b200_context_window(const DASContext *ctx);

@@ -99,7 +99,7 @@ CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext* ctx, 
 }
 
 int eth_kzg_b200_context_device(const DASContext* ctx) { return cx(ctx).device(); }
-int eth_kzg_b200_context_window(const DASContext* ctx) { return cx(ctx).tables().w; }
+int eth_kzg_b200_context_window(const DASContext* ctx) { return cx(ctx).tables().fk20.w; }
 uint64_t eth_kzg_b200_context_table_bytes(const DASContext* ctx) { return cx(ctx).table_bytes(); }
 int eth_kzg_b200_launches_per_batch(void) { return ekzg::FK20_LAUNCHES_PER_BATCH + 1 /* status memset */; }
 
@@ -126,7 +126,7 @@ CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blo
     if (launch_blob_to_coeffs_cells(ws->d_blobs, ws->d_coeffs, ws->d_cells, ws->d_status, T, 1, true, st) != cudaSuccess) return fail("k1");
     if (launch_toeplitz_scalars(ws->d_coeffs, ws->d_scalars, T, 1, st) != cudaSuccess) return fail("k2");
     if (cudaMemcpyAsync(out_scalars, ws->d_scalars, 128 * 64 * 32, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("d2h scalars");
-    if (launch_fk20_msm(ws->d_scalars, ws->d_pts, T, 1, st) != cudaSuccess) return fail("k4");
+    if (launch_fixed_msm(ws->d_scalars, ws->d_pts, T.fk20, FK20_MSMS, 1, st) != cudaSuccess) return fail("k4");
     // MSM outputs sit at bit-reversed positions; compress all 128 then un-permute on the host
     if (launch_g1_compress(ws->d_pts, ws->d_proofs, 128, 1, st) != cudaSuccess) return fail("k6");
     uint8_t tmp[128 * 48];
@@ -149,13 +149,26 @@ CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blo
 // ---- not built yet in this round: fail loudly, never fall back to a CPU path ----
 static CResult not_yet(const char* what) { return c_err(std::string(what) + ": not implemented in this build of c_eth_kzg_b200"); }
 
-CResult eth_kzg_blob_to_kzg_commitment(const DASContext* ctx, const uint8_t*, uint8_t*) { cx(ctx); return not_yet("blob_to_kzg_commitment"); }
+CResult eth_kzg_blob_to_kzg_commitment(const DASContext* ctx, const uint8_t* blob, uint8_t* out) {
+    return to_c(cx(ctx).blob_to_kzg_commitment_batch(1, blob, out, nullptr));
+}
+CResult eth_kzg_compute_kzg_proof(const DASContext* ctx, const uint8_t* blob, const uint8_t* z, uint8_t* out_proof, uint8_t* out_y) {
+    return to_c(cx(ctx).compute_kzg_proof_batch(1, blob, z, out_proof, out_y, nullptr));
+}
+CResult eth_kzg_compute_blob_kzg_proof(const DASContext* ctx, const uint8_t* blob, const uint8_t* commitment, uint8_t* out_proof) {
+    return to_c(cx(ctx).compute_blob_kzg_proof_batch(1, blob, commitment, out_proof, nullptr));
+}
+CResult eth_kzg_b200_blob_to_kzg_commitment_batch(const DASContext* ctx, uint64_t n, const uint8_t* blobs, uint8_t* out, uint8_t* item_status) {
+    return to_c(cx(ctx).blob_to_kzg_commitment_batch(n, blobs, out, item_status));
+}
+CResult eth_kzg_b200_compute_blob_kzg_proof_batch(const DASContext* ctx, uint64_t n, const uint8_t* blobs, const uint8_t* commitments,
+                                                  uint8_t* out_proofs, uint8_t* item_status) {
+    return to_c(cx(ctx).compute_blob_kzg_proof_batch(n, blobs, commitments, out_proofs, item_status));
+}
 CResult eth_kzg_verify_cell_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint64_t*, uint64_t,
                                             const uint8_t* const*, uint64_t, const uint8_t* const*, bool*) { cx(ctx); return not_yet("verify_cell_kzg_proof_batch"); }
 CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint64_t*, uint8_t**,
                                          uint8_t**) { cx(ctx); return not_yet("recover_cells_and_proofs"); }
-CResult eth_kzg_compute_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, uint8_t*, uint8_t*) { cx(ctx); return not_yet("compute_kzg_proof"); }
-CResult eth_kzg_compute_blob_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, uint8_t*) { cx(ctx); return not_yet("compute_blob_kzg_proof"); }
 CResult eth_kzg_verify_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_kzg_proof"); }
 CResult eth_kzg_verify_blob_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_blob_kzg_proof"); }
 CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint8_t* const*, uint64_t,

@@ -15,6 +15,15 @@ constexpr int BYTES_PER_G1 = 48;
 constexpr int FK20_POINTS = 64;      // points per fixed-base MSM  (fk20/prover.rs:95-104)
 constexpr int FK20_MSMS = 128;       // MSMs per blob = circulant domain size (fk20/batch_toeplitz.rs:113)
 
+// Fixed-base window table over `npoints` base points P_i: entry (i, t, m) = (m+1) * 2^(t*w) * P_i, affine,
+// at index ((i*nw + t)*half + m).
+struct MsmTable {
+    const G1Affine* table;
+    int w;      // window width in bits
+    int nw;     // number of windows = 255/w + 1
+    int half;   // entries per window = 2^(w-1)
+};
+
 // Read-only tables, built once per device at context creation.  All Fr/Fp values in Montgomery form.
 struct DevTables {
     const Fr* tw4096;        // omega_4096^i,  i < 2048
@@ -28,17 +37,12 @@ struct DevTables {
     // F_k = NTT_128^{G1}(V_k || O^64)  (fk20/batch_toeplitz.rs:49-58); the reference's table holds only
     // the t = 0 slice and pays w doublings per window at MSM time (fixed_base_msm_window.rs:154-165);
     // here every window has its own slice, so an MSM is additions only.
-    const G1Affine* fk20_table;
-    int w;      // window width in bits
-    int nw;     // number of windows = 255/w + 1
-    int half;   // entries per window = 2^(w-1)
+    MsmTable fk20;                     // base point i = j*64 + k  ->  F_k[j]
+    // Same construction over the 4096 monomial SRS points, for commitments and single-point proofs
+    // (reference: g1_lincomb -> blst Pippenger, bls12_381/src/lincomb.rs:7-30; fixed bases make it additions only).
+    MsmTable srs;
     const G1Affine* srs_g1;            // g1_monomial[4096]
     const G1Affine* srs_g1_lagrange;   // g1_lagrange[4096] in the JSON's (bit-reversed) order
 };
-
-// fk20 table index
-__host__ __device__ inline size_t fk20_index(const DevTables& T, int j, int k, int t, int m) {
-    return (((size_t)(j * FK20_POINTS + k) * T.nw + t) * T.half) + m;
-}
 
 }  // namespace ekzg

@@ -172,7 +172,7 @@ k_toeplitz_scalars(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars
 // ------------------------------------------------------------------------------------------------
 template <int NSLICE>
 __global__ void __launch_bounds__(128)
-k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, DevTables T, int B) {
+k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTable T, int B) {
     // block = 128 threads = NSLICE slices x (128/NSLICE) blobs of one MSM j
     constexpr int BLOBS_PER_CTA = 128 / NSLICE;
     constexpr int KPER = FK20_POINTS / NSLICE;
@@ -189,7 +189,7 @@ k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, DevTab
             const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)(j * FK20_POINTS + k) * B + b) * 8);
             uint4 s0 = sp[0], s1 = sp[1];
             uint32_t s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-            const G1Affine* tb = T.fk20_table + fk20_index(T, j, k, 0, 0);
+            const G1Affine* tb = T.table + (size_t)(j * FK20_POINTS + k) * T.nw * T.half;
             for (int t = 0; t < nw; t++) {
                 int d = booth_digit(s, t, w);
                 if (d != 0) {
@@ -338,11 +338,17 @@ __global__ void k_fk20_setup_vectors(const G1Affine* __restrict__ srs, G1Jac* __
 // bases Q_t = 2^(t*w) P, normalised to affine with one shared inversion per thread.
 constexpr int MAX_NW = 64;
 __global__ void __launch_bounds__(64)
-k_fk20_window_bases(const G1Jac* __restrict__ pts, G1Affine* __restrict__ qaff, int w, int nw) {
+k_fk20_window_bases(const G1Jac* __restrict__ pts, const G1Affine* __restrict__ aff, G1Affine* __restrict__ qaff, int w, int nw, int npoints) {
     int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= FK20_MSMS * FK20_POINTS) return;
-    int j = gid / FK20_POINTS, k = gid % FK20_POINTS;
-    G1Jac p = ld_vec(&pts[(size_t)rev_bits(j, 7) * 64 + k]);
+    if (gid >= npoints) return;
+    G1Jac p;
+    if (aff) {  // plain list of affine base points
+        G1Affine a = ld_vec(&aff[gid]);
+        jac_from_affine(p, a);
+    } else {    // FK20: base (j, k) sits at pts[rev7(j)][k] after the DIF NTT
+        int j = gid / FK20_POINTS, k = gid % FK20_POINTS;
+        p = ld_vec(&pts[(size_t)rev_bits(j, 7) * 64 + k]);
+    }
     G1Affine* dst = qaff + (size_t)gid * nw;
     G1Jac qs[MAX_NW];
     Fp prefix[MAX_NW];
@@ -448,12 +454,13 @@ cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const D
     return cudaSuccess;
 }
 
-cudaError_t launch_fk20_msm(const uint32_t* scalars, G1Jac* pts, const DevTables& T, int B, cudaStream_t st) {
+cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st) {
+    // ngroups MSMs of 64 points each per blob (FK20: 128; SRS commitment: 64 partial sums).
     // fewer blobs per launch -> more slices per MSM so the machine still fills
-    if (B >= 512) {
-        k_fk20_msm<4><<<dim3((B + 31) / 32, FK20_MSMS), 128, 0, st>>>(scalars, pts, T, B);
+    if ((size_t)B * ngroups >= 512 * 128) {
+        k_fk20_msm<4><<<dim3((B + 31) / 32, ngroups), 128, 0, st>>>(scalars, pts, T, B);
     } else {
-        k_fk20_msm<16><<<dim3((B + 7) / 8, FK20_MSMS), 128, 0, st>>>(scalars, pts, T, B);
+        k_fk20_msm<16><<<dim3((B + 7) / 8, ngroups), 128, 0, st>>>(scalars, pts, T, B);
     }
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
@@ -491,23 +498,31 @@ cudaError_t launch_g1_decompress(const uint8_t* in, G1Affine* out, uint32_t* sta
     return cudaSuccess;
 }
 
+static cudaError_t fill_table(const G1Jac* pts, const G1Affine* aff, int npoints, G1Affine* qaff, G1Affine* table, const MsmTable& T, cudaStream_t st) {
+    if (T.nw > MAX_NW) return cudaErrorInvalidValue;
+    k_fk20_window_bases<<<(npoints + 63) / 64, 64, 0, st>>>(pts, aff, qaff, T.w, T.nw, npoints);
+    EKZG_LAUNCH_CHECK();
+    size_t nbases = (size_t)npoints * T.nw;
+    int chunks = (T.half + TBL_CH - 1) / TBL_CH;
+    size_t nthreads = nbases * chunks;
+    k_fk20_table_fill<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(qaff, table, T.half, nbases);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
 cudaError_t launch_fk20_setup(const G1Affine* srs, G1Jac* pts_scratch /*128*64*/, G1Affine* qaff /*8192*nw*/, G1Affine* table,
                               const DevTables& T, cudaStream_t st) {
-    if (T.nw > MAX_NW) return cudaErrorInvalidValue;
     k_fk20_setup_vectors<<<(128 * 64 + 127) / 128, 128, 0, st>>>(srs, pts_scratch);
     EKZG_LAUNCH_CHECK();
     for (int s = 6; s >= 0; s--) {
         cudaError_t e = launch_g1_ntt_stage(pts_scratch, T, 64, s, 1, st);
         if (e != cudaSuccess) return e;
     }
-    k_fk20_window_bases<<<(FK20_MSMS * FK20_POINTS + 63) / 64, 64, 0, st>>>(pts_scratch, qaff, T.w, T.nw);
-    EKZG_LAUNCH_CHECK();
-    size_t nbases = (size_t)FK20_MSMS * FK20_POINTS * T.nw;
-    int chunks = (T.half + TBL_CH - 1) / TBL_CH;
-    size_t nthreads = nbases * chunks;
-    k_fk20_table_fill<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(qaff, table, T.half, nbases);
-    EKZG_LAUNCH_CHECK();
-    return cudaSuccess;
+    return fill_table(pts_scratch, nullptr, FK20_MSMS * FK20_POINTS, qaff, table, T.fk20, st);
+}
+
+cudaError_t launch_srs_table_setup(const G1Affine* srs, int npoints, G1Affine* qaff, G1Affine* table, const MsmTable& T, cudaStream_t st) {
+    return fill_table(nullptr, srs, npoints, qaff, table, T, st);
 }
 
 }  // namespace ekzg

@@ -1,0 +1,189 @@
+// sm_100a kernels of the EIP-4844 prover path (blob_to_kzg_commitment, compute_kzg_proof,
+// compute_blob_kzg_proof) and point validation shared with the verifiers.
+//   reference: crates/eip4844/src/prover.rs:17-88, crates/eip4844/src/verifier.rs:146-196,
+//              crates/cryptography/kzg_single_open/src/prover.rs:33-65, crates/serialization/src/lib.rs:69-99.
+// The two MSMs (4096 coefficients x monomial SRS) reuse the fixed-base kernel of the FK20 path: the SRS is
+// fixed, so commitment and proof are table additions only (the reference calls blst's Pippenger per blob).
+#include "kzg_kernels.h"
+#include "fr_ntt.cuh"
+#include "sha256.cuh"
+
+namespace ekzg {
+
+// 32 big-endian bytes -> Fr (Montgomery), value reduced mod r  (bls12_381/src/lib.rs:128-140 reduce_bytes_to_scalar_bias)
+__device__ __forceinline__ Fr fr_from_be_reduce(const uint8_t* p) {
+    Fr x;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        const uint8_t* q = p + 4 * (7 - l);
+        x.v[l] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+    // 2^256 < 3r: two conditional subtractions bring x below r (the Montgomery product needs an operand < r,
+    // otherwise its running sum can exceed 8 limbs)
+    fe_final_sub<FrParams>(x.v);
+    fe_final_sub<FrParams>(x.v);
+    fe_to_mont(x, x);
+    return x;
+}
+
+// z = SHA-256("FSBLOBVERIFY_V1_" || u128_be(4096) || blob || commitment) mod r, one thread per blob
+// (crates/eip4844/src/verifier.rs:155-196)
+__global__ void __launch_bounds__(32)
+k_blob_challenge(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments, Fr* __restrict__ z_out, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    Sha256 s;
+    sha256_init(s);
+    uint8_t head[32] = {'F', 'S', 'B', 'L', 'O', 'B', 'V', 'E', 'R', 'I', 'F', 'Y', '_', 'V', '1', '_', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10, 0x00};
+    sha256_update(s, head, 32);
+    sha256_update(s, blobs + (size_t)b * BYTES_PER_BLOB, BYTES_PER_BLOB);
+    sha256_update(s, commitments + (size_t)b * 48, 48);
+    uint8_t h[32];
+    sha256_final(s, h);
+    st_vec(&z_out[b], fr_from_be_reduce(h));
+}
+
+// user-supplied evaluation points (compute_kzg_proof): 32 BE bytes -> Fr, status |= 2 if not canonical
+__global__ void k_scalars_from_be(const uint8_t* __restrict__ in, Fr* __restrict__ out, uint32_t* __restrict__ status, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[32];
+    for (int c = 0; c < 32; c++) buf[c] = in[(size_t)i * 32 + c];
+    Fr x;
+#pragma unroll
+    for (int l = 0; l < 8; l++) {
+        const uint8_t* q = buf + 4 * (7 - l);
+        x.v[l] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
+    }
+    if (fe_plain_ge_mod(x)) atomicOr(&status[i], 2u);
+    fe_to_mont(x, x);
+    st_vec(&out[i], x);
+}
+
+// Quotient by (X - z) with Ruffini's rule, one thread per blob (kzg_single_open/src/prover.rs:48-65):
+// t_i = c_i + z*t_{i+1};  q_{i-1} = t_i (i = 4095..1);  y = t_0.  q is written as plain integers in the MSM
+// scalar layout [i][B]; q_4095 = 0 so the 4096-point MSM is the reference's 4095-point one.
+__global__ void __launch_bounds__(32)
+k_quotient(const Fr* __restrict__ coeffs, const Fr* __restrict__ z_in, uint32_t* __restrict__ scalars, uint8_t* __restrict__ y_out, int B) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const Fr* c = coeffs + (size_t)b * N_BLOB;
+    const Fr z = ld_vec(&z_in[b]);
+    Fr t;
+    fe_set_zero(t);
+    {
+        uint4* d4 = reinterpret_cast<uint4*>(scalars + ((size_t)(N_BLOB - 1) * B + b) * 8);
+        d4[0] = make_uint4(0, 0, 0, 0);
+        d4[1] = make_uint4(0, 0, 0, 0);
+    }
+    for (int i = N_BLOB - 1; i >= 0; i--) {
+        Fr ci = ld_vec(&c[i]);
+        fe_mul(t, t, z);
+        fe_add(t, t, ci);
+        if (i >= 1) {
+            Fr p;
+            fe_from_mont(p, t);
+            uint4* d4 = reinterpret_cast<uint4*>(scalars + ((size_t)(i - 1) * B + b) * 8);
+            d4[0] = make_uint4(p.v[0], p.v[1], p.v[2], p.v[3]);
+            d4[1] = make_uint4(p.v[4], p.v[5], p.v[6], p.v[7]);
+        }
+    }
+    if (y_out) {
+        Fr y;
+        fe_from_mont(y, t);
+        fr_store_be(y_out + (size_t)b * 32, y);
+    }
+}
+
+// coefficients [B][4096] (Montgomery) -> plain MSM scalars [4096][B]
+__global__ void k_coeffs_to_scalars(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars, int B) {
+    size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)N_BLOB * B) return;
+    int i = (int)(gid / B), b = (int)(gid % B);
+    Fr v = ld_vec(&coeffs[(size_t)b * N_BLOB + i]);
+    fe_from_mont(v, v);
+    uint4* d4 = reinterpret_cast<uint4*>(scalars + gid * 8);
+    d4[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+    d4[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+
+// pts[0][b] = sum_{i < count} pts[stride*i][b]   (the 64 partial sums the fixed-base kernel leaves at even positions)
+__global__ void __launch_bounds__(64)
+k_sum_positions(G1Jac* __restrict__ pts, int B, int count, int stride) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    G1Jac acc = ld_vec(&pts[b]);
+    for (int i = 1; i < count; i++) {
+        G1Jac q = ld_vec(&pts[(size_t)stride * i * B + b]);
+        jac_add(acc, q);
+    }
+    st_vec(&pts[b], acc);
+}
+
+// r = BLS12-381 group order as plain limbs
+__device__ __forceinline__ void fr_modulus(uint32_t* k) {
+#pragma unroll
+    for (int l = 0; l < 8; l++) k[l] = FrParams::mod(l);
+}
+
+// 48-byte compressed -> affine with curve and (optionally) prime-order subgroup check
+// (serialization/src/lib.rs:69-81 -> blstrs from_compressed).  status: 0 ok, 1 malformed/not on curve, 2 not in G1.
+__global__ void __launch_bounds__(64)
+k_g1_validate(const uint8_t* __restrict__ in, G1Affine* __restrict__ out, uint32_t* __restrict__ status, int n, int check_subgroup) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t buf[48];
+    for (int c = 0; c < 48; c++) buf[c] = in[(size_t)i * 48 + c];
+    G1Affine a;
+    uint32_t st = 0;
+    if (g1a_decompress(a, buf)) {
+        g1a_set_inf(a);
+        st = 1;
+    } else if (check_subgroup && !g1a_is_inf(a)) {
+        G1Jac p, q;
+        jac_from_affine(p, a);
+        uint32_t k[8];
+        fr_modulus(k);
+        jac_mul_u256(q, p, k);
+        if (!jac_is_inf(q)) st = 2;
+    }
+    status[i] = st;
+    st_vec(&out[i], a);
+}
+
+// ------------------------------------------------------------------------------------------------
+#define EKZG_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t launch_blob_challenge(const uint8_t* blobs, const uint8_t* commitments, Fr* z, int B, cudaStream_t st) {
+    k_blob_challenge<<<(B + 31) / 32, 32, 0, st>>>(blobs, commitments, z, B);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t launch_scalars_from_be(const uint8_t* in, Fr* out, uint32_t* status, int n, cudaStream_t st) {
+    k_scalars_from_be<<<(n + 63) / 64, 64, 0, st>>>(in, out, status, n);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t launch_quotient(const Fr* coeffs, const Fr* z, uint32_t* scalars, uint8_t* y_out, int B, cudaStream_t st) {
+    k_quotient<<<(B + 31) / 32, 32, 0, st>>>(coeffs, z, scalars, y_out, B);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B, cudaStream_t st) {
+    size_t n = (size_t)N_BLOB * B;
+    k_coeffs_to_scalars<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(coeffs, scalars, B);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t launch_sum_positions(G1Jac* pts, int B, int count, int stride, cudaStream_t st) {
+    k_sum_positions<<<(B + 63) / 64, 64, 0, st>>>(pts, B, count, stride);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t launch_g1_validate(const uint8_t* in, G1Affine* out, uint32_t* status, int n, bool check_subgroup, cudaStream_t st) {
+    k_g1_validate<<<(n + 63) / 64, 64, 0, st>>>(in, out, status, n, check_subgroup ? 1 : 0);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+
+}  // namespace ekzg

@@ -35,6 +35,12 @@ Status Workspace::alloc(int cap, bool with_io) {
         EKZG_CUDA(cudaMalloc(&d_cells, (size_t)cap * N_EXT * 32));
         EKZG_CUDA(cudaMalloc(&d_proofs, (size_t)cap * N_CELLS * BYTES_PER_G1));
         EKZG_CUDA(cudaMalloc(&d_status, (size_t)cap * sizeof(uint32_t)));
+        EKZG_CUDA(cudaMalloc(&d_c48, (size_t)cap * 48));
+        EKZG_CUDA(cudaMalloc(&d_z32, (size_t)cap * 32));
+        EKZG_CUDA(cudaMalloc(&d_out48, (size_t)cap * 48));
+        EKZG_CUDA(cudaMalloc(&d_z, (size_t)cap * sizeof(Fr)));
+        EKZG_CUDA(cudaMalloc(&d_aff, (size_t)cap * sizeof(G1Affine)));
+        EKZG_CUDA(cudaMalloc(&d_status2, (size_t)cap * sizeof(uint32_t)));
         EKZG_CUDA(cudaMallocHost(&h_blobs, (size_t)cap * BYTES_PER_BLOB));
         EKZG_CUDA(cudaMallocHost(&h_cells, (size_t)cap * N_EXT * 32));
         EKZG_CUDA(cudaMallocHost(&h_proofs, (size_t)cap * N_CELLS * BYTES_PER_G1));
@@ -44,6 +50,7 @@ Status Workspace::alloc(int cap, bool with_io) {
 }
 
 void Workspace::release() {
+    cudaFree(d_c48); cudaFree(d_z32); cudaFree(d_out48); cudaFree(d_z); cudaFree(d_aff); cudaFree(d_status2);
     cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_proofs); cudaFree(d_status);
     cudaFreeHost(h_blobs); cudaFreeHost(h_cells); cudaFreeHost(h_proofs); cudaFreeHost(h_status);
     if (done) cudaEventDestroy(done);
@@ -100,9 +107,15 @@ Status Context::init(bool use_precomp) {
         if (const char* e = getenv("EKZG_FK20_WINDOW")) w = atoi(e);
     }
     if (w < 4 || w > 16) return Status::Error("EKZG_FK20_WINDOW must be in [4, 16]");
-    T_.w = w;
-    T_.nw = 255 / w + 1;
-    T_.half = 1 << (w - 1);
+    T_.fk20.w = w;
+    T_.fk20.nw = 255 / w + 1;
+    T_.fk20.half = 1 << (w - 1);
+    int ws = 8;
+    if (const char* e = getenv("EKZG_SRS_WINDOW")) ws = atoi(e);
+    if (ws < 4 || ws > 16) return Status::Error("EKZG_SRS_WINDOW must be in [4, 16]");
+    T_.srs.w = ws;
+    T_.srs.nw = 255 / ws + 1;
+    T_.srs.half = 1 << (ws - 1);
 
     cudaStream_t st = 0;
     // twiddles
@@ -154,8 +167,8 @@ Status Context::init(bool use_precomp) {
     T_.srs_g1_lagrange = srs + n_g1;
 
     // FK20 tables
-    size_t nbases = (size_t)FK20_MSMS * FK20_POINTS * T_.nw;
-    size_t nentries = nbases * T_.half;
+    size_t nbases = (size_t)FK20_MSMS * FK20_POINTS * T_.fk20.nw;
+    size_t nentries = nbases * T_.fk20.half;
     G1Affine* table;
     EKZG_TRY(dev_alloc(allocs_, &table, nentries));
     table_bytes_ = nentries * sizeof(G1Affine);
@@ -163,10 +176,20 @@ Status Context::init(bool use_precomp) {
     G1Affine* qaff = nullptr;
     EKZG_CUDA(cudaMalloc(&scratch, (size_t)128 * 64 * sizeof(G1Jac)));
     EKZG_CUDA(cudaMalloc(&qaff, nbases * sizeof(G1Affine)));
-    T_.fk20_table = table;
+    T_.fk20.table = table;
     EKZG_CUDA(launch_fk20_setup(T_.srs_g1, scratch, qaff, table, T_, st));
     EKZG_CUDA(cudaDeviceSynchronize());
     cudaFree(scratch);
+    cudaFree(qaff);
+    // monomial SRS tables (commitments, single-point proofs)
+    size_t sbases = (size_t)n_g1 * T_.srs.nw;
+    G1Affine* stable;
+    EKZG_TRY(dev_alloc(allocs_, &stable, sbases * T_.srs.half));
+    table_bytes_ += sbases * T_.srs.half * sizeof(G1Affine);
+    EKZG_CUDA(cudaMalloc(&qaff, sbases * sizeof(G1Affine)));
+    T_.srs.table = stable;
+    EKZG_CUDA(launch_srs_table_setup(T_.srs_g1, (int)n_g1, qaff, stable, T_.srs, st));
+    EKZG_CUDA(cudaDeviceSynchronize());
     cudaFree(qaff);
     return Status::Ok();
 }
@@ -221,7 +244,7 @@ Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells
     std::vector<cudaEvent_t>* ev = (profiling_ && !prof_events_.empty()) ? &prof_events_.back() : nullptr;
     EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, n, stream));
     if (ev) cudaEventRecord((*ev)[2], stream);
-    EKZG_CUDA(launch_fk20_msm(ws.d_scalars, ws.d_pts, T_, n, stream));
+    EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, n, stream));
     if (ev) cudaEventRecord((*ev)[3], stream);
     EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, T_, n, stream));
     if (ev) cudaEventRecord((*ev)[4], stream);
@@ -305,6 +328,78 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
     if (!result.ok) return result;
     if (any_bad) return Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus");
     return Status::Ok();
+}
+
+// ------------------------------------------------------------------------------------------------
+// EIP-4844 prover side.  One code path for the three functions; chunks of up to chunk_capacity() blobs.
+Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const uint8_t* aux_in, uint8_t* out48, uint8_t* out_y32,
+                         uint8_t* item_status) const {
+    if (n == 0) return Status::Ok();
+    EKZG_TRY(bind_device());
+    const int cap = (int)std::min<uint64_t>(n, (uint64_t)chunk_capacity());
+    Workspace* wsp = acquire(cap, true);
+    if (!wsp) return Status::Error("device/pinned memory allocation failed");
+    Workspace& ws = *wsp;
+    cudaStream_t st = ws.stream;
+    bool bad_blob = false, bad_aux = false;
+    Status result = Status::Ok();
+    std::vector<uint32_t> hs(cap), hs2(cap);
+    auto body = [&](uint64_t first, int cnt) -> Status {
+        memcpy(ws.h_blobs, blobs + first * BYTES_PER_BLOB, (size_t)cnt * BYTES_PER_BLOB);
+        EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)cnt * BYTES_PER_BLOB, cudaMemcpyHostToDevice, st));
+        EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * cnt, st));
+        EKZG_CUDA(cudaMemsetAsync(ws.d_status2, 0, sizeof(uint32_t) * cnt, st));
+        EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs, ws.d_coeffs, nullptr, ws.d_status, T_, cnt, false, st));
+        if (mode == Mode4844::Commit) {
+            EKZG_CUDA(launch_coeffs_to_scalars(ws.d_coeffs, ws.d_scalars, cnt, st));
+        } else {
+            if (mode == Mode4844::BlobProof) {
+                EKZG_CUDA(cudaMemcpyAsync(ws.d_c48, aux_in + first * 48, (size_t)cnt * 48, cudaMemcpyHostToDevice, st));
+                EKZG_CUDA(launch_g1_validate(ws.d_c48, ws.d_aff, ws.d_status2, cnt, true, st));
+                EKZG_CUDA(launch_blob_challenge(ws.d_blobs, ws.d_c48, ws.d_z, cnt, st));
+            } else {
+                EKZG_CUDA(cudaMemcpyAsync(ws.d_z32, aux_in + first * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, st));
+                EKZG_CUDA(launch_scalars_from_be(ws.d_z32, ws.d_z, ws.d_status2, cnt, st));
+            }
+            EKZG_CUDA(launch_quotient(ws.d_coeffs, ws.d_z, ws.d_scalars, mode == Mode4844::PointProof ? ws.d_z32 : nullptr, cnt, st));
+        }
+        EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.srs, N_BLOB / FK20_POINTS, cnt, st));
+        EKZG_CUDA(launch_sum_positions(ws.d_pts, cnt, N_BLOB / FK20_POINTS, 2, st));
+        EKZG_CUDA(launch_g1_compress(ws.d_pts, ws.d_out48, 1, cnt, st));
+        EKZG_CUDA(cudaMemcpyAsync(out48 + first * 48, ws.d_out48, (size_t)cnt * 48, cudaMemcpyDeviceToHost, st));
+        if (mode == Mode4844::PointProof) EKZG_CUDA(cudaMemcpyAsync(out_y32 + first * 32, ws.d_z32, (size_t)cnt * 32, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaMemcpyAsync(hs.data(), ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaMemcpyAsync(hs2.data(), ws.d_status2, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < cnt; i++) {
+            uint8_t code = hs[i] ? 1 : (hs2[i] ? 2 : 0);
+            if (code == 1) bad_blob = true;
+            if (code == 2) bad_aux = true;
+            if (item_status) item_status[first + i] = code;
+        }
+        return Status::Ok();
+    };
+    for (uint64_t first = 0; first < n && result.ok; first += cap) result = body(first, (int)std::min<uint64_t>(cap, n - first));
+    if (!result.ok) cudaStreamSynchronize(st);
+    give_back(wsp);
+    if (!result.ok) return result;
+    if (bad_blob) return Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus");
+    if (bad_aux)
+        return Status::Error(mode == Mode4844::BlobProof ? "Serialization(G1PointInvalid): commitment is not a valid compressed G1 point in the prime-order subgroup"
+                                                         : "Serialization(ScalarNotCanonical): z is >= the BLS12-381 scalar modulus");
+    return Status::Ok();
+}
+
+Status Context::blob_to_kzg_commitment_batch(uint64_t n, const uint8_t* blobs, uint8_t* out48, uint8_t* item_status) const {
+    return run_4844(Mode4844::Commit, n, blobs, nullptr, out48, nullptr, item_status);
+}
+Status Context::compute_blob_kzg_proof_batch(uint64_t n, const uint8_t* blobs, const uint8_t* commitments48, uint8_t* out48,
+                                             uint8_t* item_status) const {
+    return run_4844(Mode4844::BlobProof, n, blobs, commitments48, out48, nullptr, item_status);
+}
+Status Context::compute_kzg_proof_batch(uint64_t n, const uint8_t* blobs, const uint8_t* z32, uint8_t* out_proof48, uint8_t* out_y32,
+                                        uint8_t* item_status) const {
+    return run_4844(Mode4844::PointProof, n, blobs, z32, out_proof48, out_y32, item_status);
 }
 
 }  // namespace ekzg

@@ -39,6 +39,13 @@ struct Workspace {
     G1Jac* d_pts = nullptr;
     uint8_t* d_proofs = nullptr;
     uint32_t* d_status = nullptr;
+    // small per-blob side buffers of the 4844 path
+    uint8_t* d_c48 = nullptr;      // commitments in (48 B)
+    uint8_t* d_z32 = nullptr;      // evaluation points in / y out (32 B)
+    uint8_t* d_out48 = nullptr;    // commitment / proof out (48 B)
+    Fr* d_z = nullptr;
+    G1Affine* d_aff = nullptr;
+    uint32_t* d_status2 = nullptr;
     // pinned host staging (the ABI hands us scattered caller buffers)
     uint8_t* h_blobs = nullptr;
     uint8_t* h_cells = nullptr;
@@ -67,6 +74,14 @@ public:
     Status compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* blobs, uint8_t* cells, uint8_t* proofs,
                                               uint8_t* blob_status, bool want_proofs) const;
 
+    // EIP-4844 prover side (crates/eip4844/src/prover.rs:17-88), batched.  Host buffers, contiguous.
+    // item_status[i]: 0 ok, 1 invalid blob, 2 invalid commitment / z.
+    Status blob_to_kzg_commitment_batch(uint64_t n, const uint8_t* blobs, uint8_t* out48, uint8_t* item_status) const;
+    Status compute_blob_kzg_proof_batch(uint64_t n, const uint8_t* blobs, const uint8_t* commitments48, uint8_t* out48,
+                                        uint8_t* item_status) const;
+    Status compute_kzg_proof_batch(uint64_t n, const uint8_t* blobs, const uint8_t* z32, uint8_t* out_proof48, uint8_t* out_y32,
+                                   uint8_t* item_status) const;
+
     // workspace pool (calls are re-entrant: concurrent callers each borrow their own workspaces)
     Workspace* acquire(int min_capacity, bool with_io) const;
     void give_back(Workspace* ws) const;
@@ -82,6 +97,9 @@ public:
     int collect_stage_times(double* ms) const;
 
 private:
+    enum class Mode4844 { Commit, BlobProof, PointProof };
+    Status run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const uint8_t* aux_in, uint8_t* out48, uint8_t* out_y32,
+                    uint8_t* item_status) const;
     Context() = default;
     Status init(bool use_precomp);
     int device_ = 0;

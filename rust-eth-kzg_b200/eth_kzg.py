@@ -59,7 +59,8 @@ def load_library():
                  "eth_kzg_verify_cell_kzg_proof_batch", "eth_kzg_recover_cells_and_proofs", "eth_kzg_compute_kzg_proof",
                  "eth_kzg_compute_blob_kzg_proof", "eth_kzg_verify_kzg_proof", "eth_kzg_verify_blob_kzg_proof",
                  "eth_kzg_verify_blob_kzg_proof_batch", "eth_kzg_b200_compute_cells_and_kzg_proofs_batch",
-                 "eth_kzg_b200_compute_cells_and_kzg_proofs_device", "eth_kzg_b200_debug_fk20_stages"):
+                 "eth_kzg_b200_compute_cells_and_kzg_proofs_device", "eth_kzg_b200_debug_fk20_stages",
+                 "eth_kzg_b200_blob_to_kzg_commitment_batch", "eth_kzg_b200_compute_blob_kzg_proof_batch"):
         getattr(lib, name).restype = _CResult
     _lib = lib
     return lib
@@ -225,6 +226,30 @@ class DASContext:
             if not any(st):
                 raise KzgError("batch failed")
         return cells.raw, (proofs.raw if want_proofs else None), st
+
+    def blob_to_kzg_commitment_batch(self, blobs_flat, n):
+        """-> (commitments_flat (n*48 B), status list); raises only on infrastructure errors"""
+        out = C.create_string_buffer(max(n, 1) * 48)
+        status = C.create_string_buffer(max(n, 1))
+        res = self._lib.eth_kzg_b200_blob_to_kzg_commitment_batch(C.c_void_p(self._ctx), C.c_uint64(n), _exact(blobs_flat, n * BYTES_PER_BLOB, "blobs"), out, status)
+        st = list(status.raw[:n])
+        if res.status != 0:
+            self._lib.eth_kzg_free_error_message(res.error_msg)
+            if not any(st):
+                raise KzgError("batch failed")
+        return out.raw[:n * 48], st
+
+    def compute_blob_kzg_proof_batch(self, blobs_flat, commitments_flat, n):
+        out = C.create_string_buffer(max(n, 1) * 48)
+        status = C.create_string_buffer(max(n, 1))
+        res = self._lib.eth_kzg_b200_compute_blob_kzg_proof_batch(C.c_void_p(self._ctx), C.c_uint64(n), _exact(blobs_flat, n * BYTES_PER_BLOB, "blobs"),
+                                                                  _exact(commitments_flat, n * 48, "commitments"), out, status)
+        st = list(status.raw[:n])
+        if res.status != 0:
+            self._lib.eth_kzg_free_error_message(res.error_msg)
+            if not any(st):
+                raise KzgError("batch failed")
+        return out.raw[:n * 48], st
 
     def compute_cells_and_kzg_proofs_device(self, n, d_blobs, d_cells, d_proofs, d_status, stream=0):
         """device pointers (ints), asynchronous on `stream`"""
