@@ -125,6 +125,14 @@ CResult eth_kzg_b200_blob_to_kzg_commitment_batch(const DASContext *ctx, uint64_
 CResult eth_kzg_b200_compute_blob_kzg_proof_batch(const DASContext *ctx, uint64_t n, const uint8_t *blobs,
                                                   const uint8_t *commitments, uint8_t *out_proofs, uint8_t *item_status);
 
+/* Batch form of eth_kzg_recover_cells_and_proofs (BASELINE.json config #4).  Blob i supplies cell_counts[i] cells;
+ * cell_indices and cells (2048 B each) of all blobs are concatenated in blob order.  Outputs contiguous per blob
+ * (128*2048 B cells, 128*48 B proofs).  item_status[i] (optional): 0 ok, 3 invalid indices (range / order / count),
+ * 1 non-canonical cell scalar, 4 recovered polynomial of degree >= 4096.  Err iff any item is invalid. */
+CResult eth_kzg_b200_recover_cells_and_kzg_proofs_batch(const DASContext *ctx, uint64_t n, const uint64_t *cell_counts,
+                                                        const uint64_t *cell_indices, const uint8_t *cells, uint8_t *out_cells,
+                                                        uint8_t *out_proofs, uint8_t *item_status);
+
 /* CUDA device ordinal the context lives on, fixed-base window width, and bytes of HBM its tables occupy. */
 int eth_kzg_b200_context_device(const DASContext *ctx);
 int eth_kzg_b200_context_window(const DASContext *ctx);

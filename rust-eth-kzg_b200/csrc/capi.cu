@@ -167,8 +167,28 @@ CResult eth_kzg_b200_compute_blob_kzg_proof_batch(const DASContext* ctx, uint64_
 }
 CResult eth_kzg_verify_cell_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint64_t*, uint64_t,
                                             const uint8_t* const*, uint64_t, const uint8_t* const*, bool*) { cx(ctx); return not_yet("verify_cell_kzg_proof_batch"); }
-CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint64_t*, uint8_t**,
-                                         uint8_t**) { cx(ctx); return not_yet("recover_cells_and_proofs"); }
+CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t cells_length, const uint8_t* const* cells, uint64_t cell_indices_length,
+                                         const uint64_t* cell_indices, uint8_t** out_cells, uint8_t** out_proofs) {
+    const ekzg::Context& c = cx(ctx);
+    if (cells_length != cell_indices_length)  // recovery.rs:95-100
+        return c_err("Recovery(NumCellIndicesNotEqualToNumCells)");
+    if (cells_length > 4096) return c_err("Recovery(TooManyCellsReceived)");
+    std::vector<uint8_t> flat((size_t)cells_length * ekzg::BYTES_PER_CELL);
+    for (uint64_t i = 0; i < cells_length; i++) memcpy(flat.data() + i * ekzg::BYTES_PER_CELL, cells[i], ekzg::BYTES_PER_CELL);
+    std::vector<uint8_t> oc((size_t)ekzg::N_EXT * 32), op((size_t)ekzg::N_CELLS * 48);
+    uint64_t cnt = cells_length;
+    Status s = c.recover_cells_and_kzg_proofs_batch(1, &cnt, cell_indices, flat.data(), oc.data(), op.data(), nullptr);
+    if (!s.ok) return c_err(s.msg);
+    for (int i = 0; i < ekzg::N_CELLS; i++) {
+        memcpy(out_cells[i], oc.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
+        memcpy(out_proofs[i], op.data() + (size_t)i * 48, 48);
+    }
+    return c_ok();
+}
+CResult eth_kzg_b200_recover_cells_and_kzg_proofs_batch(const DASContext* ctx, uint64_t n, const uint64_t* cell_counts, const uint64_t* cell_indices,
+                                                        const uint8_t* cells, uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) {
+    return to_c(cx(ctx).recover_cells_and_kzg_proofs_batch(n, cell_counts, cell_indices, cells, out_cells, out_proofs, item_status));
+}
 CResult eth_kzg_verify_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_kzg_proof"); }
 CResult eth_kzg_verify_blob_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_blob_kzg_proof"); }
 CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint8_t* const*, uint64_t,

@@ -19,11 +19,10 @@ __device__ __forceinline__ int rev_bits(int x, int bits) { return (int)(__brev((
 // ------------------------------------------------------------------------------------------------
 // setup: twiddle tables  tw[i] = base^i
 // ------------------------------------------------------------------------------------------------
-__global__ void k_powers(Fr* out, Fr base, int n) {
+__global__ void k_powers(Fr* out, Fr base, Fr scale, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr acc, b = base;
-    fe_set_one(acc);
+    Fr acc = scale, b = base;
     for (int e = i; e; e >>= 1) {
         if (e & 1) fe_mul(acc, acc, b);
         fe_sqr(b, b);
@@ -421,10 +420,11 @@ k_fk20_table_fill(const G1Affine* __restrict__ qaff, G1Affine* __restrict__ tabl
 // ------------------------------------------------------------------------------------------------
 #define EKZG_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
-cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st) {
-    Fr b;
+cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st, const uint32_t* scale_mont) {
+    Fr b, sc;
     for (int i = 0; i < 8; i++) b.v[i] = base_mont[i];
-    k_powers<<<(n + 127) / 128, 128, 0, st>>>(out, b, n);
+    for (int i = 0; i < 8; i++) sc.v[i] = scale_mont ? scale_mont[i] : FrParams::one(i);
+    k_powers<<<(n + 127) / 128, 128, 0, st>>>(out, b, sc, n);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -5,7 +5,7 @@
 namespace ekzg {
 
 cudaError_t kernels_init();
-cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st);
+cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st, const uint32_t* scale_mont = nullptr);
 cudaError_t launch_blob_to_coeffs_cells(const uint8_t* blobs, Fr* coeffs, uint8_t* cells, uint32_t* status, const DevTables& T,
                                         int B, bool want_cells, cudaStream_t st);
 cudaError_t launch_coeffs_to_cells(const Fr* coeffs, uint8_t* cells, const DevTables& T, int B, cudaStream_t st);
@@ -26,6 +26,12 @@ cudaError_t launch_quotient(const Fr* coeffs, const Fr* z, uint32_t* scalars, ui
 cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B, cudaStream_t st);
 cudaError_t launch_sum_positions(G1Jac* pts, int B, int count, int stride, cudaStream_t st);
 cudaError_t launch_g1_validate(const uint8_t* in, G1Affine* out, uint32_t* status, int n, bool check_subgroup, cudaStream_t st);
+
+// kzg_kernels_recover.cu
+cudaError_t recover_kernels_init();
+cudaError_t launch_recover_coeffs(const uint8_t* cells, const int16_t* slotmap, Fr* ze, Fr* czinv, Fr* bufA, Fr* bufB, Fr* coeffs,
+                                  uint32_t* status, const DevTables& T, const Fr* shift_fwd, const Fr* shift_inv, const uint32_t* gen64_mont,
+                                  int B, cudaStream_t st);
 
 // number of kernel launches one compute_cells_and_kzg_proofs batch issues (for bench.py's gpu_launches)
 constexpr int FK20_LAUNCHES_PER_BATCH = 1 /*K1*/ + 1 /*K2*/ + 1 /*K4*/ + 14 /*K5*/ + 1 /*K6*/;

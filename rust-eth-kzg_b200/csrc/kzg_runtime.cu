@@ -49,7 +49,19 @@ Status Workspace::alloc(int cap, bool with_io) {
     return Status::Ok();
 }
 
+Status Workspace::ensure_recover_buffers() {
+    if (d_rcells) return Status::Ok();
+    EKZG_CUDA(cudaMalloc(&d_rcells, (size_t)capacity * N_CELLS * BYTES_PER_CELL));
+    EKZG_CUDA(cudaMallocHost(&h_rcells, (size_t)capacity * N_CELLS * BYTES_PER_CELL));
+    EKZG_CUDA(cudaMalloc(&d_slotmap, (size_t)capacity * 128 * sizeof(int16_t)));
+    EKZG_CUDA(cudaMallocHost(&h_slotmap, (size_t)capacity * 128 * sizeof(int16_t)));
+    EKZG_CUDA(cudaMalloc(&d_ze, (size_t)capacity * 128 * sizeof(Fr)));
+    EKZG_CUDA(cudaMalloc(&d_czinv, (size_t)capacity * 128 * sizeof(Fr)));
+    return Status::Ok();
+}
+
 void Workspace::release() {
+    cudaFree(d_rcells); cudaFreeHost(h_rcells); cudaFree(d_slotmap); cudaFreeHost(h_slotmap); cudaFree(d_ze); cudaFree(d_czinv);
     cudaFree(d_c48); cudaFree(d_z32); cudaFree(d_out48); cudaFree(d_z); cudaFree(d_aff); cudaFree(d_status2);
     cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_proofs); cudaFree(d_status);
     cudaFreeHost(h_blobs); cudaFreeHost(h_cells); cudaFreeHost(h_proofs); cudaFreeHost(h_status);
@@ -101,6 +113,7 @@ Status Context::init(bool use_precomp) {
     EKZG_CUDA(cudaGetDeviceProperties(&prop, device_));
     if (prop.major < 10) return Status::Error(std::string("device '") + prop.name + "' is not sm_100-class; this library is built for sm_100a only");
     EKZG_CUDA(kernels_init());
+    EKZG_CUDA(recover_kernels_init());
 
     int w = 8;
     if (use_precomp) {
@@ -134,6 +147,13 @@ Status Context::init(bool use_precomp) {
     EKZG_CUDA(launch_powers(tw64_inv, fr_omega_64_inv().v, 32, st));
     T_.tw4096 = tw4096; T_.tw4096_inv = tw4096_inv; T_.tw8192 = tw8192; T_.tw8192_inv = tw8192_inv;
     T_.tw128 = tw128; T_.tw64_inv = tw64_inv;
+    Fr *sh_fwd, *sh_inv;
+    EKZG_TRY(dev_alloc(allocs_, &sh_fwd, 8192));
+    EKZG_TRY(dev_alloc(allocs_, &sh_inv, 8192));
+    EKZG_CUDA(launch_powers(sh_fwd, fr_coset_gen().v, 8192, st, fr_inv_8192().v));
+    EKZG_CUDA(launch_powers(sh_inv, fr_coset_gen_inv().v, 8192, st, fr_inv_8192().v));
+    coset_shift_fwd_ = sh_fwd;
+    coset_shift_inv_ = sh_inv;
     int8_t* glv;
     EKZG_TRY(dev_alloc(allocs_, &glv, 128 * 66));
     EKZG_CUDA(cudaMemcpy(glv, GLV_TWIDDLE_DIGITS_HOST, 128 * 66, cudaMemcpyHostToDevice));
@@ -327,6 +347,95 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
     }
     if (!result.ok) return result;
     if (any_bad) return Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus");
+    return Status::Ok();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Erasure recovery.
+static int rev7(int x) {
+    int r = 0;
+    for (int b = 0; b < 7; b++) r |= ((x >> b) & 1) << (6 - b);
+    return r;
+}
+
+Status Context::recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
+                                                   uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const {
+    if (n == 0) return Status::Ok();
+    EKZG_TRY(bind_device());
+    // host-side validation in the reference's order (recovery.rs:90-146); invalid items are skipped on the device
+    std::vector<uint64_t> offset(n + 1, 0);
+    for (uint64_t i = 0; i < n; i++) offset[i + 1] = offset[i] + counts[i];
+    std::vector<uint8_t> code(n, 0);
+    std::string first_err;
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t* idx = indices + offset[i];
+        const uint64_t c = counts[i];
+        const char* err = nullptr;
+        for (uint64_t k = 0; k < c && !err; k++)
+            if (idx[k] >= (uint64_t)N_CELLS) err = "Recovery(CellIndexOutOfRange)";
+        for (uint64_t k = 1; k < c && !err; k++)
+            if (!(idx[k - 1] < idx[k])) err = "Recovery(CellIndicesNotUniquelyOrdered)";
+        if (!err && c < (uint64_t)N_CELLS / 2) err = "Recovery(NotEnoughCellsToReconstruct)";
+        if (!err && c > (uint64_t)N_CELLS) err = "Recovery(TooManyCellsReceived)";
+        if (err) {
+            code[i] = 3;
+            if (first_err.empty()) first_err = err;
+        }
+    }
+    const int cap = (int)std::min<uint64_t>(n, (uint64_t)chunk_capacity());
+    Workspace* wsp = acquire(cap, true);
+    if (!wsp) return Status::Error("device/pinned memory allocation failed");
+    Workspace& ws = *wsp;
+    Status result = ws.ensure_recover_buffers();
+    cudaStream_t st = ws.stream;
+    std::vector<uint32_t> hs(cap);
+    auto body = [&](uint64_t first, int cnt) -> Status {
+        for (int i = 0; i < cnt; i++) {
+            int16_t* sm = ws.h_slotmap + (size_t)i * 128;
+            uint8_t* dstc = ws.h_rcells + (size_t)i * N_CELLS * BYTES_PER_CELL;
+            const uint64_t g = first + i;
+            if (code[g]) {  // give the device a harmless well-formed instance: all cells present, all zero
+                for (int m = 0; m < 128; m++) sm[m] = (int16_t)m;
+                memset(dstc, 0, (size_t)N_CELLS * BYTES_PER_CELL);
+                continue;
+            }
+            for (int m = 0; m < 128; m++) sm[m] = -1;
+            for (uint64_t k = 0; k < counts[g]; k++) {
+                sm[rev7((int)indices[offset[g] + k])] = (int16_t)k;
+                memcpy(dstc + k * BYTES_PER_CELL, cells + (offset[g] + k) * BYTES_PER_CELL, BYTES_PER_CELL);
+            }
+        }
+        EKZG_CUDA(cudaMemcpyAsync(ws.d_rcells, ws.h_rcells, (size_t)cnt * N_CELLS * BYTES_PER_CELL, cudaMemcpyHostToDevice, st));
+        EKZG_CUDA(cudaMemcpyAsync(ws.d_slotmap, ws.h_slotmap, (size_t)cnt * 128 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+        EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * cnt, st));
+        EKZG_CUDA(launch_recover_coeffs(ws.d_rcells, ws.d_slotmap, ws.d_ze, ws.d_czinv, reinterpret_cast<Fr*>(ws.d_scalars),
+                                        reinterpret_cast<Fr*>(ws.d_cells), ws.d_coeffs, ws.d_status, T_, coset_shift_fwd_, coset_shift_inv_,
+                                        fr_coset_gen_pow64().v, cnt, st));
+        EKZG_CUDA(launch_coeffs_to_cells(ws.d_coeffs, ws.d_cells, T_, cnt, st));
+        EKZG_TRY(fk20_from_coeffs_device(ws, cnt, ws.d_cells, ws.d_proofs, st));
+        EKZG_CUDA(cudaMemcpyAsync(ws.h_cells, ws.d_cells, (size_t)cnt * N_EXT * 32, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaMemcpyAsync(ws.h_proofs, ws.d_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaStreamSynchronize(st));
+        memcpy(out_cells + first * (N_EXT * 32), ws.h_cells, (size_t)cnt * N_EXT * 32);
+        memcpy(out_proofs + first * (N_CELLS * BYTES_PER_G1), ws.h_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1);
+        for (int i = 0; i < cnt; i++) {
+            const uint64_t g = first + i;
+            if (!code[g] && ws.h_status[i]) {
+                code[g] = (ws.h_status[i] & 1) ? 1 : 4;
+                if (first_err.empty())
+                    first_err = (ws.h_status[i] & 1) ? "Serialization(ScalarNotCanonical): a cell field element is >= the scalar modulus"
+                                                     : "ReedSolomon(PolynomialHasInvalidLength): recovered polynomial has degree >= 4096";
+            }
+        }
+        return Status::Ok();
+    };
+    for (uint64_t first = 0; first < n && result.ok; first += cap) result = body(first, (int)std::min<uint64_t>(cap, n - first));
+    if (!result.ok) cudaStreamSynchronize(st);
+    give_back(wsp);
+    if (item_status) memcpy(item_status, code.data(), n);
+    if (!result.ok) return result;
+    if (!first_err.empty()) return Status::Error(first_err);
     return Status::Ok();
 }
 

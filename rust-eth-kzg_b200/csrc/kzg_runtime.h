@@ -46,6 +46,14 @@ struct Workspace {
     Fr* d_z = nullptr;
     G1Affine* d_aff = nullptr;
     uint32_t* d_status2 = nullptr;
+    // recovery inputs (allocated on first use)
+    uint8_t* d_rcells = nullptr;   // [cap][128 slots][2048]
+    uint8_t* h_rcells = nullptr;
+    int16_t* d_slotmap = nullptr;  // [cap][128]
+    int16_t* h_slotmap = nullptr;
+    Fr* d_ze = nullptr;            // [cap][128]
+    Fr* d_czinv = nullptr;
+    Status ensure_recover_buffers();
     // pinned host staging (the ABI hands us scattered caller buffers)
     uint8_t* h_blobs = nullptr;
     uint8_t* h_cells = nullptr;
@@ -82,6 +90,12 @@ public:
     Status compute_kzg_proof_batch(uint64_t n, const uint8_t* blobs, const uint8_t* z32, uint8_t* out_proof48, uint8_t* out_y32,
                                    uint8_t* item_status) const;
 
+    // Erasure recovery (crates/eip7594/src/prover.rs:156-171, recovery.rs:22-146), batched: blob i provides counts[i]
+    // cells; indices and cells of all blobs are concatenated.  item_status: 0 ok, 3 invalid indices, 1 non-canonical
+    // cell scalar, 4 recovered polynomial of too high degree.  out_* contiguous per blob (128*2048 B, 128*48 B).
+    Status recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
+                                              uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const;
+
     // workspace pool (calls are re-entrant: concurrent callers each borrow their own workspaces)
     Workspace* acquire(int min_capacity, bool with_io) const;
     void give_back(Workspace* ws) const;
@@ -106,6 +120,8 @@ private:
     DevTables T_{};
     std::vector<void*> allocs_;
     uint64_t table_bytes_ = 0;
+    const Fr* coset_shift_fwd_ = nullptr;   // 7^i / 8192
+    const Fr* coset_shift_inv_ = nullptr;   // 7^-i / 8192
     mutable bool profiling_ = false;
     mutable std::vector<std::vector<cudaEvent_t>> prof_events_;  // one vector of N_STAGES+1 events per batch
     mutable std::mutex pool_mu_;

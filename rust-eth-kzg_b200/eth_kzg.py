@@ -60,7 +60,7 @@ def load_library():
                  "eth_kzg_compute_blob_kzg_proof", "eth_kzg_verify_kzg_proof", "eth_kzg_verify_blob_kzg_proof",
                  "eth_kzg_verify_blob_kzg_proof_batch", "eth_kzg_b200_compute_cells_and_kzg_proofs_batch",
                  "eth_kzg_b200_compute_cells_and_kzg_proofs_device", "eth_kzg_b200_debug_fk20_stages",
-                 "eth_kzg_b200_blob_to_kzg_commitment_batch", "eth_kzg_b200_compute_blob_kzg_proof_batch"):
+                 "eth_kzg_b200_recover_cells_and_kzg_proofs_batch", "eth_kzg_b200_blob_to_kzg_commitment_batch", "eth_kzg_b200_compute_blob_kzg_proof_batch"):
         getattr(lib, name).restype = _CResult
     _lib = lib
     return lib
@@ -250,6 +250,24 @@ class DASContext:
             if not any(st):
                 raise KzgError("batch failed")
         return out.raw[:n * 48], st
+
+    def recover_cells_and_kzg_proofs_batch(self, indices_per_blob, cells_per_blob):
+        """lists (one entry per blob) of cell index lists and of lists of 2048-byte cells -> (cells_flat, proofs_flat, status)"""
+        n = len(indices_per_blob)
+        counts = (C.c_uint64 * max(n, 1))(*[len(x) for x in indices_per_blob])
+        flat_idx = [i for x in indices_per_blob for i in x]
+        idx = (C.c_uint64 * max(len(flat_idx), 1))(*flat_idx)
+        cells = b"".join(_exact(c, BYTES_PER_CELL, "cell") for x in cells_per_blob for c in x)
+        oc = C.create_string_buffer(max(n, 1) * CELLS_PER_EXT_BLOB * BYTES_PER_CELL)
+        op = C.create_string_buffer(max(n, 1) * CELLS_PER_EXT_BLOB * 48)
+        status = C.create_string_buffer(max(n, 1))
+        res = self._lib.eth_kzg_b200_recover_cells_and_kzg_proofs_batch(C.c_void_p(self._ctx), C.c_uint64(n), counts, idx, cells, oc, op, status)
+        st = list(status.raw[:n])
+        if res.status != 0:
+            self._lib.eth_kzg_free_error_message(res.error_msg)
+            if not any(st):
+                raise KzgError("batch failed")
+        return oc.raw, op.raw, st
 
     def compute_cells_and_kzg_proofs_device(self, n, d_blobs, d_cells, d_proofs, d_status, stream=0):
         """device pointers (ints), asynchronous on `stream`"""
