@@ -6,6 +6,7 @@
 #include <cstring>
 #include "../../include/c_eth_kzg.h"
 #include "kzg_runtime.h"
+#include "host_pairing.h"
 
 using ekzg::Status;
 
@@ -146,8 +147,20 @@ CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blo
     return c_ok();
 }
 
-// ---- not built yet in this round: fail loudly, never fall back to a CPU path ----
-static CResult not_yet(const char* what) { return c_err(std::string(what) + ": not implemented in this build of c_eth_kzg_b200"); }
+// Test hook (host only, needs no GPU): prod e(P_i, Q_i) == 1 for affine G1 points given as 96 bytes each (x then y, plain
+// little-endian 64-bit limbs; all-zero = identity) and G2 selectors 0 [1]_2, 1 [tau]_2, 2 [tau^64]_2, +3 for the negation.
+int eth_kzg_b200_debug_pairing_check(int n, const uint8_t* g1_xy, const int* g2_sel) {
+    std::vector<ekzg::host::PairingInput> in(n);
+    for (int i = 0; i < n; i++) {
+        memcpy(in[i].g1_x, g1_xy + 96 * i, 48);
+        memcpy(in[i].g1_y, g1_xy + 96 * i + 48, 48);
+        bool z = true;
+        for (int b = 0; b < 96; b++) z = z && g1_xy[96 * i + b] == 0;
+        in[i].g1_is_identity = z;
+        in[i].g2 = (ekzg::host::G2Sel)g2_sel[i];
+    }
+    return ekzg::host::pairing_check(in.data(), n) ? 1 : 0;
+}
 
 CResult eth_kzg_blob_to_kzg_commitment(const DASContext* ctx, const uint8_t* blob, uint8_t* out) {
     return to_c(cx(ctx).blob_to_kzg_commitment_batch(1, blob, out, nullptr));
@@ -165,8 +178,6 @@ CResult eth_kzg_b200_compute_blob_kzg_proof_batch(const DASContext* ctx, uint64_
                                                   uint8_t* out_proofs, uint8_t* item_status) {
     return to_c(cx(ctx).compute_blob_kzg_proof_batch(n, blobs, commitments, out_proofs, item_status));
 }
-CResult eth_kzg_verify_cell_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint64_t*, uint64_t,
-                                            const uint8_t* const*, uint64_t, const uint8_t* const*, bool*) { cx(ctx); return not_yet("verify_cell_kzg_proof_batch"); }
 CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t cells_length, const uint8_t* const* cells, uint64_t cell_indices_length,
                                          const uint64_t* cell_indices, uint8_t** out_cells, uint8_t** out_proofs) {
     const ekzg::Context& c = cx(ctx);
@@ -189,9 +200,28 @@ CResult eth_kzg_b200_recover_cells_and_kzg_proofs_batch(const DASContext* ctx, u
                                                         const uint8_t* cells, uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) {
     return to_c(cx(ctx).recover_cells_and_kzg_proofs_batch(n, cell_counts, cell_indices, cells, out_cells, out_proofs, item_status));
 }
-CResult eth_kzg_verify_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_kzg_proof"); }
-CResult eth_kzg_verify_blob_kzg_proof(const DASContext* ctx, const uint8_t*, const uint8_t*, const uint8_t*, bool*) { cx(ctx); return not_yet("verify_blob_kzg_proof"); }
-CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext* ctx, uint64_t, const uint8_t* const*, uint64_t, const uint8_t* const*, uint64_t,
-                                            const uint8_t* const*, bool*) { cx(ctx); return not_yet("verify_blob_kzg_proof_batch"); }
+
+CResult eth_kzg_verify_cell_kzg_proof_batch(const DASContext* ctx, uint64_t commitments_length, const uint8_t* const* commitments,
+                                            uint64_t cell_indices_length, const uint64_t* cell_indices, uint64_t cells_length,
+                                            const uint8_t* const* cells, uint64_t proofs_length, const uint8_t* const* proofs, bool* verified) {
+    return to_c(cx(ctx).verify_cell_kzg_proof_batch(commitments_length, commitments, cell_indices_length, cell_indices, cells_length, cells,
+                                                    proofs_length, proofs, verified));
+}
+CResult eth_kzg_verify_kzg_proof(const DASContext* ctx, const uint8_t* commitment, const uint8_t* z, const uint8_t* y, const uint8_t* proof,
+                                 bool* verified) {
+    return to_c(cx(ctx).verify_kzg_proofs(0, 1, nullptr, &commitment, z, y, &proof, verified));
+}
+CResult eth_kzg_verify_blob_kzg_proof(const DASContext* ctx, const uint8_t* blob, const uint8_t* commitment, const uint8_t* proof, bool* verified) {
+    return to_c(cx(ctx).verify_kzg_proofs(1, 1, &blob, &commitment, nullptr, nullptr, &proof, verified));
+}
+CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext* ctx, uint64_t blobs_length, const uint8_t* const* blobs, uint64_t commitments_length,
+                                            const uint8_t* const* commitments, uint64_t proofs_length, const uint8_t* const* proofs,
+                                            bool* verified) {
+    if (!(blobs_length == commitments_length && blobs_length == proofs_length)) {  // eip4844/src/verifier.rs:86-95
+        *verified = false;
+        return c_err("Verifier(BatchVerificationInputsMustHaveSameLength)");
+    }
+    return to_c(cx(ctx).verify_kzg_proofs(1, blobs_length, blobs, commitments, nullptr, nullptr, proofs, verified));
+}
 
 }  // extern "C"

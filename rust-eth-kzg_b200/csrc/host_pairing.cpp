@@ -1,0 +1,279 @@
+// Host-side optimal-ate pairing check on BLS12-381 for the verifiers: prod_i e(P_i, Q_i) == 1 with the Q_i
+// taken from the three FIXED G2 points of the verification keys, so all G2 work (the line coefficients of the
+// Miller loop) is done once at start-up and a check costs two sparse Miller loops + one final exponentiation.
+//   reference: multi_pairings (crates/cryptography/bls12_381/src/lib.rs:45-50 -> blstrs Bls12::multi_miller_loop +
+//   final_exponentiation) with G2Prepared inputs (kzg_multi_open/src/fk20/verifier.rs:100-106, 251-254;
+//   kzg_single_open/src/verifier.rs:33-58).  One pairing check per verify call: latency-bound scalar work that stays on
+//   the CPU (SURVEY.md §2.2 "(host) 2-pairing check").
+// Tower: Fp2 = Fp[u]/(u^2+1), Fp6 = Fp2[v]/(v^3-(1+u)), Fp12 = Fp6[w]/(w^2-v).  Fp: 6x64-bit Montgomery.
+#include "host_pairing.h"
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include "host_consts.h"
+
+namespace ekzg {
+namespace host {
+
+typedef unsigned __int128 u128;
+
+struct Fp { uint64_t v[6]; };
+
+static inline bool fp_is_zero(const Fp& a) { uint64_t x = 0; for (int i = 0; i < 6; i++) x |= a.v[i]; return x == 0; }
+static inline bool fp_eq(const Fp& a, const Fp& b) { return memcmp(a.v, b.v, 48) == 0; }
+static inline bool ge_p(const uint64_t* t) {
+    for (int i = 5; i >= 0; i--) { if (t[i] > FP_P[i]) return true; if (t[i] < FP_P[i]) return false; }
+    return true;
+}
+static inline void sub_p(uint64_t* t) {
+    uint64_t br = 0;
+    for (int i = 0; i < 6; i++) { u128 d = (u128)t[i] - FP_P[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+}
+static inline void fp_add(Fp& r, const Fp& a, const Fp& b) {
+    uint64_t t[6]; u128 c = 0;
+    for (int i = 0; i < 6; i++) { c += (u128)a.v[i] + b.v[i]; t[i] = (uint64_t)c; c >>= 64; }
+    if (ge_p(t)) sub_p(t);
+    memcpy(r.v, t, 48);
+}
+static inline void fp_sub(Fp& r, const Fp& a, const Fp& b) {
+    uint64_t t[6], br = 0;
+    for (int i = 0; i < 6; i++) { u128 d = (u128)a.v[i] - b.v[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
+    if (br) { u128 c = 0; for (int i = 0; i < 6; i++) { c += (u128)t[i] + FP_P[i]; t[i] = (uint64_t)c; c >>= 64; } }
+    memcpy(r.v, t, 48);
+}
+static inline void fp_neg(Fp& r, const Fp& a) {
+    if (fp_is_zero(a)) { r = a; return; }
+    Fp z; memset(&z, 0, sizeof z); fp_sub(r, z, a);
+}
+static inline void fp_mul(Fp& r, const Fp& a, const Fp& b) {  // CIOS
+    uint64_t t[8] = {0};
+    for (int i = 0; i < 6; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 6; j++) { c += (u128)a.v[j] * b.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[6] = (uint64_t)c; t[7] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * FP_M0;
+        c = ((u128)m * FP_P[0] + t[0]) >> 64;
+        for (int j = 1; j < 6; j++) { c += (u128)m * FP_P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[6]; t[5] = (uint64_t)c; t[6] = t[7] + (uint64_t)(c >> 64);
+    }
+    if (t[6] || ge_p(t)) sub_p(t);
+    memcpy(r.v, t, 48);
+}
+static inline void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
+static Fp fp_from_plain(const uint64_t* x) { Fp a, r2; memcpy(a.v, x, 48); memcpy(r2.v, FP_R2, 48); Fp o; fp_mul(o, a, r2); return o; }
+static Fp fp_one() { Fp o; memcpy(o.v, FP_ONE, 48); return o; }
+static void fp_inv(Fp& r, const Fp& a) {
+    Fp acc = fp_one(), base = a;
+    for (int i = 0; i < 384; i++) {
+        if ((FP_EXP_INV[i / 64] >> (i % 64)) & 1) fp_mul(acc, acc, base);
+        fp_sqr(base, base);
+    }
+    r = acc;
+}
+
+struct Fp2 { Fp c0, c1; };
+static inline void f2_add(Fp2& r, const Fp2& a, const Fp2& b) { fp_add(r.c0, a.c0, b.c0); fp_add(r.c1, a.c1, b.c1); }
+static inline void f2_sub(Fp2& r, const Fp2& a, const Fp2& b) { fp_sub(r.c0, a.c0, b.c0); fp_sub(r.c1, a.c1, b.c1); }
+static inline void f2_neg(Fp2& r, const Fp2& a) { fp_neg(r.c0, a.c0); fp_neg(r.c1, a.c1); }
+static inline void f2_mul(Fp2& r, const Fp2& a, const Fp2& b) {  // Karatsuba, 3 Fp mul
+    Fp t0, t1, s0, s1, m;
+    fp_mul(t0, a.c0, b.c0); fp_mul(t1, a.c1, b.c1);
+    fp_add(s0, a.c0, a.c1); fp_add(s1, b.c0, b.c1); fp_mul(m, s0, s1);
+    fp_sub(m, m, t0); fp_sub(m, m, t1);
+    fp_sub(r.c0, t0, t1); r.c1 = m;
+}
+static inline void f2_sqr(Fp2& r, const Fp2& a) {  // (a0+a1)(a0-a1), 2 a0 a1
+    Fp s, d, m;
+    fp_add(s, a.c0, a.c1); fp_sub(d, a.c0, a.c1); fp_mul(m, a.c0, a.c1);
+    fp_mul(r.c0, s, d); fp_add(r.c1, m, m);
+}
+static inline void f2_mul_fp(Fp2& r, const Fp2& a, const Fp& b) { fp_mul(r.c0, a.c0, b); fp_mul(r.c1, a.c1, b); }
+static inline void f2_mul_xi(Fp2& r, const Fp2& a) { Fp t0, t1; fp_sub(t0, a.c0, a.c1); fp_add(t1, a.c0, a.c1); r.c0 = t0; r.c1 = t1; }
+static inline bool f2_is_zero(const Fp2& a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+static void f2_inv(Fp2& r, const Fp2& a) {
+    Fp n, t; fp_sqr(n, a.c0); fp_sqr(t, a.c1); fp_add(n, n, t); fp_inv(n, n);
+    fp_mul(r.c0, a.c0, n); fp_mul(t, a.c1, n); fp_neg(r.c1, t);
+}
+static Fp2 f2_zero() { Fp2 z; memset(&z, 0, sizeof z); return z; }
+
+struct Fp6 { Fp2 a0, a1, a2; };
+static inline void f6_add(Fp6& r, const Fp6& a, const Fp6& b) { f2_add(r.a0, a.a0, b.a0); f2_add(r.a1, a.a1, b.a1); f2_add(r.a2, a.a2, b.a2); }
+static inline void f6_sub(Fp6& r, const Fp6& a, const Fp6& b) { f2_sub(r.a0, a.a0, b.a0); f2_sub(r.a1, a.a1, b.a1); f2_sub(r.a2, a.a2, b.a2); }
+static inline void f6_neg(Fp6& r, const Fp6& a) { f2_neg(r.a0, a.a0); f2_neg(r.a1, a.a1); f2_neg(r.a2, a.a2); }
+static void f6_mul(Fp6& r, const Fp6& a, const Fp6& b) {  // Karatsuba (6 Fp2 mul), v^3 = xi
+    Fp2 v0, v1, v2, t, s1, s2, o0, o1, o2;
+    f2_mul(v0, a.a0, b.a0); f2_mul(v1, a.a1, b.a1); f2_mul(v2, a.a2, b.a2);
+    // o0 = v0 + xi*((a1+a2)(b1+b2) - v1 - v2)
+    f2_add(s1, a.a1, a.a2); f2_add(s2, b.a1, b.a2); f2_mul(t, s1, s2); f2_sub(t, t, v1); f2_sub(t, t, v2); f2_mul_xi(t, t); f2_add(o0, v0, t);
+    // o1 = (a0+a1)(b0+b1) - v0 - v1 + xi*v2
+    f2_add(s1, a.a0, a.a1); f2_add(s2, b.a0, b.a1); f2_mul(t, s1, s2); f2_sub(t, t, v0); f2_sub(t, t, v1); f2_mul_xi(s1, v2); f2_add(o1, t, s1);
+    // o2 = (a0+a2)(b0+b2) - v0 - v2 + v1
+    f2_add(s1, a.a0, a.a2); f2_add(s2, b.a0, b.a2); f2_mul(t, s1, s2); f2_sub(t, t, v0); f2_sub(t, t, v2); f2_add(o2, t, v1);
+    r.a0 = o0; r.a1 = o1; r.a2 = o2;
+}
+static inline void f6_mul_v(Fp6& r, const Fp6& a) { Fp6 o; f2_mul_xi(o.a0, a.a2); o.a1 = a.a0; o.a2 = a.a1; r = o; }
+static void f6_inv(Fp6& r, const Fp6& a) {
+    // standard: c0 = a0^2 - xi a1 a2, c1 = xi a2^2 - a0 a1, c2 = a1^2 - a0 a2, t = a0 c0 + xi(a2 c1 + a1 c2)
+    Fp2 c0, c1, c2, t, u;
+    f2_sqr(c0, a.a0); f2_mul(t, a.a1, a.a2); f2_mul_xi(t, t); f2_sub(c0, c0, t);
+    f2_sqr(c1, a.a2); f2_mul_xi(c1, c1); f2_mul(t, a.a0, a.a1); f2_sub(c1, c1, t);
+    f2_sqr(c2, a.a1); f2_mul(t, a.a0, a.a2); f2_sub(c2, c2, t);
+    f2_mul(t, a.a2, c1); f2_mul(u, a.a1, c2); f2_add(t, t, u); f2_mul_xi(t, t); f2_mul(u, a.a0, c0); f2_add(t, t, u);
+    f2_inv(t, t);
+    f2_mul(r.a0, c0, t); f2_mul(r.a1, c1, t); f2_mul(r.a2, c2, t);
+}
+
+struct Fp12 { Fp6 c0, c1; };
+static Fp12 f12_one() { Fp12 o; memset(&o, 0, sizeof o); o.c0.a0.c0 = fp_one(); return o; }
+static void f12_mul(Fp12& r, const Fp12& a, const Fp12& b) {  // Karatsuba (3 Fp6 mul), w^2 = v
+    Fp6 t0, t1, s0, s1, m, v;
+    f6_mul(t0, a.c0, b.c0); f6_mul(t1, a.c1, b.c1);
+    f6_add(s0, a.c0, a.c1); f6_add(s1, b.c0, b.c1); f6_mul(m, s0, s1);
+    f6_sub(m, m, t0); f6_sub(m, m, t1);
+    f6_mul_v(v, t1);
+    f6_add(r.c0, t0, v); r.c1 = m;
+}
+static void f12_sqr(Fp12& r, const Fp12& a) {  // complex squaring: 2 Fp6 mul
+    Fp6 ab, s, t, v;
+    f6_mul(ab, a.c0, a.c1);
+    f6_add(s, a.c0, a.c1); f6_mul_v(v, a.c1); f6_add(t, a.c0, v);
+    f6_mul(s, s, t);               // (c0+c1)(c0+v c1) = c0^2 + v c1^2 + c0c1 + v c0c1
+    f6_sub(s, s, ab); f6_mul_v(v, ab); f6_sub(s, s, v);
+    r.c0 = s; f6_add(r.c1, ab, ab);
+}
+static void f12_conj(Fp12& r, const Fp12& a) { r.c0 = a.c0; f6_neg(r.c1, a.c1); }
+static void f12_inv(Fp12& r, const Fp12& a) {
+    Fp6 t0, t1;
+    f6_mul(t0, a.c0, a.c0); f6_mul(t1, a.c1, a.c1); f6_mul_v(t1, t1); f6_sub(t0, t0, t1);  // c0^2 - v c1^2
+    f6_inv(t0, t0);
+    f6_mul(r.c0, a.c0, t0); f6_mul(t1, a.c1, t0); f6_neg(r.c1, t1);
+}
+static bool f12_is_one(const Fp12& a) { Fp12 o = f12_one(); return memcmp(&a, &o, sizeof o) == 0; }
+
+struct G2Aff { Fp2 x, y; };
+struct Line { Fp2 lam, c; };  // line through T: value at P=(xP,yP) is (c - lam*xP v) + (yP v) w
+
+struct State {
+    Fp gamma[6];
+    std::vector<Line> lines[6];  // G2Sel index
+    bool ok = false;
+};
+static State g_state;
+static std::once_flag g_once;
+
+static void f12_frob2(Fp12& r, const Fp12& a) {
+    const Fp* g = g_state.gamma;
+    r.c0.a0 = a.c0.a0;
+    f2_mul_fp(r.c0.a1, a.c0.a1, g[2]);
+    f2_mul_fp(r.c0.a2, a.c0.a2, g[4]);
+    f2_mul_fp(r.c1.a0, a.c1.a0, g[1]);
+    f2_mul_fp(r.c1.a1, a.c1.a1, g[3]);
+    f2_mul_fp(r.c1.a2, a.c1.a2, g[5]);
+}
+
+static void prepare(std::vector<Line>& out, const G2Aff& q) {
+    G2Aff t = q;
+    out.clear();
+    for (int bit = 62; bit >= 0; bit--) {
+        for (int pass = 0; pass < 2; pass++) {
+            if (pass == 1 && !((BLS_X_ABS >> bit) & 1)) break;
+            Fp2 num, den, lam, tmp;
+            if (pass == 0) {  // tangent at T
+                f2_sqr(num, t.x); f2_add(tmp, num, num); f2_add(num, tmp, num);
+                f2_add(den, t.y, t.y);
+            } else {          // chord through T and Q
+                f2_sub(num, q.y, t.y); f2_sub(den, q.x, t.x);
+            }
+            f2_inv(den, den); f2_mul(lam, num, den);
+            Line l;
+            l.lam = lam;
+            f2_mul(l.c, lam, t.x); f2_sub(l.c, l.c, t.y);
+            out.push_back(l);
+            const Fp2& x2 = pass == 0 ? t.x : q.x;
+            Fp2 x3, y3;
+            f2_sqr(x3, lam); f2_sub(x3, x3, t.x); f2_sub(x3, x3, x2);
+            f2_sub(tmp, t.x, x3); f2_mul(y3, lam, tmp); f2_sub(y3, y3, t.y);
+            t.x = x3; t.y = y3;
+        }
+    }
+}
+
+static G2Aff g2_const(const uint64_t* x0, const uint64_t* x1, const uint64_t* y0, const uint64_t* y1, bool neg) {
+    G2Aff q;
+    q.x.c0 = fp_from_plain(x0); q.x.c1 = fp_from_plain(x1); q.y.c0 = fp_from_plain(y0); q.y.c1 = fp_from_plain(y1);
+    if (neg) f2_neg(q.y, q.y);
+    return q;
+}
+
+static bool on_twist(const G2Aff& q) {  // y^2 == x^3 + 4(1+u)
+    Fp2 l, r, b;
+    f2_sqr(l, q.y); f2_sqr(r, q.x); f2_mul(r, r, q.x);
+    uint64_t four[6] = {4, 0, 0, 0, 0, 0};
+    b.c0 = fp_from_plain(four); b.c1 = b.c0;
+    f2_add(r, r, b);
+    return fp_eq(l.c0, r.c0) && fp_eq(l.c1, r.c1);
+}
+
+static void init_state() {
+    State& s = g_state;
+    s.gamma[0] = fp_one();
+    const uint64_t* gs[5] = {FROB2_GAMMA_1, FROB2_GAMMA_2, FROB2_GAMMA_3, FROB2_GAMMA_4, FROB2_GAMMA_5};
+    for (int i = 0; i < 5; i++) memcpy(s.gamma[i + 1].v, gs[i], 48);
+    bool ok = true;
+    for (int neg = 0; neg < 2; neg++) {
+        G2Aff gen = g2_const(G2_GEN_X0, G2_GEN_X1, G2_GEN_Y0, G2_GEN_Y1, neg);
+        G2Aff tau = g2_const(G2_TAU_X0, G2_TAU_X1, G2_TAU_Y0, G2_TAU_Y1, neg);
+        G2Aff t64 = g2_const(G2_TAU64_X0, G2_TAU64_X1, G2_TAU64_Y0, G2_TAU64_Y1, neg);
+        ok = ok && on_twist(gen) && on_twist(tau) && on_twist(t64);
+        prepare(s.lines[0 + 3 * neg], gen);
+        prepare(s.lines[1 + 3 * neg], tau);
+        prepare(s.lines[2 + 3 * neg], t64);
+    }
+    s.ok = ok;
+}
+
+bool pairing_check(const PairingInput* in, int n) {
+    std::call_once(g_once, init_state);
+    if (!g_state.ok) return false;
+    struct Pt { Fp x, y; const std::vector<Line>* ls; };
+    std::vector<Pt> pts;
+    for (int i = 0; i < n; i++) {
+        if (in[i].g1_is_identity) continue;  // e(O, Q) = 1 (blstrs skips identity pairs as well)
+        Pt p;
+        p.x = fp_from_plain(in[i].g1_x); p.y = fp_from_plain(in[i].g1_y);
+        p.ls = &g_state.lines[(int)in[i].g2];
+        pts.push_back(p);
+    }
+    Fp12 f = f12_one();
+    size_t idx = 0;
+    for (int bit = 62; bit >= 0; bit--) {
+        f12_sqr(f, f);
+        int steps = ((BLS_X_ABS >> bit) & 1) ? 2 : 1;
+        for (int sidx = 0; sidx < steps; sidx++, idx++) {
+            for (const Pt& p : pts) {
+                const Line& l = (*p.ls)[idx];
+                Fp12 lf;
+                memset(&lf, 0, sizeof lf);
+                lf.c0.a0 = l.c;
+                f2_mul_fp(lf.c0.a1, l.lam, p.x); f2_neg(lf.c0.a1, lf.c0.a1);
+                lf.c1.a1.c0 = p.y;
+                f12_mul(f, f, lf);
+            }
+        }
+    }
+    // final exponentiation: easy part (p^6-1)(p^2+1), then the hard part (p^4-p^2+1)/r by square-and-multiply
+    Fp12 t, u;
+    f12_conj(t, f); f12_inv(u, f); f12_mul(t, t, u);
+    f12_frob2(u, t); f12_mul(t, u, t);
+    Fp12 acc = f12_one();
+    int top = HARD_EXP_LIMBS * 64 - 1;
+    while (!((HARD_EXP[top / 64] >> (top % 64)) & 1)) top--;
+    for (int i = top; i >= 0; i--) {
+        f12_sqr(acc, acc);
+        if ((HARD_EXP[i / 64] >> (i % 64)) & 1) f12_mul(acc, acc, t);
+    }
+    return f12_is_one(acc);
+}
+
+}  // namespace host
+}  // namespace ekzg

@@ -33,6 +33,21 @@ cudaError_t launch_recover_coeffs(const uint8_t* cells, const int16_t* slotmap, 
                                   uint32_t* status, const DevTables& T, const Fr* shift_fwd, const Fr* shift_inv, const uint32_t* gen64_mont,
                                   int B, cudaStream_t st);
 
+// kzg_kernels_verify.cu
+cudaError_t launch_powers_from_hash(const uint8_t* hash, Fr* rpow, int n, cudaStream_t st);
+cudaError_t launch_cell_verify_scalars(const Fr* rpow, const uint32_t* col, uint32_t* s1, uint32_t* s2, const DevTables& T, int n, cudaStream_t st);
+cudaError_t launch_commitment_weights(const Fr* rpow, const uint32_t* row, uint32_t* wout, int n, int m, cudaStream_t st);
+cudaError_t launch_scalar_mul(const G1Affine* pts, const uint32_t* scalars, G1Jac* out, int n, cudaStream_t st);
+cudaError_t launch_sum_points(const G1Jac* in, int n, G1Jac* scratch, G1Jac* out, cudaStream_t st);
+cudaError_t launch_cell_interp(const uint8_t* cells, const uint32_t* col, const Fr* rpow, Fr* interp, uint32_t* status, const DevTables& T,
+                               int n, cudaStream_t st);
+cudaError_t launch_interp_column_sum(const Fr* interp, uint32_t* out, int n, cudaStream_t st);
+cudaError_t launch_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* b1, const G1Jac* b2, uint32_t* out, cudaStream_t st);
+cudaError_t launch_kzg_verify_terms(const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* rpow, G1Jac* L,
+                                    G1Jac* R, int n, cudaStream_t st);
+cudaError_t launch_poly_eval(const Fr* coeffs, const Fr* z, Fr* y, uint8_t* y_be, int B, cudaStream_t st);
+cudaError_t launch_fr_to_be(const Fr* in, uint8_t* out, int n, cudaStream_t st);
+
 // number of kernel launches one compute_cells_and_kzg_proofs batch issues (for bench.py's gpu_launches)
 constexpr int FK20_LAUNCHES_PER_BATCH = 1 /*K1*/ + 1 /*K2*/ + 1 /*K4*/ + 14 /*K5*/ + 1 /*K6*/;
 

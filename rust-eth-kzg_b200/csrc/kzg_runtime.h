@@ -96,6 +96,14 @@ public:
     Status recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
                                               uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const;
 
+    // Verifiers.  Err = malformed input, Ok + *verified = false = the proof does not check (bindings/c/src/lib.rs:272-280).
+    Status verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_t* const* commitments, uint64_t n_indices,
+                                       const uint64_t* cell_indices, uint64_t n_cells, const uint8_t* const* cells, uint64_t n_proofs,
+                                       const uint8_t* const* proofs, bool* verified) const;
+    // mode 0: verify_kzg_proof items (commitment, z, y, proof); mode 1: verify_blob_kzg_proof(_batch) items (blob, commitment, proof)
+    Status verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* blobs, const uint8_t* const* commitments, const uint8_t* z32,
+                             const uint8_t* y32, const uint8_t* const* proofs, bool* verified) const;
+
     // workspace pool (calls are re-entrant: concurrent callers each borrow their own workspaces)
     Workspace* acquire(int min_capacity, bool with_io) const;
     void give_back(Workspace* ws) const;

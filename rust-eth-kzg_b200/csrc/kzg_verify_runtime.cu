@@ -1,0 +1,283 @@
+// Host orchestration of the verifiers (see kzg_kernels_verify.cu for the device side, host_pairing.cpp for the pairing).
+//   reference: crates/eip7594/src/verifier.rs:49-164 (dedup + validation + dispatch),
+//              kzg_multi_open/src/fk20/verifier.rs:129-328, crates/eip4844/src/verifier.rs:19-260.
+#include <cstring>
+#include <map>
+#include <string>
+#include "host_pairing.h"
+#include "kzg_runtime.h"
+#include "sha256.cuh"
+
+namespace ekzg {
+
+#define EKZG_TRY(expr) do { ::ekzg::Status s_ = (expr); if (!s_.ok) return s_; } while (0)
+
+namespace {
+
+// stream-ordered scratch that frees itself
+struct Scratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit Scratch(cudaStream_t s) : st(s) {}
+    ~Scratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+    template <class T>
+    Status get(T** out, size_t count) {
+        void* p = nullptr;
+        EKZG_CUDA(cudaMallocAsync(&p, (count ? count : 1) * sizeof(T), st));
+        ptrs.push_back(p);
+        *out = reinterpret_cast<T*>(p);
+        return Status::Ok();
+    }
+};
+
+void be64(uint8_t* o, uint64_t v) { for (int i = 0; i < 8; i++) o[i] = (uint8_t)(v >> (56 - 8 * i)); }
+
+bool run_pairing(const uint32_t* w /*2 x 25 words*/, host::G2Sel q0, host::G2Sel q1) {
+    host::PairingInput in[2];
+    for (int i = 0; i < 2; i++) {
+        const uint32_t* o = w + 25 * i;
+        for (int l = 0; l < 6; l++) {
+            in[i].g1_x[l] = (uint64_t)o[2 * l] | ((uint64_t)o[2 * l + 1] << 32);
+            in[i].g1_y[l] = (uint64_t)o[12 + 2 * l] | ((uint64_t)o[12 + 2 * l + 1] << 32);
+        }
+        in[i].g1_is_identity = o[24] != 0;
+    }
+    in[0].g2 = q0;
+    in[1].g2 = q1;
+    return host::pairing_check(in, 2);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_t* const* commitments, uint64_t n_indices,
+                                            const uint64_t* cell_indices, uint64_t n_cells, const uint8_t* const* cells, uint64_t n_proofs,
+                                            const uint8_t* const* proofs, bool* verified) const {
+    *verified = false;
+    // deduplicate_with_indices (verifier.rs:49-65): first occurrence order is part of the transcript
+    std::vector<const uint8_t*> uniq;
+    std::vector<uint32_t> rows(n_commitments);
+    {
+        std::map<std::string, uint32_t> seen;
+        for (uint64_t i = 0; i < n_commitments; i++) {
+            std::string key(reinterpret_cast<const char*>(commitments[i]), 48);
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, (uint32_t)uniq.size()).first;
+                uniq.push_back(commitments[i]);
+            }
+            rows[i] = it->second;
+        }
+    }
+    // validation (verifier.rs:123-164)
+    if (!(n_commitments == n_indices && n_commitments == n_cells && n_commitments == n_proofs))
+        return Status::Error("Verifier(BatchVerificationInputsMustHaveSameLength)");
+    for (uint64_t i = 0; i < n_indices; i++)
+        if (cell_indices[i] >= (uint64_t)N_CELLS) return Status::Error("Verifier(CellIndexOutOfRange)");
+    const int N = (int)n_cells, M = (int)uniq.size();
+    if (N == 0) { *verified = true; return Status::Ok(); }
+    EKZG_TRY(bind_device());
+
+    // pack inputs
+    std::vector<uint8_t> hc((size_t)M * 48), hp((size_t)N * 48), hcells((size_t)N * BYTES_PER_CELL);
+    std::vector<uint32_t> hcol(N);
+    for (int i = 0; i < M; i++) memcpy(&hc[(size_t)i * 48], uniq[i], 48);
+    for (int k = 0; k < N; k++) {
+        memcpy(&hp[(size_t)k * 48], proofs[k], 48);
+        memcpy(&hcells[(size_t)k * BYTES_PER_CELL], cells[k], BYTES_PER_CELL);
+        hcol[k] = (uint32_t)cell_indices[k];
+    }
+    Workspace* wsp = acquire(1, true);
+    if (!wsp) return Status::Error("allocation failed");
+    cudaStream_t st = wsp->stream;
+    Status result = Status::Ok();
+    uint32_t pin[50];
+    std::vector<uint32_t> stc(M), stp(N);
+    uint32_t cell_status = 0;
+    {
+        Scratch S(st);
+        auto run = [&]() -> Status {
+            uint8_t *d_c, *d_p, *d_cells, *d_hash;
+            uint32_t *d_col, *d_row, *d_stc, *d_stp, *d_cellst, *d_s1, *d_s2, *d_w, *d_i, *d_out;
+            G1Affine *a_c, *a_p;
+            Fr *d_rpow, *d_interp;
+            G1Jac *d_mul, *d_part, *d_sums;
+            EKZG_TRY(S.get(&d_c, (size_t)M * 48)); EKZG_TRY(S.get(&d_p, (size_t)N * 48)); EKZG_TRY(S.get(&d_cells, (size_t)N * BYTES_PER_CELL));
+            EKZG_TRY(S.get(&d_hash, 32)); EKZG_TRY(S.get(&d_col, N)); EKZG_TRY(S.get(&d_row, N)); EKZG_TRY(S.get(&d_stc, M)); EKZG_TRY(S.get(&d_stp, N));
+            EKZG_TRY(S.get(&d_cellst, 1)); EKZG_TRY(S.get(&d_s1, (size_t)N * 8)); EKZG_TRY(S.get(&d_s2, (size_t)N * 8)); EKZG_TRY(S.get(&d_w, (size_t)M * 8));
+            EKZG_TRY(S.get(&d_i, 64 * 8)); EKZG_TRY(S.get(&d_out, 50)); EKZG_TRY(S.get(&a_c, M)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_rpow, N));
+            EKZG_TRY(S.get(&d_interp, (size_t)N * 64)); EKZG_TRY(S.get(&d_mul, std::max(N, 64))); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 4));
+            EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemcpyAsync(d_cells, hcells.data(), hcells.size(), cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemcpyAsync(d_col, hcol.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemcpyAsync(d_row, rows.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemsetAsync(d_cellst, 0, 4, st));
+            // point validation runs while the host hashes the transcript
+            EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, M, true, st));
+            EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, true, st));
+            // Fiat-Shamir transcript (fk20/verifier.rs:269-328), sequential SHA-256 on the host
+            uint8_t hash[32];
+            {
+                Sha256 h;
+                sha256_init(h);
+                uint8_t head[16 + 32];
+                memcpy(head, "RCKZGCBATCH__V1_", 16);
+                be64(head + 16, N_BLOB); be64(head + 24, CELL_ELEMS); be64(head + 32, (uint64_t)M); be64(head + 40, (uint64_t)N);
+                sha256_update(h, head, sizeof head);
+                sha256_update(h, hc.data(), hc.size());
+                for (int k = 0; k < N; k++) {
+                    uint8_t idx[16];
+                    be64(idx, rows[k]); be64(idx + 8, hcol[k]);
+                    sha256_update(h, idx, 16);
+                    sha256_update(h, &hcells[(size_t)k * BYTES_PER_CELL], BYTES_PER_CELL);
+                    sha256_update(h, &hp[(size_t)k * 48], 48);
+                }
+                sha256_final(h, hash);
+            }
+            EKZG_CUDA(cudaMemcpyAsync(d_hash, hash, 32, cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(launch_powers_from_hash(d_hash, d_rpow, N, st));
+            EKZG_CUDA(launch_cell_verify_scalars(d_rpow, d_col, d_s1, d_s2, T_, N, st));
+            // P = sum rho_k pi_k ; W = sum rho_k h_k^64 pi_k
+            EKZG_CUDA(launch_scalar_mul(a_p, d_s1, d_mul, N, st));
+            EKZG_CUDA(launch_sum_points(d_mul, N, d_part, &d_sums[0], st));
+            EKZG_CUDA(launch_scalar_mul(a_p, d_s2, d_mul, N, st));
+            EKZG_CUDA(launch_sum_points(d_mul, N, d_part, &d_sums[1], st));
+            // Cs = sum w_i C_i
+            EKZG_CUDA(launch_commitment_weights(d_rpow, d_row, d_w, N, M, st));
+            EKZG_CUDA(launch_scalar_mul(a_c, d_w, d_mul, M, st));
+            EKZG_CUDA(launch_sum_points(d_mul, M, d_part, &d_sums[2], st));
+            // Ic = commit(sum rho_k I_k)
+            EKZG_CUDA(launch_cell_interp(d_cells, d_col, d_rpow, d_interp, d_cellst, T_, N, st));
+            EKZG_CUDA(launch_interp_column_sum(d_interp, d_i, N, st));
+            EKZG_CUDA(launch_scalar_mul(T_.srs_g1, d_i, d_mul, 64, st));
+            EKZG_CUDA(launch_sum_points(d_mul, 64, d_part, &d_sums[3], st));
+            // pairing inputs: (P, [tau^64]_2), (Cs - Ic + W, -[1]_2)
+            EKZG_CUDA(launch_pairing_inputs(&d_sums[0], &d_sums[2], &d_sums[3], &d_sums[1], d_out, st));
+            EKZG_CUDA(cudaMemcpyAsync(pin, d_out, sizeof pin, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaMemcpyAsync(stc.data(), d_stc, sizeof(uint32_t) * M, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaMemcpyAsync(stp.data(), d_stp, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaMemcpyAsync(&cell_status, d_cellst, 4, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaStreamSynchronize(st));
+            return Status::Ok();
+        };
+        result = run();
+        if (!result.ok) cudaStreamSynchronize(st);
+    }
+    give_back(wsp);
+    if (!result.ok) return result;
+    // deserialisation errors in the reference's order: commitments, proofs, cells (verifier.rs:96-98)
+    for (uint32_t v : stc) if (v) return Status::Error("Serialization(G1PointInvalid): commitment");
+    for (uint32_t v : stp) if (v) return Status::Error("Serialization(G1PointInvalid): proof");
+    if (cell_status) return Status::Error("Serialization(ScalarNotCanonical): cell");
+    *verified = run_pairing(pin, host::G2Sel::Tau64, host::G2Sel::NegGen);
+    return Status::Ok();
+}
+
+// ------------------------------------------------------------------------------------------------
+// EIP-4844 verifiers.  mode 0: (commitment, z, y, proof) given; mode 1: blobs given, z and y derived on the device.
+Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* blobs, const uint8_t* const* commitments, const uint8_t* z32,
+                                  const uint8_t* y32, const uint8_t* const* proofs, bool* verified) const {
+    *verified = false;
+    if (n == 0) { *verified = true; return Status::Ok(); }
+    if (n > (1u << 16)) return Status::Error("batch too large");
+    EKZG_TRY(bind_device());
+    const int N = (int)n;
+    std::vector<uint8_t> hc((size_t)N * 48), hp((size_t)N * 48);
+    for (int i = 0; i < N; i++) { memcpy(&hc[(size_t)i * 48], commitments[i], 48); memcpy(&hp[(size_t)i * 48], proofs[i], 48); }
+    Workspace* wsp = acquire(mode == 1 ? N : 1, true);
+    if (!wsp) return Status::Error("allocation failed");
+    Workspace& ws = *wsp;
+    cudaStream_t st = ws.stream;
+    Status result = Status::Ok();
+    uint32_t pin[50];
+    std::vector<uint32_t> stc(N), stp(N), stb(N, 0), stz(N, 0), sty(N, 0);
+    {
+        Scratch S(st);
+        auto run = [&]() -> Status {
+            uint8_t *d_c, *d_p, *d_zb, *d_yb, *d_hash;
+            uint32_t *d_stc, *d_stp, *d_stz, *d_sty, *d_out;
+            G1Affine *a_c, *a_p;
+            Fr *d_z, *d_y, *d_rpow;
+            G1Jac *d_L, *d_R, *d_part, *d_sums;
+            EKZG_TRY(S.get(&d_c, (size_t)N * 48)); EKZG_TRY(S.get(&d_p, (size_t)N * 48)); EKZG_TRY(S.get(&d_zb, (size_t)N * 32)); EKZG_TRY(S.get(&d_yb, (size_t)N * 32));
+            EKZG_TRY(S.get(&d_hash, 32)); EKZG_TRY(S.get(&d_stc, N)); EKZG_TRY(S.get(&d_stp, N)); EKZG_TRY(S.get(&d_stz, N)); EKZG_TRY(S.get(&d_sty, N));
+            EKZG_TRY(S.get(&d_out, 50)); EKZG_TRY(S.get(&a_c, N)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_z, N)); EKZG_TRY(S.get(&d_y, N));
+            EKZG_TRY(S.get(&d_rpow, N)); EKZG_TRY(S.get(&d_L, N)); EKZG_TRY(S.get(&d_R, N)); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 2));
+            EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemsetAsync(d_stz, 0, sizeof(uint32_t) * N, st));
+            EKZG_CUDA(cudaMemsetAsync(d_sty, 0, sizeof(uint32_t) * N, st));
+            EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, N, true, st));
+            EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, true, st));
+            std::vector<uint8_t> zb((size_t)N * 32), yb((size_t)N * 32);
+            if (mode == 0) {
+                EKZG_CUDA(cudaMemcpyAsync(d_zb, z32, (size_t)N * 32, cudaMemcpyHostToDevice, st));
+                EKZG_CUDA(cudaMemcpyAsync(d_yb, y32, (size_t)N * 32, cudaMemcpyHostToDevice, st));
+                EKZG_CUDA(launch_scalars_from_be(d_zb, d_z, d_stz, N, st));
+                EKZG_CUDA(launch_scalars_from_be(d_yb, d_y, d_sty, N, st));
+            } else {
+                for (int i = 0; i < N; i++) memcpy(ws.h_blobs + (size_t)i * BYTES_PER_BLOB, blobs[i], BYTES_PER_BLOB);
+                EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)N * BYTES_PER_BLOB, cudaMemcpyHostToDevice, st));
+                EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * N, st));
+                EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs, ws.d_coeffs, nullptr, ws.d_status, T_, N, false, st));
+                EKZG_CUDA(launch_blob_challenge(ws.d_blobs, d_c, d_z, N, st));
+                EKZG_CUDA(launch_poly_eval(ws.d_coeffs, d_z, d_y, d_yb, N, st));
+                EKZG_CUDA(cudaMemcpyAsync(stb.data(), ws.d_status, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+            }
+            uint8_t hash[32] = {0};
+            if (N > 1) {
+                // r = H("RCKZGBATCH___V1_" || u64(4096) || u64(n) || (C, z, y, pi)*)  (eip4844/src/verifier.rs:202-260)
+                if (mode == 1) {
+                    EKZG_CUDA(launch_fr_to_be(d_z, d_zb, N, st));
+                    EKZG_CUDA(cudaMemcpyAsync(zb.data(), d_zb, zb.size(), cudaMemcpyDeviceToHost, st));
+                    EKZG_CUDA(cudaMemcpyAsync(yb.data(), d_yb, yb.size(), cudaMemcpyDeviceToHost, st));
+                    EKZG_CUDA(cudaStreamSynchronize(st));
+                } else {
+                    memcpy(zb.data(), z32, zb.size());
+                    memcpy(yb.data(), y32, yb.size());
+                }
+                Sha256 h;
+                sha256_init(h);
+                uint8_t head[32];
+                memcpy(head, "RCKZGBATCH___V1_", 16);
+                be64(head + 16, N_BLOB); be64(head + 24, (uint64_t)N);
+                sha256_update(h, head, 32);
+                for (int i = 0; i < N; i++) {
+                    sha256_update(h, &hc[(size_t)i * 48], 48);
+                    sha256_update(h, &zb[(size_t)i * 32], 32);
+                    sha256_update(h, &yb[(size_t)i * 32], 32);
+                    sha256_update(h, &hp[(size_t)i * 48], 48);
+                }
+                sha256_final(h, hash);
+            }
+            // N == 1: the only power used is r^0 = 1, whatever the digest
+            EKZG_CUDA(cudaMemcpyAsync(d_hash, hash, 32, cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(launch_powers_from_hash(d_hash, d_rpow, N, st));
+            EKZG_CUDA(launch_kzg_verify_terms(a_c, a_p, d_z, d_y, d_rpow, d_L, d_R, N, st));
+            EKZG_CUDA(launch_sum_points(d_R, N, d_part, &d_sums[0], st));
+            EKZG_CUDA(launch_sum_points(d_L, N, d_part, &d_sums[1], st));
+            EKZG_CUDA(launch_pairing_inputs(&d_sums[0], &d_sums[1], nullptr, nullptr, d_out, st));
+            EKZG_CUDA(cudaMemcpyAsync(pin, d_out, sizeof pin, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaMemcpyAsync(stc.data(), d_stc, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaMemcpyAsync(stp.data(), d_stp, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaMemcpyAsync(stz.data(), d_stz, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaMemcpyAsync(sty.data(), d_sty, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+            EKZG_CUDA(cudaStreamSynchronize(st));
+            return Status::Ok();
+        };
+        result = run();
+        if (!result.ok) cudaStreamSynchronize(st);
+    }
+    give_back(wsp);
+    if (!result.ok) return result;
+    for (uint32_t v : stb) if (v) return Status::Error("Serialization(ScalarNotCanonical): blob");
+    for (uint32_t v : stc) if (v) return Status::Error("Serialization(G1PointInvalid): commitment");
+    for (uint32_t v : stp) if (v) return Status::Error("Serialization(G1PointInvalid): proof");
+    for (uint32_t v : stz) if (v) return Status::Error("Serialization(ScalarNotCanonical): z");
+    for (uint32_t v : sty) if (v) return Status::Error("Serialization(ScalarNotCanonical): y");
+    *verified = run_pairing(pin, host::G2Sel::Tau, host::G2Sel::NegGen);
+    return Status::Ok();
+}
+
+}  // namespace ekzg

