@@ -35,7 +35,7 @@ EKZG_HD void fe_final_sub(uint32_t* r) {
 }
 
 template <class P>
-EKZG_HD void fe_mul(Fe<P>& out, const Fe<P>& a_, const Fe<P>& b_) {
+EKZG_HD void fe_mul_inline(Fe<P>& out, const Fe<P>& a_, const Fe<P>& b_) {
     constexpr int N = P::N;
     static_assert(N % 2 == 0, "even limb count");
     const uint32_t* a = a_.v;
@@ -101,6 +101,31 @@ EKZG_HD void fe_mul(Fe<P>& out, const Fe<P>& a_, const Fe<P>& b_) {
     fe_final_sub<P>(r);
 #pragma unroll
     for (int j = 0; j < N; j++) out.v[j] = r[j];
+}
+
+// The ~620-instruction Fp multiplication is ONE subroutine per kernel image on the device: operands and result
+// travel in registers (by-value aggregates; ptxas keeps them out of memory), so a point operation is a short
+// sequence of calls and the hot code of every kernel fits the 32 KB L1.5 instruction cache.  Fully inlined,
+// a Jacobian doubling alone is 70 KB of straight-line code and warps that are not in lock step starve on
+// instruction fetch (ncu: stall_no_instruction 21 cycles per issue in the first persistent G1-NTT kernel).
+#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
+static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) {
+    Fp r;
+    fe_mul_inline(r, a, b);
+    return r;
+}
+#endif
+
+template <class P>
+EKZG_HD void fe_mul(Fe<P>& out, const Fe<P>& a, const Fe<P>& b) {
+    fe_mul_inline(out, a, b);
+}
+EKZG_HD void fe_mul(Fp& out, const Fp& a, const Fp& b) {
+#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
+    out = fp_mul_call(a, b);
+#else
+    fe_mul_inline(out, a, b);
+#endif
 }
 
 template <class P>

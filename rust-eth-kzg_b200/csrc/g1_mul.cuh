@@ -79,6 +79,103 @@ EKZG_HD_CALL void jac_mul_glv16(G1Jac& out, const G1Jac& p, const int8_t* d) {
     out = acc;
 }
 
+// r = a + b for Jacobian a, affine b, a != +-b, neither the identity (madd-2004-hmv: 8M + 3S, Z3 = Z1*H);
+// zr = H = Z3/Z1 is handed back for the common-Z table below.
+EKZG_HD_CALL void jac_madd_zr(G1Jac& r, const G1Jac& a, const G1Affine& b, Fp& zr) {
+    Fp t1, t2, t3, t4;
+    fe_sqr(t1, a.z);
+    fe_mul(t2, t1, a.z);
+    fe_mul(t1, t1, b.x);
+    fe_mul(t2, t2, b.y);
+    fe_sub(t1, t1, a.x);       // H
+    fe_sub(t2, t2, a.y);       // R
+    zr = t1;
+    fe_mul(r.z, a.z, t1);
+    fe_sqr(t3, t1);            // HH
+    fe_mul(t4, t3, t1);        // HHH
+    fe_mul(t3, t3, a.x);       // V
+    fe_dbl(t1, t3);
+    Fp x3;
+    fe_sqr(x3, t2);
+    fe_sub(x3, x3, t1);
+    fe_sub(x3, x3, t4);
+    fe_sub(t3, t3, x3);
+    fe_mul(t3, t3, t2);
+    fe_mul(t4, t4, a.y);
+    fe_sub(r.y, t3, t4);
+    r.x = x3;
+}
+
+// k*P for a FIXED scalar given as an op list (tools/gen_device_constants.py: width-5 NAF of the two GLV
+// halves, merged).  This is the `*b * twiddle` of the reference's G1 butterfly (polynomial/src/fft.rs:164-177).
+//   1. odd multiples P, 3P, .., 15P by repeated mixed addition of 2P on the curve isomorphic by 2P's Z, then
+//      rescaled to ONE common Z (the z-ratios of the additions are the H values), so the eight entries are
+//      affine points of an isomorphic curve y^2 = x^3 + 4*Zg^6 -- no inversion;
+//   2. the ladder runs on that curve with mixed additions (11 instead of 16 multiplications each; the
+//      a = 0 formulas never see the curve constant); phi(x, y) = (beta*x, y) holds there as well;
+//   3. Z *= Zg maps the result back.
+// P must be a non-identity point of the prime-order subgroup (callers skip the identity).
+constexpr int MULOPS_STRIDE = 64;
+EKZG_HD_CALL void jac_mul_ops(G1Jac& out, const G1Jac& p, const uint16_t* ops) {
+    G1Affine tbl[8];   // (2i+1)P, common Z
+    Fp bx[8];          // beta * x of the same
+    Fp zr[8];
+    Fp zg;             // common Z (before the factor Z(2P))
+    G1Jac d;
+    jac_dbl(d, p);
+    {
+        G1Jac cur;
+        Fp dz2, dz3;
+        fe_sqr(dz2, d.z);
+        fe_mul(dz3, dz2, d.z);
+        fe_mul(cur.x, p.x, dz2);
+        fe_mul(cur.y, p.y, dz3);
+        cur.z = p.z;
+        G1Affine da;
+        da.x = d.x; da.y = d.y;
+        tbl[0].x = cur.x; tbl[0].y = cur.y;
+        for (int i = 1; i < 8; i++) {
+            G1Jac nxt;
+            jac_madd_zr(nxt, cur, da, zr[i]);
+            cur = nxt;
+            tbl[i].x = cur.x; tbl[i].y = cur.y;
+        }
+        zg = cur.z;
+        Fp zs = zr[7];
+        for (int i = 6; i >= 0; i--) {
+            Fp z2, z3;
+            fe_sqr(z2, zs);
+            fe_mul(z3, z2, zs);
+            fe_mul(tbl[i].x, tbl[i].x, z2);
+            fe_mul(tbl[i].y, tbl[i].y, z3);
+            if (i) fe_mul(zs, zs, zr[i]);
+        }
+        Fp beta;
+#pragma unroll
+        for (int j = 0; j < 12; j++) beta.v[j] = FpParams::beta(j);
+        for (int i = 0; i < 8; i++) fe_mul(bx[i], tbl[i].x, beta);
+    }
+    G1Jac acc;
+    jac_set_inf(acc);
+    const int n = ops[0];
+    for (int c = 1; c <= n; c++) {
+        const uint32_t op = ops[c];
+        for (int s = op >> 8; s > 0; s--) jac_dbl(acc, acc);
+        if (op & 0x20) {
+            const int idx = op & 7;
+            G1Affine e;
+            e.x = (op & 0x10) ? bx[idx] : tbl[idx].x;
+            e.y = tbl[idx].y;
+            jac_madd(acc, e, (op & 8) != 0);
+        }
+    }
+    if (!jac_is_inf(acc)) {
+        fe_mul(acc.z, acc.z, zg);
+        fe_mul(acc.z, acc.z, d.z);
+    }
+    out = acc;
+}
+
 // k*P for a plain 256-bit little-endian scalar (unsigned 4-bit windows); setup paths only
 EKZG_HD_CALL void jac_mul_u256(G1Jac& out, const G1Jac& p, const uint32_t* k) {
     G1Jac tbl[15];
@@ -93,5 +190,10 @@ EKZG_HD_CALL void jac_mul_u256(G1Jac& out, const G1Jac& p, const uint32_t* k) {
     }
     out = acc;
 }
+
+// op lists of the 128th roots of unity, row e = omega_128^e (host copy; the kernels keep one in __constant__)
+static const uint16_t TWIDDLE_OPS_HOST[128][MULOPS_STRIDE] =
+#include "twiddle_ops.inc"
+    ;
 
 }  // namespace ekzg

@@ -32,7 +32,6 @@ struct DevTables {
     const Fr* tw8192_inv;    // omega_8192^-i, i < 4096
     const Fr* tw128;         // omega_128^i,   i < 64
     const Fr* tw64_inv;      // omega_64^-i,   i < 32     (verifier: 64-point coset IFFT)
-    const int8_t* glv_digits;  // [128][66] signed radix-16 GLV digits of omega_128^e
     // FK20 fixed-base tables: entry (j, k, t, m) = (m+1) * 2^(t*w) * F_k[j], affine.
     // F_k = NTT_128^{G1}(V_k || O^64)  (fk20/batch_toeplitz.rs:49-58); the reference's table holds only
     // the t = 0 slice and pays w doublings per window at MSM time (fixed_base_msm_window.rs:154-165);

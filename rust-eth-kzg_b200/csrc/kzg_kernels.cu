@@ -11,6 +11,8 @@
 //   proofs  [B][128*48]  bytes as on the wire
 #include "kzg_kernels.h"
 #include "fr_ntt.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace ekzg {
 
@@ -216,21 +218,55 @@ k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTab
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5  G1 NTT stages  (HOT LOOP #2)
+// K5  the two 128-point G1 NTTs of every blob   (HOT LOOP #2)
 //   reference: Domain::ifft_g1_take_n / fft_g1 (polynomial/src/domain.rs:149-194) over the generic
 //   butterfly `dit` (fft.rs:164-177) whose `*b * twiddle` is a full scalar multiplication.
-//   One thread per (butterfly, blob), blob fastest: a warp is the same butterfly of 32 blobs, so the
-//   twiddle (hence the GLV digit string) is warp-uniform and trivial twiddles skip whole warps.
-//   mode 0: inverse DIT stage `st` (input bit-reversed, written that way by K4).  The last stage only
-//           produces the 64 kept outputs (ifft_g1_take_n(.., 64)); the 1/128 is already in the scalars.
-//   mode 1: forward DIF stage on (h || O^64): the first stage (st = 6) is h[i] -> (h[i], w^i h[i]).
-//           The output of the last stage is in bit-reversed order = proof order (fk20/prover.rs:222).
+//
+//   Work unit = one butterfly of 32 blobs (a warp; blob fastest), so the twiddle -- hence the whole
+//   double-and-add schedule of jac_mul_ops -- is warp-uniform.  A butterfly with a non-trivial twiddle
+//   costs ~1500 Fp multiplications per lane, one with twiddle 1 costs ~30, and a phase of a batch holds
+//   only 64*B/32 units: per-stage launches leave most SMs idle in every tail.  So the 14 phases run in
+//   ONE persistent kernel: warps pull units from a global ticket counter in (phase, blob group,
+//   butterfly) order; a unit of phase p waits until the 64 units of phase p-1 of ITS blob group are
+//   done (release/acquire counter per (group, phase)).  A unit only ever waits for tickets handed out
+//   before its own, each held by a running warp, so there is no deadlock whatever the residency.
+//   phase 0..6 : inverse DIT stage `ph` (input bit-reversed, written that way by K4).  The last one only
+//                produces the 64 kept outputs (ifft_g1_take_n(.., 64)); the 1/128 is already in the scalars.
+//   phase 7..13: forward DIF stage 13-ph on (h || O^64): the first (stage 6) is h[i] -> (h[i], w^i h[i]).
+//                The output of the last stage is in bit-reversed order = proof order (fk20/prover.rs:222).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_g1_ntt_stage(G1Jac* __restrict__ pts, DevTables T, int B, int st, int mode) {
-    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= 64 * B) return;
-    const int t = gid / B, b = gid - t * B;
+__constant__ uint16_t c_twiddle_ops[128][MULOPS_STRIDE] =
+#include "twiddle_ops.inc"
+    ;
+
+constexpr int NTT_THREADS = 128;
+constexpr int NTT_PHASES = 14;
+
+__device__ __forceinline__ G1Jac ld_pt(const G1Jac* p) {  // L2-coherent: the producer ran on another SM
+    G1Jac r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) d[i] = __ldcg(s + i);
+    return r;
+}
+__device__ __forceinline__ void st_pt(G1Jac* p, const G1Jac& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) __stcg(d + i, s[i]);
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_inc(unsigned* p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+__device__ __noinline__ void g1_ntt_butterfly(G1Jac* __restrict__ pts, int B, int b, int t, int ph) {
+    const int mode = ph >= 7, st = mode ? 13 - ph : ph;
     const int len = 1 << st;
     const int pos = t & (len - 1);
     const int i = ((t >> st) << (st + 1)) + pos, j = i + len;
@@ -238,31 +274,58 @@ k_g1_ntt_stage(G1Jac* __restrict__ pts, DevTables T, int B, int st, int mode) {
     G1Jac* pi = &pts[(size_t)i * B + b];
     G1Jac* pj = &pts[(size_t)j * B + b];
     if (mode == 0) {
-        G1Jac u = ld_vec(pi), v = ld_vec(pj);
-        if (e != 0 && !jac_is_inf(v)) jac_mul_glv16(v, v, T.glv_digits + 66 * ((128 - e) & 127));
+        G1Jac u = ld_pt(pi), v = ld_pt(pj);
+        if (e != 0 && !jac_is_inf(v)) jac_mul_ops(v, v, c_twiddle_ops[(128 - e) & 127]);
         G1Jac s = u;
         jac_add(s, v);
-        st_vec(pi, s);
+        st_pt(pi, s);
         if (st != 6) {
             jac_neg(v, v);
             jac_add(u, v);
-            st_vec(pj, u);
+            st_pt(pj, u);
         }
+    } else if (st == 6) {
+        G1Jac u = ld_pt(pi);
+        if (e != 0 && !jac_is_inf(u)) jac_mul_ops(u, u, c_twiddle_ops[e]);
+        st_pt(pj, u);
     } else {
-        if (st == 6) {
-            G1Jac u = ld_vec(pi);
-            if (e != 0 && !jac_is_inf(u)) jac_mul_glv16(u, u, T.glv_digits + 66 * e);
-            st_vec(pj, u);
-        } else {
-            G1Jac u = ld_vec(pi), v = ld_vec(pj);
-            G1Jac s = u;
-            jac_add(s, v);
-            jac_neg(v, v);
-            jac_add(u, v);
-            if (e != 0 && !jac_is_inf(u)) jac_mul_glv16(u, u, T.glv_digits + 66 * e);
-            st_vec(pi, s);
-            st_vec(pj, u);
+        G1Jac u = ld_pt(pi), v = ld_pt(pj);
+        G1Jac s = u;
+        jac_add(s, v);
+        jac_neg(v, v);
+        jac_add(u, v);
+        if (e != 0 && !jac_is_inf(u)) jac_mul_ops(u, u, c_twiddle_ops[e]);
+        st_pt(pi, s);
+        st_pt(pj, u);
+    }
+}
+
+// queue[0] = ticket counter, queue[1 + g*14 + ph] = finished units of (blob group g, phase ph); zeroed by the launcher
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(NTT_THREADS, MIN_BLOCKS)
+k_fk20_g1_ntts(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned* __restrict__ queue) {
+    const int lane = threadIdx.x & 31;
+    const unsigned per_phase = (unsigned)G * 64u;
+    const unsigned total = (unsigned)(ph1 - ph0) * per_phase;
+    for (;;) {
+        unsigned id = 0;
+        if (lane == 0) id = atomicAdd(&queue[0], 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= total) break;
+        const unsigned rel = id / per_phase, rem = id - rel * per_phase;
+        const int g = (int)(rem >> 6), t = (int)(rem & 63u), ph = ph0 + (int)rel;
+        unsigned* cnt = queue + 1 + (size_t)g * NTT_PHASES;
+        if (rel > 0) {
+            if (lane == 0) {
+                while (ld_acquire_u32(cnt + ph - 1) < 64u) __nanosleep(256);
+            }
+            __syncwarp();
         }
+        const int b = g * 32 + lane;
+        if (b < B) g1_ntt_butterfly(pts, B, b, t, ph);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_inc(cnt + ph);
     }
 }
 
@@ -466,23 +529,39 @@ cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable
     return cudaSuccess;
 }
 
-cudaError_t launch_g1_ntt_stage(G1Jac* pts, const DevTables& T, int B, int stage, int mode, cudaStream_t st) {
-    int n = 64 * B;
-    k_g1_ntt_stage<<<(n + 127) / 128, 128, 0, st>>>(pts, T, B, stage, mode);
+static int g_ntt_sms = 0;
+static int ntt_min_blocks() {
+    static int v = [] { const char* e = getenv("EKZG_NTT_OCC"); int x = e ? atoi(e) : 3; return x < 2 ? 2 : (x > 4 ? 4 : x); }();
+    return v;
+}
+
+size_t g1_ntt_queue_words(int B) { return 1 + (size_t)((B + 31) / 32) * NTT_PHASES; }
+
+// phases [ph0, ph1) of the two transforms over pts[128][B]; queue: g1_ntt_queue_words(B) words of scratch
+cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* queue, cudaStream_t st) {
+    if (!g_ntt_sms) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&g_ntt_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+    }
+    const int G = (B + 31) / 32;
+    cudaError_t e = cudaMemsetAsync(queue, 0, g1_ntt_queue_words(B) * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    const int mb = ntt_min_blocks();
+    const long units = (long)G * 64;                                   // warps that can run at once
+    const int grid = (int)std::min<long>((long)g_ntt_sms * mb, (units + NTT_THREADS / 32 - 1) / (NTT_THREADS / 32));
+    unsigned* q = reinterpret_cast<unsigned*>(queue);
+    if (mb == 2) k_fk20_g1_ntts<2><<<grid, NTT_THREADS, 0, st>>>(pts, B, G, ph0, ph1, q);
+    else if (mb == 3) k_fk20_g1_ntts<3><<<grid, NTT_THREADS, 0, st>>>(pts, B, G, ph0, ph1, q);
+    else k_fk20_g1_ntts<4><<<grid, NTT_THREADS, 0, st>>>(pts, B, G, ph0, ph1, q);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t launch_fk20_g1_ntts(G1Jac* pts, const DevTables& T, int B, cudaStream_t st) {
-    for (int s = 0; s <= 6; s++) {
-        cudaError_t e = launch_g1_ntt_stage(pts, T, B, s, 0, st);
-        if (e != cudaSuccess) return e;
-    }
-    for (int s = 6; s >= 0; s--) {
-        cudaError_t e = launch_g1_ntt_stage(pts, T, B, s, 1, st);
-        if (e != cudaSuccess) return e;
-    }
-    return cudaSuccess;
+cudaError_t launch_fk20_g1_ntts(G1Jac* pts, int B, uint32_t* queue, cudaStream_t st) {
+    return launch_g1_ntt_phases(pts, B, 0, NTT_PHASES, queue, st);
 }
 
 cudaError_t launch_g1_compress(const G1Jac* pts, uint8_t* out, int npos, int B, cudaStream_t st) {
@@ -511,13 +590,12 @@ static cudaError_t fill_table(const G1Jac* pts, const G1Affine* aff, int npoints
 }
 
 cudaError_t launch_fk20_setup(const G1Affine* srs, G1Jac* pts_scratch /*128*64*/, G1Affine* qaff /*8192*nw*/, G1Affine* table,
-                              const DevTables& T, cudaStream_t st) {
+                              const DevTables& T, uint32_t* queue /*g1_ntt_queue_words(64)*/, cudaStream_t st) {
     k_fk20_setup_vectors<<<(128 * 64 + 127) / 128, 128, 0, st>>>(srs, pts_scratch);
     EKZG_LAUNCH_CHECK();
-    for (int s = 6; s >= 0; s--) {
-        cudaError_t e = launch_g1_ntt_stage(pts_scratch, T, 64, s, 1, st);
-        if (e != cudaSuccess) return e;
-    }
+    // F_k = NTT_128(V_k || O^64) for the 64 vectors at once: the forward half of K5 with "blob" := k
+    cudaError_t e = launch_g1_ntt_phases(pts_scratch, 64, 7, NTT_PHASES, queue, st);
+    if (e != cudaSuccess) return e;
     return fill_table(pts_scratch, nullptr, FK20_MSMS * FK20_POINTS, qaff, table, T.fk20, st);
 }
 

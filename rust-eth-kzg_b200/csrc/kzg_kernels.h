@@ -11,12 +11,13 @@ cudaError_t launch_blob_to_coeffs_cells(const uint8_t* blobs, Fr* coeffs, uint8_
 cudaError_t launch_coeffs_to_cells(const Fr* coeffs, uint8_t* cells, const DevTables& T, int B, cudaStream_t st);
 cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st);
 cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st);
-cudaError_t launch_g1_ntt_stage(G1Jac* pts, const DevTables& T, int B, int stage, int mode, cudaStream_t st);
-cudaError_t launch_fk20_g1_ntts(G1Jac* pts, const DevTables& T, int B, cudaStream_t st);
+size_t g1_ntt_queue_words(int B);
+cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* queue, cudaStream_t st);
+cudaError_t launch_fk20_g1_ntts(G1Jac* pts, int B, uint32_t* queue, cudaStream_t st);
 cudaError_t launch_g1_compress(const G1Jac* pts, uint8_t* out, int npos, int B, cudaStream_t st);
 cudaError_t launch_g1_decompress(const uint8_t* in, G1Affine* out, uint32_t* status, int n, cudaStream_t st);
 cudaError_t launch_fk20_setup(const G1Affine* srs, G1Jac* pts_scratch, G1Affine* qaff, G1Affine* table, const DevTables& T,
-                              cudaStream_t st);
+                              uint32_t* queue, cudaStream_t st);
 cudaError_t launch_srs_table_setup(const G1Affine* srs, int npoints, G1Affine* qaff, G1Affine* table, const MsmTable& T, cudaStream_t st);
 
 // kzg_kernels_4844.cu
@@ -49,6 +50,6 @@ cudaError_t launch_poly_eval(const Fr* coeffs, const Fr* z, Fr* y, uint8_t* y_be
 cudaError_t launch_fr_to_be(const Fr* in, uint8_t* out, int n, cudaStream_t st);
 
 // number of kernel launches one compute_cells_and_kzg_proofs batch issues (for bench.py's gpu_launches)
-constexpr int FK20_LAUNCHES_PER_BATCH = 1 /*K1*/ + 1 /*K2*/ + 1 /*K4*/ + 14 /*K5*/ + 1 /*K6*/;
+constexpr int FK20_LAUNCHES_PER_BATCH = 1 /*K1*/ + 1 /*K2*/ + 1 /*K4*/ + 1 /*K5*/ + 1 /*K6*/;
 
 }  // namespace ekzg

@@ -30,6 +30,7 @@ Status Workspace::alloc(int cap, bool with_io) {
     EKZG_CUDA(cudaMalloc(&d_coeffs, (size_t)cap * N_BLOB * sizeof(Fr)));
     EKZG_CUDA(cudaMalloc(&d_scalars, (size_t)cap * FK20_MSMS * FK20_POINTS * 32));
     EKZG_CUDA(cudaMalloc(&d_pts, (size_t)cap * 128 * sizeof(G1Jac)));
+    EKZG_CUDA(cudaMalloc(&d_queue, g1_ntt_queue_words(cap) * sizeof(uint32_t)));
     if (with_io) {
         EKZG_CUDA(cudaMalloc(&d_blobs, (size_t)cap * BYTES_PER_BLOB));
         EKZG_CUDA(cudaMalloc(&d_cells, (size_t)cap * N_EXT * 32));
@@ -63,7 +64,7 @@ Status Workspace::ensure_recover_buffers() {
 void Workspace::release() {
     cudaFree(d_rcells); cudaFreeHost(h_rcells); cudaFree(d_slotmap); cudaFreeHost(h_slotmap); cudaFree(d_ze); cudaFree(d_czinv);
     cudaFree(d_c48); cudaFree(d_z32); cudaFree(d_out48); cudaFree(d_z); cudaFree(d_aff); cudaFree(d_status2);
-    cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_proofs); cudaFree(d_status);
+    cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_queue); cudaFree(d_proofs); cudaFree(d_status);
     cudaFreeHost(h_blobs); cudaFreeHost(h_cells); cudaFreeHost(h_proofs); cudaFreeHost(h_status);
     if (done) cudaEventDestroy(done);
     if (stream) cudaStreamDestroy(stream);
@@ -154,10 +155,6 @@ Status Context::init(bool use_precomp) {
     EKZG_CUDA(launch_powers(sh_inv, fr_coset_gen_inv().v, 8192, st, fr_inv_8192().v));
     coset_shift_fwd_ = sh_fwd;
     coset_shift_inv_ = sh_inv;
-    int8_t* glv;
-    EKZG_TRY(dev_alloc(allocs_, &glv, 128 * 66));
-    EKZG_CUDA(cudaMemcpy(glv, GLV_TWIDDLE_DIGITS_HOST, 128 * 66, cudaMemcpyHostToDevice));
-    T_.glv_digits = glv;
 
     // trusted setup
     const unsigned char* ts = ekzg_trusted_setup_start;
@@ -197,8 +194,11 @@ Status Context::init(bool use_precomp) {
     EKZG_CUDA(cudaMalloc(&scratch, (size_t)128 * 64 * sizeof(G1Jac)));
     EKZG_CUDA(cudaMalloc(&qaff, nbases * sizeof(G1Affine)));
     T_.fk20.table = table;
-    EKZG_CUDA(launch_fk20_setup(T_.srs_g1, scratch, qaff, table, T_, st));
+    uint32_t* setup_queue = nullptr;
+    EKZG_CUDA(cudaMalloc(&setup_queue, g1_ntt_queue_words(64) * sizeof(uint32_t)));
+    EKZG_CUDA(launch_fk20_setup(T_.srs_g1, scratch, qaff, table, T_, setup_queue, st));
     EKZG_CUDA(cudaDeviceSynchronize());
+    cudaFree(setup_queue);
     cudaFree(scratch);
     cudaFree(qaff);
     // monomial SRS tables (commitments, single-point proofs)
@@ -266,7 +266,7 @@ Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells
     if (ev) cudaEventRecord((*ev)[2], stream);
     EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, n, stream));
     if (ev) cudaEventRecord((*ev)[3], stream);
-    EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, T_, n, stream));
+    EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, n, ws.d_queue, stream));
     if (ev) cudaEventRecord((*ev)[4], stream);
     EKZG_CUDA(launch_g1_compress(ws.d_pts, d_proofs, N_CELLS, n, stream));
     if (ev) cudaEventRecord((*ev)[5], stream);

@@ -37,6 +37,7 @@ struct Workspace {
     uint8_t* d_cells = nullptr;
     uint32_t* d_scalars = nullptr;
     G1Jac* d_pts = nullptr;
+    uint32_t* d_queue = nullptr;   // ticket counter + per-(blob group, phase) completion counters of K5
     uint8_t* d_proofs = nullptr;
     uint32_t* d_status = nullptr;
     // small per-blob side buffers of the 4844 path

@@ -67,5 +67,11 @@ int emu_g1_mul_twiddle(const uint8_t* p48, int e, uint8_t* out) {
     jac_dbl(j, j);  // make Z != 1; python accounts for the factor 2
     jac_mul_glv16(r, j, GLV_TWIDDLE_DIGITS_HOST[e]); out48(out, r); return 0;
 }
+int emu_g1_mul_twiddle_ops(const uint8_t* p48, int e, uint8_t* out) {
+    G1Affine p; if (g1a_decompress(p, p48)) return 1;
+    G1Jac j, r; jac_from_affine(j, p);
+    jac_dbl(j, j);  // make Z != 1; python accounts for the factor 2
+    jac_mul_ops(r, j, TWIDDLE_OPS_HOST[e]); out48(out, r); return 0;
+}
 int emu_booth_digit(const uint32_t* s, int t, int w) { return booth_digit(s, t, w); }
 }

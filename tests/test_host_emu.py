@@ -151,6 +151,10 @@ def test_g1_scalar_mul(emu_g1):
     for e in [0, 1, 32, 63, 64, 127]:
         assert emu_g1.emu_g1_mul_twiddle(pb, e, out) == 0
         assert out.raw == pyref.g1_compress(pyref.g1_mul(pt, 2 * pow(w128, e, R) % R)), e
+    # the op-list ladder (common-Z odd-multiples table + width-5 NAF) over every twiddle
+    for e in range(128):
+        assert emu_g1.emu_g1_mul_twiddle_ops(pb, e, out) == 0
+        assert out.raw == pyref.g1_compress(pyref.g1_mul(pt, 2 * pow(w128, e, R) % R)), e
 
 
 def _booth_ref(s, t, w):
