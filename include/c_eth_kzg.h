@@ -137,8 +137,8 @@ CResult eth_kzg_b200_recover_cells_and_kzg_proofs_batch(const DASContext *ctx, u
 int eth_kzg_b200_context_device(const DASContext *ctx);
 int eth_kzg_b200_context_window(const DASContext *ctx);
 uint64_t eth_kzg_b200_context_table_bytes(const DASContext *ctx);
-/* kernel launches issued by one device batch call (for launch accounting in benchmarks) */
-int eth_kzg_b200_launches_per_batch(void);
+/* kernels launched by this library in this process so far (launch accounting in benchmarks) */
+uint64_t eth_kzg_b200_kernel_launch_count(void);
 
 
 /* Per-stage device timing of the FK20 pipeline (CUDA events on the launching stream), for benchmarks.

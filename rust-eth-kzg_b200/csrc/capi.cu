@@ -89,6 +89,7 @@ CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext* ctx, 
     ekzg::Workspace* ws = c.acquire((int)n, false);
     if (!ws) return c_err("device memory allocation failed");
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    cudaStreamWaitEvent(st, ws->done, 0);  // the scratch buffers' previous user may have run on another stream
     s = c.fk20_device(*ws, (int)n, (const uint8_t*)d_blobs, (uint8_t*)d_cells, (uint8_t*)d_proofs, (uint32_t*)d_status, st);
     // the scratch buffers are reused by the next call on this context: order later work after this batch
     if (s.ok) {
@@ -102,7 +103,7 @@ CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext* ctx, 
 int eth_kzg_b200_context_device(const DASContext* ctx) { return cx(ctx).device(); }
 int eth_kzg_b200_context_window(const DASContext* ctx) { return cx(ctx).tables().fk20.w; }
 uint64_t eth_kzg_b200_context_table_bytes(const DASContext* ctx) { return cx(ctx).table_bytes(); }
-int eth_kzg_b200_launches_per_batch(void) { return ekzg::FK20_LAUNCHES_PER_BATCH + 1 /* status memset */; }
+uint64_t eth_kzg_b200_kernel_launch_count(void) { return ekzg::g_kernel_launches.load(); }
 
 void eth_kzg_b200_set_profiling(const DASContext* ctx, bool on) { cx(ctx).set_profiling(on); }
 int eth_kzg_b200_collect_stage_times(const DASContext* ctx, double* ms_out) {

@@ -16,6 +16,8 @@
 
 namespace ekzg {
 
+std::atomic<unsigned long long> g_kernel_launches{0};
+
 __device__ __forceinline__ int rev_bits(int x, int bits) { return (int)(__brev((unsigned)x) >> (32 - bits)); }
 
 // ------------------------------------------------------------------------------------------------
@@ -481,7 +483,6 @@ k_fk20_table_fill(const G1Affine* __restrict__ qaff, G1Affine* __restrict__ tabl
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
-#define EKZG_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
 cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st, const uint32_t* scale_mont) {
     Fr b, sc;
@@ -531,7 +532,7 @@ cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable
 
 static int g_ntt_sms = 0;
 static int ntt_min_blocks() {
-    static int v = [] { const char* e = getenv("EKZG_NTT_OCC"); int x = e ? atoi(e) : 3; return x < 2 ? 2 : (x > 4 ? 4 : x); }();
+    static int v = [] { const char* e = getenv("EKZG_NTT_OCC"); int x = e ? atoi(e) : 2; return x < 2 ? 2 : (x > 4 ? 4 : x); }();
     return v;
 }
 

@@ -1,8 +1,18 @@
 // Host-visible launch wrappers for the kernels in kzg_kernels.cu / kzg_kernels_*.cu.
 #pragma once
+#include <atomic>
 #include "kzg_device.cuh"
 
 namespace ekzg {
+
+// every kernel launch of the library goes through this check; the counter feeds bench.py's gpu_launches
+extern std::atomic<unsigned long long> g_kernel_launches;
+#define EKZG_LAUNCH_CHECK()                                                  \
+    do {                                                                     \
+        ::ekzg::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);   \
+        cudaError_t e_ = cudaGetLastError();                                 \
+        if (e_ != cudaSuccess) return e_;                                    \
+    } while (0)
 
 cudaError_t kernels_init();
 cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_t st, const uint32_t* scale_mont = nullptr);
@@ -49,7 +59,5 @@ cudaError_t launch_kzg_verify_terms(const G1Affine* commitments, const G1Affine*
 cudaError_t launch_poly_eval(const Fr* coeffs, const Fr* z, Fr* y, uint8_t* y_be, int B, cudaStream_t st);
 cudaError_t launch_fr_to_be(const Fr* in, uint8_t* out, int n, cudaStream_t st);
 
-// number of kernel launches one compute_cells_and_kzg_proofs batch issues (for bench.py's gpu_launches)
-constexpr int FK20_LAUNCHES_PER_BATCH = 1 /*K1*/ + 1 /*K2*/ + 1 /*K4*/ + 1 /*K5*/ + 1 /*K6*/;
 
 }  // namespace ekzg

@@ -152,7 +152,6 @@ k_g1_validate(const uint8_t* __restrict__ in, G1Affine* __restrict__ out, uint32
 }
 
 // ------------------------------------------------------------------------------------------------
-#define EKZG_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
 cudaError_t launch_blob_challenge(const uint8_t* blobs, const uint8_t* commitments, Fr* z, int B, cudaStream_t st) {
     k_blob_challenge<<<(B + 31) / 32, 32, 0, st>>>(blobs, commitments, z, B);

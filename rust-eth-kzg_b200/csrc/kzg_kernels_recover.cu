@@ -154,7 +154,6 @@ k_recover_ntt(const uint8_t* __restrict__ cells, const int16_t* __restrict__ slo
     }
 }
 
-#define EKZG_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
 cudaError_t recover_kernels_init() {
     cudaError_t e;

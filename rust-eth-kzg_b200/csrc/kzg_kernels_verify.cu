@@ -272,7 +272,6 @@ __global__ void k_fr_to_be(const Fr* __restrict__ in, uint8_t* __restrict__ out,
     fr_store_be(out + (size_t)i * 32, p);
 }
 
-#define EKZG_LAUNCH_CHECK() do { cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) return e_; } while (0)
 
 cudaError_t launch_powers_from_hash(const uint8_t* hash, Fr* rpow, int n, cudaStream_t st) {
     k_powers_from_hash<<<(n + 127) / 128, 128, 0, st>>>(hash, rpow, n);

@@ -16,7 +16,7 @@ namespace ekzg {
 
 int chunk_capacity() {
     const char* e = getenv("EKZG_CHUNK");
-    int c = e ? atoi(e) : 256;
+    int c = e ? atoi(e) : 1024;
     if (c < 1) c = 1;
     if (c > 4096) c = 4096;
     return c;
@@ -26,7 +26,12 @@ int chunk_capacity() {
 Status Workspace::alloc(int cap, bool with_io) {
     capacity = cap;
     EKZG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    EKZG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     EKZG_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    for (int i = 0; i < MAX_SUB; i++) {
+        EKZG_CUDA(cudaEventCreateWithFlags(&sub_ready[i], cudaEventDisableTiming));
+        EKZG_CUDA(cudaEventCreateWithFlags(&sub_out[i], cudaEventDisableTiming));
+    }
     EKZG_CUDA(cudaMalloc(&d_coeffs, (size_t)cap * N_BLOB * sizeof(Fr)));
     EKZG_CUDA(cudaMalloc(&d_scalars, (size_t)cap * FK20_MSMS * FK20_POINTS * 32));
     EKZG_CUDA(cudaMalloc(&d_pts, (size_t)cap * 128 * sizeof(G1Jac)));
@@ -67,6 +72,11 @@ void Workspace::release() {
     cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_queue); cudaFree(d_proofs); cudaFree(d_status);
     cudaFreeHost(h_blobs); cudaFreeHost(h_cells); cudaFreeHost(h_proofs); cudaFreeHost(h_status);
     if (done) cudaEventDestroy(done);
+    for (int i = 0; i < MAX_SUB; i++) {
+        if (sub_ready[i]) cudaEventDestroy(sub_ready[i]);
+        if (sub_out[i]) cudaEventDestroy(sub_out[i]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -116,9 +126,23 @@ Status Context::init(bool use_precomp) {
     EKZG_CUDA(kernels_init());
     EKZG_CUDA(recover_kernels_init());
 
+    // use_precomp = false (the reference's UsePrecomp::No, fixed_base_msm.rs:83-89): smallest tables.
+    // use_precomp = true: the widest window whose per-window tables fit the free HBM with room for the batch
+    // workspaces -- every extra bit removes additions from the MSM (w = 14: 19 per scalar, 114 GiB of tables).
     int w = 8;
     if (use_precomp) {
-        if (const char* e = getenv("EKZG_FK20_WINDOW")) w = atoi(e);
+        if (const char* e = getenv("EKZG_FK20_WINDOW")) {
+            w = atoi(e);
+        } else {
+            size_t free_b = 0, total_b = 0;
+            EKZG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            const size_t reserve = (size_t)16 << 30;
+            for (int cand : {14, 13, 12, 10, 8}) {
+                w = cand;
+                const size_t need = (size_t)FK20_MSMS * FK20_POINTS * (255 / cand + 1) * ((size_t)1 << (cand - 1)) * sizeof(G1Affine);
+                if (need + reserve <= free_b) break;
+            }
+        }
     }
     if (w < 4 || w > 16) return Status::Error("EKZG_FK20_WINDOW must be in [4, 16]");
     T_.fk20.w = w;
@@ -260,8 +284,8 @@ int Context::collect_stage_times(double* ms) const {
     return n;
 }
 
-Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells*/, uint8_t* d_proofs, cudaStream_t stream) const {
-    std::vector<cudaEvent_t>* ev = (profiling_ && !prof_events_.empty()) ? &prof_events_.back() : nullptr;
+Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells*/, uint8_t* d_proofs, cudaStream_t stream,
+                                        std::vector<cudaEvent_t>* ev) const {
     EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, n, stream));
     if (ev) cudaEventRecord((*ev)[2], stream);
     EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, n, stream));
@@ -285,10 +309,28 @@ Status Context::fk20_device(Workspace& ws, int n, const uint8_t* d_blobs, uint8_
     }
     EKZG_CUDA(launch_blob_to_coeffs_cells(d_blobs, ws.d_coeffs, d_cells, d_status, T_, n, d_cells != nullptr, stream));
     if (profiling_ && d_proofs) cudaEventRecord(prof_events_.back()[1], stream);
-    if (d_proofs) EKZG_TRY(fk20_from_coeffs_device(ws, n, d_cells, d_proofs, stream));
+    if (d_proofs) EKZG_TRY(fk20_from_coeffs_device(ws, n, d_cells, d_proofs, stream, profiling_ ? &prof_events_.back() : nullptr));
     return Status::Ok();
 }
 
+// true if the CUDA driver can DMA straight from/to this host range (cudaMallocHost / cudaHostRegister memory)
+static bool host_range_is_pinned(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// The batch scheduler behind every host-buffer prover entry point (replaces the reference's rayon fan-out,
+// crates/maybe_rayon/src/multi_threaded.rs:9-39).  A chunk (<= EKZG_CHUNK blobs, default 1024) is cut into
+// sub-blocks: sub-block s is copied in and run through K1 while s+1 is still on the wire; its cells go back to the
+// host on a second stream as soon as K1 wrote them, i.e. during the ~100 ms the FK20 kernels (K2..K6, launched
+// once for the whole chunk) need.  Caller buffers that are already pinned are used for the DMA directly; pageable
+// ones go through the workspace's pinned staging, the host copies being hidden the same way.  Chunks alternate
+// between two workspaces so the copies of chunk c+1 overlap the kernels of chunk c.
 Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* blobs, uint8_t* cells, uint8_t* proofs,
                                                    uint8_t* blob_status, bool want_proofs) const {
     if (n == 0) return Status::Ok();
@@ -300,18 +342,28 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
         for (Workspace* w : W) if (w) give_back(w);
         return Status::Error("device/pinned memory allocation failed");
     }
+    const bool in_pinned = host_range_is_pinned(blobs);
+    const bool cells_pinned = cells && host_range_is_pinned(cells);
+    const bool proofs_pinned = want_proofs && host_range_is_pinned(proofs);
+    constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
     bool any_bad = false;
     Status result = Status::Ok();
     uint64_t pending_first[2] = {0, 0};
-    int pending_cnt[2] = {0, 0};
+    int pending_cnt[2] = {0, 0}, pending_sub[2] = {0, 0}, pending_nsub[2] = {0, 0};
     auto drain = [&](int slot) -> Status {
         Workspace& ws = *W[slot];
         if (!pending_cnt[slot]) return Status::Ok();
-        EKZG_CUDA(cudaEventSynchronize(ws.done));
         const uint64_t first = pending_first[slot];
-        const int cnt = pending_cnt[slot];
-        if (cells) memcpy(cells + first * (N_EXT * 32), ws.h_cells, (size_t)cnt * N_EXT * 32);
-        if (want_proofs) memcpy(proofs + first * (N_CELLS * BYTES_PER_G1), ws.h_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1);
+        const int cnt = pending_cnt[slot], sub = pending_sub[slot];
+        if (cells) {
+            for (int s = 0; s < pending_nsub[slot]; s++) {
+                EKZG_CUDA(cudaEventSynchronize(ws.sub_out[s]));
+                const int o = s * sub, c = std::min(sub, cnt - o);
+                if (!cells_pinned) memcpy(cells + (first + o) * CELLS_PER_BLOB, ws.h_cells + (size_t)o * CELLS_PER_BLOB, (size_t)c * CELLS_PER_BLOB);
+            }
+        }
+        EKZG_CUDA(cudaEventSynchronize(ws.done));
+        if (want_proofs && !proofs_pinned) memcpy(proofs + first * PROOFS_PER_BLOB, ws.h_proofs, (size_t)cnt * PROOFS_PER_BLOB);
         for (int i = 0; i < cnt; i++) {
             if (ws.h_status[i]) any_bad = true;
             if (blob_status) blob_status[first + i] = ws.h_status[i] ? 1 : 0;
@@ -319,30 +371,54 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
         pending_cnt[slot] = 0;
         return Status::Ok();
     };
+    auto submit = [&](int slot, uint64_t first, int cnt) -> Status {
+        Workspace& ws = *W[slot];
+        const int nsub = std::min(Workspace::MAX_SUB, (cnt + 63) / 64);
+        const int sub = (cnt + nsub - 1) / nsub;
+        EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * cnt, ws.stream));
+        int used = 0;
+        for (int s = 0; s * sub < cnt; s++, used++) {
+            const int o = s * sub, c = std::min(sub, cnt - o);
+            const uint8_t* src = blobs + (first + o) * BYTES_PER_BLOB;
+            if (!in_pinned) {
+                memcpy(ws.h_blobs + (size_t)o * BYTES_PER_BLOB, src, (size_t)c * BYTES_PER_BLOB);
+                src = ws.h_blobs + (size_t)o * BYTES_PER_BLOB;
+            }
+            EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs + (size_t)o * BYTES_PER_BLOB, src, (size_t)c * BYTES_PER_BLOB, cudaMemcpyHostToDevice, ws.stream));
+            EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs + (size_t)o * BYTES_PER_BLOB, ws.d_coeffs + (size_t)o * N_BLOB,
+                                                  cells ? ws.d_cells + (size_t)o * CELLS_PER_BLOB : nullptr, ws.d_status + o, T_, c, cells != nullptr, ws.stream));
+            if (cells) {
+                EKZG_CUDA(cudaEventRecord(ws.sub_ready[s], ws.stream));
+                EKZG_CUDA(cudaStreamWaitEvent(ws.copy_stream, ws.sub_ready[s], 0));
+                uint8_t* dst = cells_pinned ? cells + (first + o) * CELLS_PER_BLOB : ws.h_cells + (size_t)o * CELLS_PER_BLOB;
+                EKZG_CUDA(cudaMemcpyAsync(dst, ws.d_cells + (size_t)o * CELLS_PER_BLOB, (size_t)c * CELLS_PER_BLOB, cudaMemcpyDeviceToHost, ws.copy_stream));
+                EKZG_CUDA(cudaEventRecord(ws.sub_out[s], ws.copy_stream));
+            }
+        }
+        if (want_proofs) {
+            EKZG_TRY(fk20_from_coeffs_device(ws, cnt, ws.d_cells, ws.d_proofs, ws.stream));
+            EKZG_CUDA(cudaMemcpyAsync(proofs_pinned ? proofs + first * PROOFS_PER_BLOB : ws.h_proofs, ws.d_proofs, (size_t)cnt * PROOFS_PER_BLOB,
+                                      cudaMemcpyDeviceToHost, ws.stream));
+        }
+        EKZG_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ws.stream));
+        EKZG_CUDA(cudaEventRecord(ws.done, ws.stream));
+        pending_first[slot] = first;
+        pending_cnt[slot] = cnt;
+        pending_sub[slot] = sub;
+        pending_nsub[slot] = used;
+        return Status::Ok();
+    };
     for (uint64_t c = 0; c < nchunks && result.ok; c++) {
         const int slot = (int)(c & 1);
-        Workspace& ws = *W[slot];
         result = drain(slot);
         if (!result.ok) break;
         const uint64_t first = c * cap;
-        const int cnt = (int)std::min<uint64_t>(cap, n - first);
-        memcpy(ws.h_blobs, blobs + first * BYTES_PER_BLOB, (size_t)cnt * BYTES_PER_BLOB);
-        cudaError_t e = cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)cnt * BYTES_PER_BLOB, cudaMemcpyHostToDevice, ws.stream);
-        if (e != cudaSuccess) { result = Status::Error(cudaGetErrorString(e)); break; }
-        result = fk20_device(ws, cnt, ws.d_blobs, cells ? ws.d_cells : nullptr, want_proofs ? ws.d_proofs : nullptr, ws.d_status, ws.stream);
-        if (!result.ok) break;
-        if (cells) cudaMemcpyAsync(ws.h_cells, ws.d_cells, (size_t)cnt * N_EXT * 32, cudaMemcpyDeviceToHost, ws.stream);
-        if (want_proofs) cudaMemcpyAsync(ws.h_proofs, ws.d_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1, cudaMemcpyDeviceToHost, ws.stream);
-        cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ws.stream);
-        e = cudaEventRecord(ws.done, ws.stream);
-        if (e != cudaSuccess) { result = Status::Error(cudaGetErrorString(e)); break; }
-        pending_first[slot] = first;
-        pending_cnt[slot] = cnt;
+        result = submit(slot, first, (int)std::min<uint64_t>(cap, n - first));
     }
     for (int slot = 0; slot < 2; slot++) {
         if (!W[slot]) continue;
         if (result.ok) result = drain(slot);
-        else cudaStreamSynchronize(W[slot]->stream);
+        if (!result.ok) { cudaStreamSynchronize(W[slot]->stream); cudaStreamSynchronize(W[slot]->copy_stream); }
         give_back(W[slot]);
     }
     if (!result.ok) return result;

@@ -30,7 +30,11 @@ struct Status {
 struct Workspace {
     int capacity = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // D2H of the cells while the FK20 kernels run on `stream`
     cudaEvent_t done = nullptr;
+    static constexpr int MAX_SUB = 16;           // sub-blocks of a chunk for copy / K1 / copy-out pipelining
+    cudaEvent_t sub_ready[MAX_SUB] = {};         // K1 of sub-block s finished (recorded on `stream`)
+    cudaEvent_t sub_out[MAX_SUB] = {};           // cells of sub-block s are in host memory (recorded on `copy_stream`)
     // device
     uint8_t* d_blobs = nullptr;
     Fr* d_coeffs = nullptr;
@@ -77,7 +81,8 @@ public:
     Status fk20_device(Workspace& ws, int n, const uint8_t* d_blobs, uint8_t* d_cells, uint8_t* d_proofs, uint32_t* d_status,
                        cudaStream_t stream) const;
     // same, starting from coefficients already in ws.d_coeffs (recovery path)
-    Status fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* d_cells, uint8_t* d_proofs, cudaStream_t stream) const;
+    Status fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* d_cells, uint8_t* d_proofs, cudaStream_t stream,
+                                   std::vector<cudaEvent_t>* stage_events = nullptr) const;
 
     // Host buffers, contiguous; chunks the batch through two workspaces.
     Status compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* blobs, uint8_t* cells, uint8_t* proofs,

@@ -50,7 +50,7 @@ def load_library():
     lib.eth_kzg_das_context_free.argtypes = [C.c_void_p]
     lib.eth_kzg_free_error_message.argtypes = [C.c_void_p]
     for name in ("eth_kzg_constant_bytes_per_cell", "eth_kzg_constant_bytes_per_proof", "eth_kzg_constant_cells_per_ext_blob",
-                 "eth_kzg_b200_context_table_bytes"):
+                 "eth_kzg_b200_context_table_bytes", "eth_kzg_b200_kernel_launch_count"):
         getattr(lib, name).restype = C.c_uint64
     lib.eth_kzg_b200_context_table_bytes.argtypes = [C.c_void_p]
     lib.eth_kzg_b200_context_device.argtypes = [C.c_void_p]
