@@ -6,6 +6,8 @@
 using namespace ekzg;
 extern "C" {
 void emu_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fe_mul(z, x, y); memcpy(r, z.v, 48); }
+void emu_fp_sqr(const uint32_t* a, uint32_t* r) { Fp x, z; memcpy(x.v, a, 48); fe_sqr(z, x); memcpy(r, z.v, 48); }
+void emu_fr_sqr(const uint32_t* a, uint32_t* r) { Fr x, z; memcpy(x.v, a, 32); fe_sqr(z, x); memcpy(r, z.v, 32); }
 void emu_fp_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fe_add(z, x, y); memcpy(r, z.v, 48); }
 void emu_fp_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fe_sub(z, x, y); memcpy(r, z.v, 48); }
 void emu_fp_neg(const uint32_t* a, uint32_t* r) { Fp x, z; memcpy(x.v, a, 48); fe_neg(z, x); memcpy(r, z.v, 48); }

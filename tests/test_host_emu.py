@@ -52,6 +52,10 @@ def test_field_ops(emu_field, mod, n, pre):
     edge = [0, 1, 2, mod - 1, mod - 2, Rm % mod, (mod - 1) // 2, (mod + 1) // 2]
     vals = edge + [rng.randrange(mod) for _ in range(200)]
     out = (ctypes.c_uint32 * n)()
+    for a in vals + [rng.randrange(mod) | (1 << 31) | (1 << 63) | (1 << 95) for _ in range(50)] + [mod - 1 - (1 << k) for k in range(0, 32 * n - 4, 7)]:
+        a %= mod
+        getattr(emu_field, "emu_%s_sqr" % pre)(arr(a, n), out)
+        assert val(out) == a * a * Ri % mod, hex(a)
     for a in vals:
         for b in rng.sample(vals, 6) + edge:
             getattr(emu_field, "emu_%s_mul" % pre)(arr(a, n), arr(b, n), out)
