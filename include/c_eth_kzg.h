@@ -157,6 +157,10 @@ CResult eth_kzg_b200_debug_fk20_stages(const DASContext *ctx, const uint8_t *blo
  * all zero = identity); g2_sel[i]: 0 [1]_2, 1 [tau]_2, 2 [tau^64]_2, +3 for the negated point.  Returns 1/0. */
 int eth_kzg_b200_debug_pairing_check(int n, const uint8_t *g1_xy, const int *g2_sel);
 
+/* Test hook (host only): SHA-256 of data[0..n) through the library's transcript hasher (x86 SHA extensions when
+ * present), fed as two updates split at `split`; force_portable != 0 runs the portable C block function instead. */
+void eth_kzg_b200_debug_sha256(const uint8_t *data, uint64_t n, uint64_t split, int force_portable, uint8_t out[32]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,8 @@
 // Host runtime of the B200 KZG backend (see kzg_runtime.h).
 #include "kzg_runtime.h"
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include "fr_consts.cuh"
 
@@ -13,6 +15,23 @@ extern const unsigned char ekzg_trusted_setup_end[];
 }
 
 namespace ekzg {
+
+double TraceClock::now() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+TraceClock::TraceClock(const char* w) : what(w) {
+    static const bool enabled = getenv("EKZG_TRACE") != nullptr;
+    on = enabled;
+    t0 = on ? now() : 0;
+}
+void TraceClock::mark(const char* phase) {
+    if (!on) return;
+    double t = now();
+    fprintf(stderr, "[ekzg trace] %s: %s %.3f ms\n", what, phase, t - t0);
+    t0 = t;
+}
 
 int chunk_capacity() {
     const char* e = getenv("EKZG_CHUNK");

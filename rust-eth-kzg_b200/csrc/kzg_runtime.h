@@ -144,4 +144,15 @@ private:
 
 int chunk_capacity();
 
+// EKZG_TRACE=1: wall-clock marks of the host-side phases on stderr (the reference's optional `tracing` feature,
+// crates/eip7594/Cargo.toml, plays this role there)
+struct TraceClock {
+    bool on;
+    const char* what;
+    double t0;
+    static double now();
+    explicit TraceClock(const char* w);
+    void mark(const char* phase);
+};
+
 }  // namespace ekzg

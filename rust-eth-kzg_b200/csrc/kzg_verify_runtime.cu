@@ -5,6 +5,8 @@
 #include <map>
 #include <string>
 #include "host_pairing.h"
+#include "host_sha256.h"
+#include <unordered_map>
 #include "kzg_runtime.h"
 #include "sha256.cuh"
 
@@ -54,19 +56,26 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
                                             const uint64_t* cell_indices, uint64_t n_cells, const uint8_t* const* cells, uint64_t n_proofs,
                                             const uint8_t* const* proofs, bool* verified) const {
     *verified = false;
+    TraceClock tr("verify_cell_kzg_proof_batch");
     // deduplicate_with_indices (verifier.rs:49-65): first occurrence order is part of the transcript
     std::vector<const uint8_t*> uniq;
     std::vector<uint32_t> rows(n_commitments);
     {
-        std::map<std::string, uint32_t> seen;
+        std::unordered_map<std::string, uint32_t> seen;
+        seen.reserve(256);
+        const uint8_t* last_ptr = nullptr;
+        uint32_t last_row = 0;
         for (uint64_t i = 0; i < n_commitments; i++) {
+            // callers repeat one commitment per cell of a blob (often the very same pointer): skip the lookup then
+            if (last_ptr && (commitments[i] == last_ptr || memcmp(commitments[i], last_ptr, 48) == 0)) { rows[i] = last_row; continue; }
             std::string key(reinterpret_cast<const char*>(commitments[i]), 48);
+            last_ptr = commitments[i];
             auto it = seen.find(key);
             if (it == seen.end()) {
                 it = seen.emplace(key, (uint32_t)uniq.size()).first;
                 uniq.push_back(commitments[i]);
             }
-            rows[i] = it->second;
+            rows[i] = last_row = it->second;
         }
     }
     // validation (verifier.rs:123-164)
@@ -79,14 +88,20 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
     EKZG_TRY(bind_device());
 
     // pack inputs
-    std::vector<uint8_t> hc((size_t)M * 48), hp((size_t)N * 48), hcells((size_t)N * BYTES_PER_CELL);
+    // the ABI hands us one pointer per item (pointer_utils.rs:25-44); when the items happen to be laid out back to
+    // back (the usual case for a caller holding a flat buffer) the gather copy of the 2 KiB cells is skipped
+    bool cells_contig = true;
+    for (int k = 1; k < N && cells_contig; k++) cells_contig = cells[k] == cells[0] + (size_t)k * BYTES_PER_CELL;
+    std::vector<uint8_t> hc((size_t)M * 48), hp((size_t)N * 48), hcells_store(cells_contig ? 0 : (size_t)N * BYTES_PER_CELL);
     std::vector<uint32_t> hcol(N);
     for (int i = 0; i < M; i++) memcpy(&hc[(size_t)i * 48], uniq[i], 48);
     for (int k = 0; k < N; k++) {
         memcpy(&hp[(size_t)k * 48], proofs[k], 48);
-        memcpy(&hcells[(size_t)k * BYTES_PER_CELL], cells[k], BYTES_PER_CELL);
+        if (!cells_contig) memcpy(&hcells_store[(size_t)k * BYTES_PER_CELL], cells[k], BYTES_PER_CELL);
         hcol[k] = (uint32_t)cell_indices[k];
     }
+    const uint8_t* hcells = cells_contig ? cells[0] : hcells_store.data();
+    tr.mark("dedup + pack");
     Workspace* wsp = acquire(1, true);
     if (!wsp) return Status::Error("allocation failed");
     cudaStream_t st = wsp->stream;
@@ -109,7 +124,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_TRY(S.get(&d_interp, (size_t)N * 64)); EKZG_TRY(S.get(&d_mul, std::max(N, 64))); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 4));
             EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
-            EKZG_CUDA(cudaMemcpyAsync(d_cells, hcells.data(), hcells.size(), cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaMemcpyAsync(d_cells, hcells, (size_t)N * BYTES_PER_CELL, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_col, hcol.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_row, rows.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemsetAsync(d_cellst, 0, 4, st));
@@ -117,24 +132,25 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, M, true, st));
             EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, true, st));
             // Fiat-Shamir transcript (fk20/verifier.rs:269-328), sequential SHA-256 on the host
+            tr.mark("alloc + enqueue copies/validation");
             uint8_t hash[32];
             {
-                Sha256 h;
-                sha256_init(h);
+                host::Sha256Stream h;
                 uint8_t head[16 + 32];
                 memcpy(head, "RCKZGCBATCH__V1_", 16);
                 be64(head + 16, N_BLOB); be64(head + 24, CELL_ELEMS); be64(head + 32, (uint64_t)M); be64(head + 40, (uint64_t)N);
-                sha256_update(h, head, sizeof head);
-                sha256_update(h, hc.data(), hc.size());
+                h.update(head, sizeof head);
+                h.update(hc.data(), hc.size());
                 for (int k = 0; k < N; k++) {
                     uint8_t idx[16];
                     be64(idx, rows[k]); be64(idx + 8, hcol[k]);
-                    sha256_update(h, idx, 16);
-                    sha256_update(h, &hcells[(size_t)k * BYTES_PER_CELL], BYTES_PER_CELL);
-                    sha256_update(h, &hp[(size_t)k * 48], 48);
+                    h.update(idx, 16);
+                    h.update(&hcells[(size_t)k * BYTES_PER_CELL], BYTES_PER_CELL);
+                    h.update(&hp[(size_t)k * 48], 48);
                 }
-                sha256_final(h, hash);
+                h.final(hash);
             }
+            tr.mark("transcript sha256");
             EKZG_CUDA(cudaMemcpyAsync(d_hash, hash, 32, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(launch_powers_from_hash(d_hash, d_rpow, N, st));
             EKZG_CUDA(launch_cell_verify_scalars(d_rpow, d_col, d_s1, d_s2, T_, N, st));
@@ -159,6 +175,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_CUDA(cudaMemcpyAsync(stp.data(), d_stp, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
             EKZG_CUDA(cudaMemcpyAsync(&cell_status, d_cellst, 4, cudaMemcpyDeviceToHost, st));
             EKZG_CUDA(cudaStreamSynchronize(st));
+            tr.mark("device work after the hash");
             return Status::Ok();
         };
         result = run();
@@ -171,6 +188,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
     for (uint32_t v : stp) if (v) return Status::Error("Serialization(G1PointInvalid): proof");
     if (cell_status) return Status::Error("Serialization(ScalarNotCanonical): cell");
     *verified = run_pairing(pin, host::G2Sel::Tau64, host::G2Sel::NegGen);
+    tr.mark("pairing");
     return Status::Ok();
 }
 
@@ -237,19 +255,18 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
                     memcpy(zb.data(), z32, zb.size());
                     memcpy(yb.data(), y32, yb.size());
                 }
-                Sha256 h;
-                sha256_init(h);
+                host::Sha256Stream h;
                 uint8_t head[32];
                 memcpy(head, "RCKZGBATCH___V1_", 16);
                 be64(head + 16, N_BLOB); be64(head + 24, (uint64_t)N);
-                sha256_update(h, head, 32);
+                h.update(head, 32);
                 for (int i = 0; i < N; i++) {
-                    sha256_update(h, &hc[(size_t)i * 48], 48);
-                    sha256_update(h, &zb[(size_t)i * 32], 32);
-                    sha256_update(h, &yb[(size_t)i * 32], 32);
-                    sha256_update(h, &hp[(size_t)i * 48], 48);
+                    h.update(&hc[(size_t)i * 48], 48);
+                    h.update(&zb[(size_t)i * 32], 32);
+                    h.update(&yb[(size_t)i * 32], 32);
+                    h.update(&hp[(size_t)i * 48], 48);
                 }
-                sha256_final(h, hash);
+                h.final(hash);
             }
             // N == 1: the only power used is r^0 = 1, whatever the digest
             EKZG_CUDA(cudaMemcpyAsync(d_hash, hash, 32, cudaMemcpyHostToDevice, st));
