@@ -155,7 +155,7 @@ Status Context::init(bool use_precomp) {
         } else {
             size_t free_b = 0, total_b = 0;
             EKZG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            const size_t reserve = (size_t)16 << 30;
+            const size_t reserve = ((size_t)16 << 30) + (size_t)4096 * (255 / 12 + 1) * ((size_t)1 << 11) * sizeof(G1Affine);  // workspaces + SRS tables
             for (int cand : {14, 13, 12, 10, 8}) {
                 w = cand;
                 const size_t need = (size_t)FK20_MSMS * FK20_POINTS * (255 / cand + 1) * ((size_t)1 << (cand - 1)) * sizeof(G1Affine);
@@ -167,7 +167,7 @@ Status Context::init(bool use_precomp) {
     T_.fk20.w = w;
     T_.fk20.nw = 255 / w + 1;
     T_.fk20.half = 1 << (w - 1);
-    int ws = 8;
+    int ws = use_precomp ? 12 : 8;   // w = 12: 17.7 GiB of tables for the 4096 monomial points, 22 additions per scalar
     if (const char* e = getenv("EKZG_SRS_WINDOW")) ws = atoi(e);
     if (ws < 4 || ws > 16) return Status::Error("EKZG_SRS_WINDOW must be in [4, 16]");
     T_.srs.w = ws;
@@ -343,6 +343,23 @@ static bool host_range_is_pinned(const void* p) {
     return a.type == cudaMemoryTypeHost;
 }
 
+// blobs of one chunk -> ws.d_blobs on ws.stream.  Pinned caller memory is DMA'd as it is; pageable memory is copied
+// into the pinned staging buffer in slices, each slice's H2D running while the host copies the next one.
+static Status upload_blobs(Workspace& ws, const uint8_t* src, int cnt, bool src_pinned) {
+    if (src_pinned) {
+        EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs, src, (size_t)cnt * BYTES_PER_BLOB, cudaMemcpyHostToDevice, ws.stream));
+        return Status::Ok();
+    }
+    const int slice = 64;
+    for (int o = 0; o < cnt; o += slice) {
+        const int c = std::min(slice, cnt - o);
+        memcpy(ws.h_blobs + (size_t)o * BYTES_PER_BLOB, src + (size_t)o * BYTES_PER_BLOB, (size_t)c * BYTES_PER_BLOB);
+        EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs + (size_t)o * BYTES_PER_BLOB, ws.h_blobs + (size_t)o * BYTES_PER_BLOB, (size_t)c * BYTES_PER_BLOB,
+                                  cudaMemcpyHostToDevice, ws.stream));
+    }
+    return Status::Ok();
+}
+
 // The batch scheduler behind every host-buffer prover entry point (replaces the reference's rayon fan-out,
 // crates/maybe_rayon/src/multi_threaded.rs:9-39).  A chunk (<= EKZG_CHUNK blobs, default 1024) is cut into
 // sub-blocks: sub-block s is copied in and run through K1 while s+1 is still on the wire; its cells go back to the
@@ -483,37 +500,54 @@ Status Context::recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* c
     Workspace& ws = *wsp;
     Status result = ws.ensure_recover_buffers();
     cudaStream_t st = ws.stream;
-    std::vector<uint32_t> hs(cap);
+    const bool in_pinned = host_range_is_pinned(cells), cells_pinned = host_range_is_pinned(out_cells), proofs_pinned = host_range_is_pinned(out_proofs);
+    constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
+    TraceClock tr("recover_cells_and_kzg_proofs_batch");
     auto body = [&](uint64_t first, int cnt) -> Status {
+        // slot maps (which input cell sits at which bit-reversed position) and the cells themselves: blob i's cells go
+        // to slots 0..count-1 of its 128-slot row on the device, straight from the caller's memory when it is pinned
         for (int i = 0; i < cnt; i++) {
             int16_t* sm = ws.h_slotmap + (size_t)i * 128;
-            uint8_t* dstc = ws.h_rcells + (size_t)i * N_CELLS * BYTES_PER_CELL;
             const uint64_t g = first + i;
+            uint8_t* d_row = ws.d_rcells + (size_t)i * N_CELLS * BYTES_PER_CELL;
             if (code[g]) {  // give the device a harmless well-formed instance: all cells present, all zero
                 for (int m = 0; m < 128; m++) sm[m] = (int16_t)m;
-                memset(dstc, 0, (size_t)N_CELLS * BYTES_PER_CELL);
+                EKZG_CUDA(cudaMemsetAsync(d_row, 0, (size_t)N_CELLS * BYTES_PER_CELL, st));
                 continue;
             }
             for (int m = 0; m < 128; m++) sm[m] = -1;
-            for (uint64_t k = 0; k < counts[g]; k++) {
-                sm[rev7((int)indices[offset[g] + k])] = (int16_t)k;
-                memcpy(dstc + k * BYTES_PER_CELL, cells + (offset[g] + k) * BYTES_PER_CELL, BYTES_PER_CELL);
+            for (uint64_t k = 0; k < counts[g]; k++) sm[rev7((int)indices[offset[g] + k])] = (int16_t)k;
+            const uint8_t* src = cells + offset[g] * BYTES_PER_CELL;
+            const size_t bytes = (size_t)counts[g] * BYTES_PER_CELL;
+            if (!in_pinned) {
+                uint8_t* stage = ws.h_rcells + (size_t)i * N_CELLS * BYTES_PER_CELL;
+                memcpy(stage, src, bytes);
+                src = stage;
             }
+            EKZG_CUDA(cudaMemcpyAsync(d_row, src, bytes, cudaMemcpyHostToDevice, st));
         }
-        EKZG_CUDA(cudaMemcpyAsync(ws.d_rcells, ws.h_rcells, (size_t)cnt * N_CELLS * BYTES_PER_CELL, cudaMemcpyHostToDevice, st));
+        tr.mark("slot maps + enqueue H2D of the cells");
         EKZG_CUDA(cudaMemcpyAsync(ws.d_slotmap, ws.h_slotmap, (size_t)cnt * 128 * sizeof(int16_t), cudaMemcpyHostToDevice, st));
         EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * cnt, st));
         EKZG_CUDA(launch_recover_coeffs(ws.d_rcells, ws.d_slotmap, ws.d_ze, ws.d_czinv, reinterpret_cast<Fr*>(ws.d_scalars),
                                         reinterpret_cast<Fr*>(ws.d_cells), ws.d_coeffs, ws.d_status, T_, coset_shift_fwd_, coset_shift_inv_,
                                         fr_coset_gen_pow64().v, cnt, st));
         EKZG_CUDA(launch_coeffs_to_cells(ws.d_coeffs, ws.d_cells, T_, cnt, st));
+        // the cells travel back on the copy stream while the FK20 kernels run
+        EKZG_CUDA(cudaEventRecord(ws.sub_ready[0], st));
+        EKZG_CUDA(cudaStreamWaitEvent(ws.copy_stream, ws.sub_ready[0], 0));
+        EKZG_CUDA(cudaMemcpyAsync(cells_pinned ? out_cells + first * CELLS_PER_BLOB : ws.h_cells, ws.d_cells, (size_t)cnt * CELLS_PER_BLOB,
+                                  cudaMemcpyDeviceToHost, ws.copy_stream));
+        EKZG_CUDA(cudaEventRecord(ws.sub_out[0], ws.copy_stream));
         EKZG_TRY(fk20_from_coeffs_device(ws, cnt, ws.d_cells, ws.d_proofs, st));
-        EKZG_CUDA(cudaMemcpyAsync(ws.h_cells, ws.d_cells, (size_t)cnt * N_EXT * 32, cudaMemcpyDeviceToHost, st));
-        EKZG_CUDA(cudaMemcpyAsync(ws.h_proofs, ws.d_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaMemcpyAsync(proofs_pinned ? out_proofs + first * PROOFS_PER_BLOB : ws.h_proofs, ws.d_proofs, (size_t)cnt * PROOFS_PER_BLOB,
+                                  cudaMemcpyDeviceToHost, st));
         EKZG_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
+        EKZG_CUDA(cudaEventSynchronize(ws.sub_out[0]));
+        if (!cells_pinned) memcpy(out_cells + first * CELLS_PER_BLOB, ws.h_cells, (size_t)cnt * CELLS_PER_BLOB);
         EKZG_CUDA(cudaStreamSynchronize(st));
-        memcpy(out_cells + first * (N_EXT * 32), ws.h_cells, (size_t)cnt * N_EXT * 32);
-        memcpy(out_proofs + first * (N_CELLS * BYTES_PER_G1), ws.h_proofs, (size_t)cnt * N_CELLS * BYTES_PER_G1);
+        tr.mark("recovery kernels + FK20 + copies");
+        if (!proofs_pinned) memcpy(out_proofs + first * PROOFS_PER_BLOB, ws.h_proofs, (size_t)cnt * PROOFS_PER_BLOB);
         for (int i = 0; i < cnt; i++) {
             const uint64_t g = first + i;
             if (!code[g] && ws.h_status[i]) {
@@ -526,7 +560,7 @@ Status Context::recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* c
         return Status::Ok();
     };
     for (uint64_t first = 0; first < n && result.ok; first += cap) result = body(first, (int)std::min<uint64_t>(cap, n - first));
-    if (!result.ok) cudaStreamSynchronize(st);
+    if (!result.ok) { cudaStreamSynchronize(st); cudaStreamSynchronize(ws.copy_stream); }
     give_back(wsp);
     if (item_status) memcpy(item_status, code.data(), n);
     if (!result.ok) return result;
@@ -548,9 +582,11 @@ Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const 
     bool bad_blob = false, bad_aux = false;
     Status result = Status::Ok();
     std::vector<uint32_t> hs(cap), hs2(cap);
+    TraceClock tr(mode == Mode4844::Commit ? "blob_to_kzg_commitment_batch" : "compute_(blob_)kzg_proof_batch");
+    const bool in_pinned = host_range_is_pinned(blobs);
     auto body = [&](uint64_t first, int cnt) -> Status {
-        memcpy(ws.h_blobs, blobs + first * BYTES_PER_BLOB, (size_t)cnt * BYTES_PER_BLOB);
-        EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)cnt * BYTES_PER_BLOB, cudaMemcpyHostToDevice, st));
+        EKZG_TRY(upload_blobs(ws, blobs + first * BYTES_PER_BLOB, cnt, in_pinned));
+        tr.mark("stage + enqueue H2D of the blobs");
         EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * cnt, st));
         EKZG_CUDA(cudaMemsetAsync(ws.d_status2, 0, sizeof(uint32_t) * cnt, st));
         EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs, ws.d_coeffs, nullptr, ws.d_status, T_, cnt, false, st));
@@ -575,6 +611,7 @@ Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const 
         EKZG_CUDA(cudaMemcpyAsync(hs.data(), ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
         EKZG_CUDA(cudaMemcpyAsync(hs2.data(), ws.d_status2, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
         EKZG_CUDA(cudaStreamSynchronize(st));
+        tr.mark("H2D + kernels + D2H");
         for (int i = 0; i < cnt; i++) {
             uint8_t code = hs[i] ? 1 : (hs2[i] ? 2 : 0);
             if (code == 1) bad_blob = true;
