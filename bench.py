@@ -30,11 +30,44 @@ CELLS_BYTES = 128 * 2048
 PROOFS_BYTES = 128 * 48
 METRIC = "blobs/sec compute_cells_and_kzg_proofs"
 
-# Work model of OUR algorithm per blob, used for the integer-issue roofline:
-#   K4: 128*64 scalars * nw windows table additions, XYZZ mixed add = 10 Fp mul
-#   K5: 642 scalar multiplications by 128th roots of unity (GLV, 132 dbl*7 + ~66 add*16 + table 76 + endo) + 1664 point adds
-FP_MUL_IMAD = 300          # IMAD.WIDE(.X) instructions per 12-limb Montgomery multiplication (12*(2*12+1))
-IMAD_WIDE_PEAK = 9.13e12   # measured on this pool's B200 by tools/gpu_probe.cu (carry-chained IMAD.WIDE, all SMs)
+# Work model of OUR algorithm per blob, in integer multiply-adds on the fmaheavy pipe (what ncu reports as
+# sm__pipe_fmaheavy_cycles_active): one 12-limb Montgomery multiplication = 12*(12+12+1) = 300 IMAD.WIDE, one dedicated
+# squaring = 78 + 12*13 = 234.
+IMAD_MUL, IMAD_SQR = 300, 234
+IMAD_WIDE_PEAK = 9.13e12   # measured on this pool's B200 by tools/gpu_probe.cu (carry-chained IMAD.WIDE, all SMs, 1965 MHz)
+OP_XYZZ_MADD = 8 * IMAD_MUL + 2 * IMAD_SQR          # K4: one table entry into an XYZZ accumulator
+OP_JAC_DBL = 2 * IMAD_MUL + 5 * IMAD_SQR
+OP_JAC_MADD = 7 * IMAD_MUL + 4 * IMAD_SQR
+OP_JAC_ADD = 11 * IMAD_MUL + 5 * IMAD_SQR
+OP_MADD_ZR = 8 * IMAD_MUL + 3 * IMAD_SQR
+
+
+def k5_imad_per_blob():
+    """exact multiply-add count of the two G1 NTTs of one blob: walks the same (phase, butterfly) list as
+    k_fk20_g1_ntts and the op lists of rust-eth-kzg_b200/csrc/twiddle_ops.inc"""
+    rows = []
+    for ln in open(os.path.join(ROOT, "rust-eth-kzg_b200", "csrc", "twiddle_ops.inc")):
+        ln = ln.strip()
+        if ln.startswith("{") and len(ln) > 2:
+            v = [int(x) for x in ln.strip("{},").split(",")]
+            rows.append(v[1:1 + v[0]])
+    assert len(rows) == 128
+    table = OP_JAC_DBL + (3 * IMAD_MUL + IMAD_SQR) + 7 * OP_MADD_ZR + (27 * IMAD_MUL + 7 * IMAD_SQR) + 8 * IMAD_MUL + 2 * IMAD_MUL
+    ladder = [sum((op >> 8) * OP_JAC_DBL + (OP_JAC_MADD if op & 0x20 else 0) for op in r) for r in rows]
+    total = heavy = 0
+    for ph in range(14):
+        mode, st = (1, 13 - ph) if ph >= 7 else (0, ph)
+        for t in range(64):
+            e = (t & ((1 << st) - 1)) << (6 - st)
+            tw = (128 - e) & 127 if mode == 0 else e
+            if e:
+                total += table + ladder[tw]
+                heavy += 1
+            if mode == 0:
+                total += OP_JAC_ADD * (1 if st == 6 else 2)
+            elif st != 6:
+                total += 2 * OP_JAC_ADD
+    return total, heavy
 
 
 def synth_blobs(n, first=0):
@@ -253,17 +286,19 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = msm_bytes / (msm_ms / 1000) / 1e9 if msm_ms else 0.0
-    msm_mul = n * 128 * 64 * nw * 10
-    ntt_mul = n * (642 * (132 * 7 + 66 * 16 + 76 + 33) + 1664 * 16)
+    msm_imad = n * 128 * 64 * nw * OP_XYZZ_MADD
+    k5_imad, k5_heavy = k5_imad_per_blob()
+    ntt_imad = n * k5_imad
     roofline = {"bound": "hbm", "kernel": "k_fk20_msm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                "note": "table gathers are L2/HBM-trivial; the kernel is integer-issue bound, see roofline_imad"}
+                "traffic": 26.75e9 * n / 1024 if w == 14 else None, "traffic_source": "ncu --set full, dram__bytes_read+write per launch at 1024 blobs, w=14 (profiles/r1_v2_prof_k4_k5_raw.csv)",
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "note": "HBM view of the table-streaming MSM: the gathers are far below the HBM roofline; the kernel is bound by the integer multiply (fmaheavy) pipe, see roofline_imad"}
     roofline_imad = {
-        "bound": "imad", "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE/s", "peak_source": "tools/gpu_probe.cu carry-chain microbenchmark on this pool",
-        "k_fk20_msm": {"fp_mul_per_launch": msm_mul, "achieved": msm_mul * FP_MUL_IMAD / (msm_ms / 1000) / 1e12 if msm_ms else 0.0},
-        "k_g1_ntt_stage(x14)": {"fp_mul_per_batch": ntt_mul, "achieved": ntt_mul * FP_MUL_IMAD / (stages["K5_g1_ntt"] / 1000) / 1e12 if stages["K5_g1_ntt"] else 0.0},
+        "bound": "imad (fmaheavy pipe)", "peak": IMAD_WIDE_PEAK / 1e12, "unit": "T IMAD.WIDE/s", "peak_source": "tools/gpu_probe.cu carry-chain microbenchmark on this pool (profiles/r1_gpu_probe.json)",
+        "k_fk20_msm": {"imad_per_launch": msm_imad, "achieved": msm_imad / (msm_ms / 1000) / 1e12 if msm_ms else 0.0},
+        "k_fk20_g1_ntts": {"imad_per_launch": ntt_imad, "scalar_muls_per_blob": k5_heavy, "achieved": ntt_imad / (stages["K5_g1_ntt"] / 1000) / 1e12 if stages["K5_g1_ntt"] else 0.0},
     }
-    for k in ("k_fk20_msm", "k_g1_ntt_stage(x14)"):
+    for k in ("k_fk20_msm", "k_fk20_g1_ntts"):
         roofline_imad[k]["frac"] = roofline_imad[k]["achieved"] * 1e12 / IMAD_WIDE_PEAK
     line = {
         "metric": METRIC, "value": value, "unit": "blobs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
