@@ -126,11 +126,19 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """all host threads this process may use -- NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(sample_blobs, threads=0):
     """the oracle port (oracle/src/kzg.c, the reference's algorithm restated in C + OpenMP) on the host cores"""
     from oracle import cref
     cref.build()
-    nthreads = threads or cref.num_threads()
+    nthreads = threads or host_threads()
     blobs = synth_blobs(sample_blobs)
     cref.compute_cells_and_kzg_proofs_batch(blobs[:BYTES_PER_BLOB * min(2, sample_blobs)], min(2, sample_blobs), nthreads)  # builds tables
     t0 = time.perf_counter()
@@ -145,7 +153,7 @@ def run_reference(args, rank, world):
         return
     from oracle import cref
     cref.build()
-    cores = cref.num_threads()
+    cores = host_threads()
     sample = max(cores, 8) * 2          # blobs per step: bounded sample of the 1024-blob workload
     blobs = synth_blobs(sample)
     cref.compute_cells_and_kzg_proofs_batch(blobs[:BYTES_PER_BLOB], 1, cores)
