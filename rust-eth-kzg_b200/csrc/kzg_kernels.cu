@@ -367,6 +367,55 @@ k_g1_compress(const G1Jac* __restrict__ pts, uint8_t* __restrict__ out, int npos
     }
 }
 
+// Same, CH consecutive positions of one blob per thread sharing ONE inversion (Montgomery's trick, the device twin of
+// the reference's shared inversion in g1_batch_normalize): 460/CH + 3 multiplications per point instead of 460.
+// Identities (z = 0) are kept out of the product and re-inserted, like the reference does (lib.rs:60-76).
+constexpr int K6_CH = 8;
+__global__ void __launch_bounds__(128)
+k_g1_compress_batched(const G1Jac* __restrict__ pts, uint8_t* __restrict__ out, int npos, int B) {
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nch = npos / K6_CH;
+    if (gid >= nch * B) return;
+    const int ch = gid / B, b = gid - ch * B;
+    const int p0 = ch * K6_CH;
+    Fp prefix[K6_CH];
+    Fp run;
+    fe_set_one(run);
+#pragma unroll 1
+    for (int i = 0; i < K6_CH; i++) {
+        Fp z = ld_vec(&pts[(size_t)(p0 + i) * B + b].z);
+        prefix[i] = run;
+        if (!fe_is_zero(z)) fe_mul(run, run, z);
+    }
+    Fp inv;
+    fp_inv(inv, run);
+#pragma unroll 1
+    for (int i = K6_CH - 1; i >= 0; i--) {
+        G1Jac q = ld_vec(&pts[(size_t)(p0 + i) * B + b]);
+        G1Affine a;
+        if (jac_is_inf(q)) {
+            g1a_set_inf(a);
+        } else {
+            Fp zi;
+            fe_mul(zi, inv, prefix[i]);
+            fe_mul(inv, inv, q.z);
+            jac_to_affine_with_inv(a, q, zi);
+        }
+        uint8_t buf[48];
+        g1a_compress(buf, a);
+        uint4* d4 = reinterpret_cast<uint4*>(out + ((size_t)b * npos + p0 + i) * BYTES_PER_G1);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            uint4 v;
+            v.x = buf[16 * c + 0] | (buf[16 * c + 1] << 8) | (buf[16 * c + 2] << 16) | ((uint32_t)buf[16 * c + 3] << 24);
+            v.y = buf[16 * c + 4] | (buf[16 * c + 5] << 8) | (buf[16 * c + 6] << 16) | ((uint32_t)buf[16 * c + 7] << 24);
+            v.z = buf[16 * c + 8] | (buf[16 * c + 9] << 8) | (buf[16 * c + 10] << 16) | ((uint32_t)buf[16 * c + 11] << 24);
+            v.w = buf[16 * c + 12] | (buf[16 * c + 13] << 8) | (buf[16 * c + 14] << 16) | ((uint32_t)buf[16 * c + 15] << 24);
+            d4[c] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // setup kernels
 // ------------------------------------------------------------------------------------------------
@@ -567,7 +616,12 @@ cudaError_t launch_fk20_g1_ntts(G1Jac* pts, int B, uint32_t* queue, cudaStream_t
 
 cudaError_t launch_g1_compress(const G1Jac* pts, uint8_t* out, int npos, int B, cudaStream_t st) {
     int n = npos * B;
-    k_g1_compress<<<(n + 127) / 128, 128, 0, st>>>(pts, out, npos, B);
+    if (npos % K6_CH == 0 && n >= 32768) {   // below that both variants are latency-bound
+        n /= K6_CH;
+        k_g1_compress_batched<<<(n + 127) / 128, 128, 0, st>>>(pts, out, npos, B);
+    } else {
+        k_g1_compress<<<(n + 127) / 128, 128, 0, st>>>(pts, out, npos, B);
+    }
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -95,7 +95,7 @@ def test_full_size_batch_properties(das_ctx, pkg):
     matter); results equal the single-blob ABI on sampled blobs; checksum is stable across chunkings."""
     syn = _synth(pkg)
     n = 1024
-    base = [syn.blob(i) for i in range(64)]
+    base = syn.edge_blobs() + [syn.blob(i) for i in range(60)]   # zero, all r-1, constant (identity proofs), dummy_blob first
     blobs = [base[(i * 37) % 64] for i in range(n)]
     cells, proofs, status = das_ctx.compute_cells_and_kzg_proofs_batch(b"".join(blobs), n)
     assert status == [0] * n
@@ -109,6 +109,7 @@ def test_full_size_batch_properties(das_ctx, pkg):
             assert first[key] == (hashlib.sha256(c).digest(), p), "blob %d differs from its duplicate" % i
         else:
             first[key] = (hashlib.sha256(c).digest(), p)
-    for key in (0, 17, 63):
+    assert first[2][1] == (b"\xc0" + bytes(47)) * 128
+    for key in (0, 1, 2, 3, 17, 63):
         c1, p1 = das_ctx.compute_cells_and_kzg_proofs(base[key])
         assert first[key] == (hashlib.sha256(b"".join(c1)).digest(), b"".join(p1))
