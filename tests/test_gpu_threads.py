@@ -1,0 +1,73 @@
+"""Re-entrancy of the C ABI on ONE shared DASContext (SURVEY.md §8b "Threading": the reference's context is immutable and
+its bindings call it from thread pools -- bindings/node/src/lib.rs:92-130).  ctypes releases the GIL during the calls,
+so these host threads really are concurrently inside the library."""
+import threading
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _synth(pkg):
+    import importlib
+    return importlib.import_module("eth_kzg_b200.synthetic")
+
+
+def test_concurrent_callers_share_one_context(das_ctx, pkg):
+    syn = _synth(pkg)
+    blobs = [syn.blob(100 + i) for i in range(6)]
+    # serial ground truth
+    want = []
+    for b in blobs:
+        cells, proofs = das_ctx.compute_cells_and_kzg_proofs(b)
+        c = das_ctx.blob_to_kzg_commitment(b)
+        p = das_ctx.compute_blob_kzg_proof(b, c)
+        want.append((cells, proofs, c, p))
+    errors = []
+
+    def worker(tid):
+        try:
+            for rep in range(3):
+                for k in range(len(blobs)):
+                    i = (k + tid) % len(blobs)
+                    b = blobs[i]
+                    cells, proofs = das_ctx.compute_cells_and_kzg_proofs(b)
+                    assert (cells, proofs) == want[i][:2]
+                    assert das_ctx.blob_to_kzg_commitment(b) == want[i][2]
+                    assert das_ctx.compute_blob_kzg_proof(b, want[i][2]) == want[i][3]
+                    assert das_ctx.verify_blob_kzg_proof(b, want[i][2], want[i][3]) is True
+                    idx = list(range(tid % 2, 128, 2))
+                    rc, rp = das_ctx.recover_cells_and_kzg_proofs(idx, [cells[j] for j in idx])
+                    assert (rc, rp) == want[i][:2]
+                    assert das_ctx.verify_cell_kzg_proof_batch([want[i][2]] * 4, [0, 5, 64, 127], [cells[j] for j in (0, 5, 64, 127)],
+                                                               [proofs[j] for j in (0, 5, 64, 127)]) is True
+        except Exception as ex:  # noqa: BLE001 - surfaced below
+            errors.append((tid, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+        assert not t.is_alive(), "a caller thread hung"
+    assert not errors, errors
+
+
+def test_concurrent_batches(das_ctx, pkg):
+    """two host threads each pushing a multi-chunk-sized batch through the scheduler at once"""
+    syn = _synth(pkg)
+    n = 96
+    flat = [b"".join(syn.blob(1000 * t + i) for i in range(n)) for t in range(2)]
+    want = [das_ctx.compute_cells_and_kzg_proofs_batch(f, n) for f in flat]
+    got = [None, None]
+
+    def worker(t):
+        got[t] = das_ctx.compute_cells_and_kzg_proofs_batch(flat[t], n)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+        assert not t.is_alive()
+    assert got == want
