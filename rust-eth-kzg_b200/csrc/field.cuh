@@ -103,6 +103,84 @@ EKZG_HD void fe_mul_inline(Fe<P>& out, const Fe<P>& a_, const Fe<P>& b_) {
     for (int j = 0; j < N; j++) out.v[j] = r[j];
 }
 
+// out = a*b + c*d with ONE Montgomery reduction (444 instead of 600 multiply-adds for Fp): every row adds both
+// partial products before its reduction step.  The running sum stays below 3p*2^32 + 3p, so the same headroom
+// argument as for fe_sqr_inline applies (Fp only); the result is below (2p^2 + pR)/R < 2p, one final subtraction.
+// Point formulas use it for  y3 = r*(v - x3) - y1*j  with the second product's factor negated beforehand.
+template <class P>
+EKZG_HD void fe_mul2_inline(Fe<P>& out, const Fe<P>& a_, const Fe<P>& b_, const Fe<P>& c_, const Fe<P>& d_) {
+    constexpr int N = P::N;
+    static_assert(N % 2 == 0, "even limb count");
+    const uint32_t* a = a_.v;
+    const uint32_t* b = b_.v;
+    const uint32_t* c = c_.v;
+    const uint32_t* d = d_.v;
+    uint32_t ev[N], od[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        uint32_t* x = (i & 1) ? od : ev;
+        uint32_t* y = (i & 1) ? ev : od;
+        const uint32_t bi = b[i], di = d[i];
+        if (i == 0) {
+#pragma unroll
+            for (int j = 0; j < N; j += 2) {
+                x[j] = mul_lo(a[j], bi);
+                x[j + 1] = mul_hi(a[j], bi);
+                y[j] = mul_lo(a[j + 1], bi);
+                y[j + 1] = mul_hi(a[j + 1], bi);
+            }
+        } else {
+            x[0] = add_cc(x[0], y[1]);
+#pragma unroll
+            for (int j = 1; j < N - 1; j += 2) {
+                y[j - 1] = madc_lo_cc(a[j], bi, y[j + 1]);
+                y[j] = madc_hi_cc(a[j], bi, y[j + 2]);
+            }
+            y[N - 2] = madc_lo_cc(a[N - 1], bi, 0u);
+            y[N - 1] = madc_hi(a[N - 1], bi, 0u);
+            x[0] = mad_lo_cc(a[0], bi, x[0]);
+            x[1] = madc_hi_cc(a[0], bi, x[1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                x[j] = madc_lo_cc(a[j], bi, x[j]);
+                x[j + 1] = madc_hi_cc(a[j], bi, x[j + 1]);
+            }
+            y[N - 1] = addc(y[N - 1], 0u);
+        }
+        // second partial product, then the Montgomery step: both add in place (no shift)
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+            const uint32_t m = pass ? mul_lo(x[0], P::M0) : di;
+            auto f = [&](int k) -> uint32_t { return pass ? P::mod(k) : c[k]; };
+            y[0] = mad_lo_cc(f(1), m, y[0]);
+            y[1] = madc_hi_cc(f(1), m, y[1]);
+#pragma unroll
+            for (int j = 3; j < N; j += 2) {
+                y[j - 1] = madc_lo_cc(f(j), m, y[j - 1]);
+                y[j] = madc_hi_cc(f(j), m, y[j]);
+            }
+            x[0] = mad_lo_cc(f(0), m, x[0]);
+            x[1] = madc_hi_cc(f(0), m, x[1]);
+#pragma unroll
+            for (int j = 2; j < N; j += 2) {
+                x[j] = madc_lo_cc(f(j), m, x[j]);
+                x[j + 1] = madc_hi_cc(f(j), m, x[j + 1]);
+            }
+            y[N - 1] = addc(y[N - 1], 0u);
+        }
+    }
+    uint32_t* x = od;
+    uint32_t* y = ev;
+    uint32_t r[N];
+    r[0] = add_cc(x[1], y[0]);
+#pragma unroll
+    for (int j = 1; j < N - 1; j++) r[j] = addc_cc(x[j + 1], y[j]);
+    r[N - 1] = addc(y[N - 1], 0u);
+    fe_final_sub<P>(r);
+#pragma unroll
+    for (int j = 0; j < N; j++) out.v[j] = r[j];
+}
+
 // Squaring: row i multiplies a_i into  S_i = a_i*2^(32i) + 2*(a >> 32(i+1)) << 32(i+1)  instead of into all of a,
 // so every cross product a_i*a_k (k > i) is computed once, already doubled: sum_i a_i * S_i = a^2.
 // The limbs of S_i are a_i, then (a_(i+1) << 1), then the limbs of 2a -- plain register values, no fix-ups.
@@ -209,6 +287,22 @@ static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) {
     return r;
 }
 #endif
+
+#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
+static __device__ __noinline__ Fp fp_mul2_call(Fp a, Fp b, Fp c, Fp d) {
+    Fp r;
+    fe_mul2_inline(r, a, b, c, d);
+    return r;
+}
+#endif
+// out = a*b + c*d  (Fp only, see fe_mul2_inline)
+EKZG_HD void fp_mul2_add(Fp& out, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
+    out = fp_mul2_call(a, b, c, d);
+#else
+    fe_mul2_inline(out, a, b, c, d);
+#endif
+}
 
 template <class P>
 EKZG_HD void fe_mul(Fe<P>& out, const Fe<P>& a, const Fe<P>& b) {

@@ -4,8 +4,11 @@
 // (crates/cryptography/bls12_381/src/lib.rs:23-42) and the reference's own batched-affine adder
 // (crates/cryptography/bls12_381/src/batch_addition.rs:14-39).  Only the final compressed bytes are
 // pinned by the consensus vectors, so the coordinate systems are chosen for the GPU:
-//   * XYZZ (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2) for accumulating table entries: mixed add 8M+2S;
-//   * Jacobian for doubling-heavy scalar multiplication in the G1 NTT: doubling 2M+5S.
+//   * XYZZ (x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2) for accumulating table entries: mixed add 8M+2S, of which the two
+//     products of  y3 = R*(Q - X3) - Y1*PPP  share one Montgomery reduction (fp_mul2_add);
+//   * Jacobian for doubling-heavy scalar multiplication in the G1 NTT: doubling 2M+5S.  The Jacobian formulas keep
+//     to the two subroutines fp_mul / fp_sqr: a third one (fp_mul2_add) pushed K5's hot code past the 32 KB
+//     instruction cache and cost more than the saved reduction (measured: 34.8 -> 35.4 ms).
 // All adders are COMPLETE: identity operands, P+P and P+(-P) are detected and handled, because a
 // constant blob makes every proof the identity (SURVEY.md §7 "Identity handling is mandatory").
 #pragma once
@@ -49,9 +52,9 @@ EKZG_HD_CALL void xyzz_dbl_affine(G1Xyzz& r, const G1Affine& p) {
     fe_sqr(t, p.x);
     fe_dbl(m, t); fe_add(m, m, t);
     fe_sqr(r.x, m); fe_sub(r.x, r.x, s); fe_sub(r.x, r.x, s);
-    fe_sub(t, s, r.x); fe_mul(t, m, t);
-    fe_mul(u, w, p.y);
-    fe_sub(r.y, t, u);
+    fe_sub(t, s, r.x);
+    fe_neg(u, p.y);
+    fp_mul2_add(r.y, m, t, w, u);   // M*(S - X3) - W*Y1
     r.zz = v; r.zzz = w;
 }
 
@@ -79,9 +82,8 @@ EKZG_HD void xyzz_madd(G1Xyzz& acc, const G1Affine& p_in, bool neg) {
     fe_sqr(t, rr);
     fe_sub(t, t, ppp); fe_sub(t, t, q); fe_sub(t, t, q);  // X3
     fe_sub(q, q, t);
-    fe_mul(q, rr, q);          // R*(Q - X3)
-    fe_mul(ppp, acc.y, ppp);   // Y1*PPP
-    fe_sub(acc.y, q, ppp);
+    fe_neg(ppp, ppp);
+    fp_mul2_add(acc.y, rr, q, acc.y, ppp);   // R*(Q - X3) - Y1*PPP, one reduction
     acc.x = t;
 }
 
@@ -97,11 +99,11 @@ EKZG_HD_CALL void xyzz_dbl(G1Xyzz& r, const G1Xyzz& p) {
     fe_dbl(m, t); fe_add(m, m, t);
     Fp x3;
     fe_sqr(x3, m); fe_sub(x3, x3, s); fe_sub(x3, x3, s);
-    fe_sub(t, s, x3); fe_mul(t, m, t);
-    fe_mul(u, w, p.y);
+    fe_sub(t, s, x3);
+    fe_neg(u, p.y);
     fe_mul(r.zz, v, p.zz);
     fe_mul(r.zzz, w, p.zzz);
-    fe_sub(r.y, t, u);
+    fp_mul2_add(r.y, m, t, w, u);   // M*(S - X3) - W*Y1
     r.x = x3;
 }
 
@@ -128,9 +130,8 @@ EKZG_HD_CALL void xyzz_add(G1Xyzz& acc, const G1Xyzz& q) {
     fe_sqr(t, s2);
     fe_sub(t, t, ppp); fe_sub(t, t, u1); fe_sub(t, t, u1);  // X3
     fe_sub(u1, u1, t);
-    fe_mul(u1, s2, u1);
-    fe_mul(s1, s1, ppp);
-    fe_sub(acc.y, u1, s1);
+    fe_neg(ppp, ppp);
+    fp_mul2_add(acc.y, s2, u1, s1, ppp);   // R*(Q - X3) - S1*PPP
     acc.x = t;
 }
 

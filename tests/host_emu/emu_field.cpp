@@ -8,6 +8,8 @@ extern "C" {
 void emu_fp_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fe_mul(z, x, y); memcpy(r, z.v, 48); }
 void emu_fp_sqr(const uint32_t* a, uint32_t* r) { Fp x, z; memcpy(x.v, a, 48); fe_sqr(z, x); memcpy(r, z.v, 48); }
 void emu_fr_sqr(const uint32_t* a, uint32_t* r) { Fr x, z; memcpy(x.v, a, 32); fe_sqr(z, x); memcpy(r, z.v, 32); }
+void emu_fp_mul2(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
+    Fp x, y, z, w, o; memcpy(x.v, a, 48); memcpy(y.v, b, 48); memcpy(z.v, c, 48); memcpy(w.v, d, 48); fp_mul2_add(o, x, y, z, w); memcpy(r, o.v, 48); }
 void emu_fp_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fe_add(z, x, y); memcpy(r, z.v, 48); }
 void emu_fp_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y, z; memcpy(x.v, a, 48); memcpy(y.v, b, 48); fe_sub(z, x, y); memcpy(r, z.v, 48); }
 void emu_fp_neg(const uint32_t* a, uint32_t* r) { Fp x, z; memcpy(x.v, a, 48); fe_neg(z, x); memcpy(r, z.v, 48); }

@@ -56,6 +56,13 @@ def test_field_ops(emu_field, mod, n, pre):
         a %= mod
         getattr(emu_field, "emu_%s_sqr" % pre)(arr(a, n), out)
         assert val(out) == a * a * Ri % mod, hex(a)
+    if pre == "fp":  # fused a*b + c*d with one reduction
+        for _ in range(300):
+            a, b, c, d = (rng.choice(vals) if rng.random() < 0.3 else rng.randrange(mod) for _ in range(4))
+            emu_field.emu_fp_mul2(arr(a, n), arr(b, n), arr(c, n), arr(d, n), out)
+            assert val(out) == (a * b + c * d) * Ri % mod
+        emu_field.emu_fp_mul2(arr(mod - 1, n), arr(mod - 1, n), arr(mod - 1, n), arr(mod - 1, n), out)
+        assert val(out) == 2 * (mod - 1) ** 2 * Ri % mod
     for a in vals:
         for b in rng.sample(vals, 6) + edge:
             getattr(emu_field, "emu_%s_mul" % pre)(arr(a, n), arr(b, n), out)
