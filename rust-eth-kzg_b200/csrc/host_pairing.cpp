@@ -154,7 +154,8 @@ struct G2Aff { Fp2 x, y; };
 struct Line { Fp2 lam, c; };  // line through T: value at P=(xP,yP) is (c - lam*xP v) + (yP v) w
 
 struct State {
-    Fp gamma[6];
+    Fp gamma[6];                 // xi^(i (p^2-1)/6), in Fp
+    Fp2 gamma1[6];               // xi^(i (p-1)/6), in Fp2
     std::vector<Line> lines[6];  // G2Sel index
     bool ok = false;
 };
@@ -169,6 +170,34 @@ static void f12_frob2(Fp12& r, const Fp12& a) {
     f2_mul_fp(r.c1.a0, a.c1.a0, g[1]);
     f2_mul_fp(r.c1.a1, a.c1.a1, g[3]);
     f2_mul_fp(r.c1.a2, a.c1.a2, g[5]);
+}
+
+// a^p: the coefficient of w^k (w^6 = xi) is conjugated and multiplied by xi^(k (p-1)/6)
+static void f12_frob1(Fp12& r, const Fp12& a) {
+    const Fp2* g = g_state.gamma1;
+    auto term = [&](Fp2& out, const Fp2& in, int k) {
+        Fp2 c = in;
+        fp_neg(c.c1, c.c1);
+        if (k == 0) out = c; else f2_mul(out, c, g[k]);
+    };
+    Fp12 o;
+    term(o.c0.a0, a.c0.a0, 0);
+    term(o.c0.a1, a.c0.a1, 2);
+    term(o.c0.a2, a.c0.a2, 4);
+    term(o.c1.a0, a.c1.a0, 1);
+    term(o.c1.a1, a.c1.a1, 3);
+    term(o.c1.a2, a.c1.a2, 5);
+    r = o;
+}
+
+// a^x for a in the cyclotomic subgroup, x = -0xd201000000010000 (negative: conjugate at the end)
+static void f12_exp_x(Fp12& r, const Fp12& a) {
+    Fp12 acc = a;
+    for (int bit = 62; bit >= 0; bit--) {
+        f12_sqr(acc, acc);
+        if ((BLS_X_ABS >> bit) & 1) f12_mul(acc, acc, a);
+    }
+    f12_conj(r, acc);
 }
 
 static void prepare(std::vector<Line>& out, const G2Aff& q) {
@@ -219,7 +248,30 @@ static void init_state() {
     s.gamma[0] = fp_one();
     const uint64_t* gs[5] = {FROB2_GAMMA_1, FROB2_GAMMA_2, FROB2_GAMMA_3, FROB2_GAMMA_4, FROB2_GAMMA_5};
     for (int i = 0; i < 5; i++) memcpy(s.gamma[i + 1].v, gs[i], 48);
+    {   // gamma1[1] = xi^((p-1)/6) by square-and-multiply, xi = 1 + u; the exponent is FP_P (p = 1 mod 6) divided by 6
+        uint64_t e[6];
+        u128 rem = 0;
+        for (int i = 5; i >= 0; i--) { u128 cur = (rem << 64) | FP_P[i]; e[i] = (uint64_t)(cur / 6); rem = cur % 6; }
+        Fp2 xi, acc;
+        xi.c0 = fp_one(); xi.c1 = fp_one();
+        acc.c0 = fp_one(); memset(&acc.c1, 0, sizeof acc.c1);
+        for (int i = 383; i >= 0; i--) {
+            f2_sqr(acc, acc);
+            if ((e[i / 64] >> (i % 64)) & 1) f2_mul(acc, acc, xi);
+        }
+        s.gamma1[0].c0 = fp_one(); memset(&s.gamma1[0].c1, 0, sizeof(Fp));
+        s.gamma1[1] = acc;
+        for (int i = 2; i < 6; i++) f2_mul(s.gamma1[i], s.gamma1[i - 1], acc);
+    }
     bool ok = true;
+    {   // self-check of the Frobenius constants: gamma1[k] * conj(gamma1[k]) == gamma[k]  (xi^(k(p-1)/6 * (p+1)) = xi^(k(p^2-1)/6))
+        for (int k = 1; k < 6; k++) {
+            Fp2 c = s.gamma1[k], prod;
+            fp_neg(c.c1, c.c1);
+            f2_mul(prod, s.gamma1[k], c);
+            ok = ok && fp_eq(prod.c0, s.gamma[k]) && fp_is_zero(prod.c1);
+        }
+    }
     for (int neg = 0; neg < 2; neg++) {
         G2Aff gen = g2_const(G2_GEN_X0, G2_GEN_X1, G2_GEN_Y0, G2_GEN_Y1, neg);
         G2Aff tau = g2_const(G2_TAU_X0, G2_TAU_X1, G2_TAU_Y0, G2_TAU_Y1, neg);
@@ -261,17 +313,22 @@ bool pairing_check(const PairingInput* in, int n) {
             }
         }
     }
-    // final exponentiation: easy part (p^6-1)(p^2+1), then the hard part (p^4-p^2+1)/r by square-and-multiply
+    // final exponentiation: easy part (p^6-1)(p^2+1), then 3x the hard part (p^4-p^2+1)/r through
+    //   3 (p^4 - p^2 + 1)/r = (x-1)^2 (x+p) (x^2 + p^2 - 1) + 3      (Hayashida-Hayasaka-Teruya; checked in
+    // tools/gen_host_constants.py) -- five exponentiations by the 64-bit x instead of a 1268-bit square-and-multiply.
+    // gcd(3, r) = 1, so the result is one exactly when the pairing product is.  After the easy part the value lies in
+    // the cyclotomic subgroup, where inversion is conjugation.
     Fp12 t, u;
     f12_conj(t, f); f12_inv(u, f); f12_mul(t, t, u);
     f12_frob2(u, t); f12_mul(t, u, t);
-    Fp12 acc = f12_one();
-    int top = HARD_EXP_LIMBS * 64 - 1;
-    while (!((HARD_EXP[top / 64] >> (top % 64)) & 1)) top--;
-    for (int i = top; i >= 0; i--) {
-        f12_sqr(acc, acc);
-        if ((HARD_EXP[i / 64] >> (i % 64)) & 1) f12_mul(acc, acc, t);
-    }
+    Fp12 a, b, c, e1, e2;
+    f12_exp_x(e1, t); f12_conj(e2, t); f12_mul(a, e1, e2);          // t^(x-1)
+    f12_exp_x(e1, a); f12_conj(e2, a); f12_mul(a, e1, e2);          // ^(x-1)
+    f12_exp_x(e1, a); f12_frob1(e2, a); f12_mul(b, e1, e2);         // ^(x+p)
+    f12_exp_x(e1, b); f12_exp_x(e1, e1); f12_frob2(e2, b); f12_mul(c, e1, e2);
+    f12_conj(e2, b); f12_mul(c, c, e2);                             // ^(x^2+p^2-1)
+    Fp12 acc;
+    f12_sqr(acc, t); f12_mul(acc, acc, t); f12_mul(acc, acc, c);    // * t^3
     return f12_is_one(acc);
 }
 
