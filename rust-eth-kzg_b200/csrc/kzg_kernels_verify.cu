@@ -62,18 +62,73 @@ __global__ void k_cell_verify_scalars(const Fr* __restrict__ rpow, const uint32_
     store_plain(s2 + (size_t)k * 8, t);
 }
 
-// weights[i] = sum_{k: row_k == i} rho_k  (verifier.rs:216-219), plain integers
-__global__ void k_commitment_weights(const Fr* __restrict__ rpow, const uint32_t* __restrict__ row, uint32_t* __restrict__ wout, int n, int m) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+// weights[i] = sum_{k: row_k == i} rho_k  (verifier.rs:216-219), plain integers.  One CTA per row.
+__global__ void __launch_bounds__(128)
+k_commitment_weights(const Fr* __restrict__ rpow, const uint32_t* __restrict__ row, uint32_t* __restrict__ wout, int n, int m) {
+    __shared__ Fr sm[128];
+    const int i = blockIdx.x;
     Fr acc;
     fe_set_zero(acc);
-    for (int k = 0; k < n; k++)
+    for (int k = threadIdx.x; k < n; k += 128)
         if ((int)row[k] == i) {
             Fr r = ld_vec(&rpow[k]);
             fe_add(acc, acc, r);
         }
-    store_plain(wout + (size_t)i * 8, acc);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) {
+            Fr a = sm[threadIdx.x], b = sm[threadIdx.x + s];
+            fe_add(a, a, b);
+            sm[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) store_plain(wout + (size_t)i * 8, sm[0]);
+}
+
+// The second random-linear-combination MSM of the verification equation, sum_k rho_k h_k^64 pi_k (verifier.rs:188-201),
+// shares its points with the first one and its extra factor h_k^64 = omega_128^rev7(col_k) only depends on the cell
+// index.  So: colsum[c] = sum_{k: col_k == c} rho_k pi_k (one CTA per column over the products the first MSM already
+// made), then  sum_k rho_k pi_k = sum_c colsum[c]  and  sum_k rho_k h_k^64 pi_k = sum_c omega^rev7(c) colsum[c]
+// -- 128 multiplications by FIXED roots of unity (the op-list ladder of the G1 NTT) instead of N variable ones.
+__constant__ uint16_t c_verify_twiddle_ops[128][MULOPS_STRIDE] =
+#include "twiddle_ops.inc"
+    ;
+
+__global__ void __launch_bounds__(128)
+k_column_sums(const G1Jac* __restrict__ prods, const uint32_t* __restrict__ col, G1Jac* __restrict__ colsum, int n) {
+    __shared__ G1Jac sm[128];
+    const int c = blockIdx.x;
+    G1Jac acc;
+    jac_set_inf(acc);
+    for (int k = threadIdx.x; k < n; k += 128)
+        if ((int)col[k] == c) {
+            G1Jac q = ld_vec(&prods[k]);
+            jac_add(acc, q);
+        }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 64; s >= 1; s >>= 1) {
+        if (threadIdx.x < s) {
+            G1Jac a = sm[threadIdx.x];
+            jac_add(a, sm[threadIdx.x + s]);
+            sm[threadIdx.x] = a;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_vec(&colsum[c], sm[0]);
+}
+
+// weighted[c] = omega_128^rev7(c) * colsum[c]
+__global__ void __launch_bounds__(32)
+k_column_twiddle(const G1Jac* __restrict__ colsum, G1Jac* __restrict__ weighted) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N_CELLS) return;
+    G1Jac q = ld_vec(&colsum[c]);
+    const int e = vbits(c, 7);
+    if (e != 0 && !jac_is_inf(q)) jac_mul_ops(q, q, c_verify_twiddle_ops[e]);
+    st_vec(&weighted[c], q);
 }
 
 // out[i] = scalar_i * P_i  (identity points / zero scalars give the identity, like lincomb.rs:13-27 filters them)
@@ -178,24 +233,29 @@ k_interp_column_sum(const Fr* __restrict__ interp, uint32_t* __restrict__ out, i
 //   out[0] = a0 ;  out[1] = b0 - b1 + b2      (each term may be null = identity)
 // layout per point: 12 limbs x, 12 limbs y (plain, little-endian 32-bit) + 1 word identity flag = 25 words
 __global__ void k_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* b1, const G1Jac* b2, uint32_t* __restrict__ out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    G1Jac p[2];
-    p[0] = ld_vec(a0);
-    jac_set_inf(p[1]);
-    if (b0) { G1Jac q = ld_vec(b0); jac_add(p[1], q); }
-    if (b1) { G1Jac q = ld_vec(b1); jac_neg(q, q); jac_add(p[1], q); }
-    if (b2) { G1Jac q = ld_vec(b2); jac_add(p[1], q); }
-    for (int i = 0; i < 2; i++) {
+    // two CTAs, one point each (the inversions are the whole cost)
+    if (threadIdx.x != 0 || blockIdx.x > 1) return;
+    const int i = blockIdx.x;
+    G1Jac pt;
+    if (i == 0) {
+        pt = ld_vec(a0);
+    } else {
+        jac_set_inf(pt);
+        if (b0) { G1Jac q = ld_vec(b0); jac_add(pt, q); }
+        if (b1) { G1Jac q = ld_vec(b1); jac_neg(q, q); jac_add(pt, q); }
+        if (b2) { G1Jac q = ld_vec(b2); jac_add(pt, q); }
+    }
+    {
         uint32_t* o = out + 25 * i;
-        if (jac_is_inf(p[i])) {
+        if (jac_is_inf(pt)) {
             for (int l = 0; l < 24; l++) o[l] = 0;
             o[24] = 1;
-            continue;
+            return;
         }
         Fp zi;
-        fp_inv(zi, p[i].z);
+        fp_inv(zi, pt.z);
         G1Affine a;
-        jac_to_affine_with_inv(a, p[i], zi);
+        jac_to_affine_with_inv(a, pt, zi);
         Fp x, y;
         fe_from_mont(x, a.x);
         fe_from_mont(y, a.y);
@@ -284,7 +344,15 @@ cudaError_t launch_cell_verify_scalars(const Fr* rpow, const uint32_t* col, uint
     return cudaSuccess;
 }
 cudaError_t launch_commitment_weights(const Fr* rpow, const uint32_t* row, uint32_t* wout, int n, int m, cudaStream_t st) {
-    k_commitment_weights<<<(m + 63) / 64, 64, 0, st>>>(rpow, row, wout, n, m);
+    k_commitment_weights<<<m, 128, 0, st>>>(rpow, row, wout, n, m);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+// colsum[128] and weighted[128] from the N products rho_k pi_k (see k_column_sums)
+cudaError_t launch_column_sums(const G1Jac* prods, const uint32_t* col, G1Jac* colsum, G1Jac* weighted, int n, cudaStream_t st) {
+    k_column_sums<<<N_CELLS, 128, 0, st>>>(prods, col, colsum, n);
+    EKZG_LAUNCH_CHECK();
+    k_column_twiddle<<<N_CELLS / 32, 32, 0, st>>>(colsum, weighted);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }
@@ -316,7 +384,7 @@ cudaError_t launch_interp_column_sum(const Fr* interp, uint32_t* out, int n, cud
     return cudaSuccess;
 }
 cudaError_t launch_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* b1, const G1Jac* b2, uint32_t* out, cudaStream_t st) {
-    k_pairing_inputs<<<1, 32, 0, st>>>(a0, b0, b1, b2, out);
+    k_pairing_inputs<<<2, 32, 0, st>>>(a0, b0, b1, b2, out);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -116,12 +116,13 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             uint32_t *d_col, *d_row, *d_stc, *d_stp, *d_cellst, *d_s1, *d_s2, *d_w, *d_i, *d_out;
             G1Affine *a_c, *a_p;
             Fr *d_rpow, *d_interp;
-            G1Jac *d_mul, *d_part, *d_sums;
+            G1Jac *d_mul, *d_part, *d_sums, *d_colsum;
+            EKZG_TRY(S.get(&d_colsum, 2 * N_CELLS));
             EKZG_TRY(S.get(&d_c, (size_t)M * 48)); EKZG_TRY(S.get(&d_p, (size_t)N * 48)); EKZG_TRY(S.get(&d_cells, (size_t)N * BYTES_PER_CELL));
             EKZG_TRY(S.get(&d_hash, 32)); EKZG_TRY(S.get(&d_col, N)); EKZG_TRY(S.get(&d_row, N)); EKZG_TRY(S.get(&d_stc, M)); EKZG_TRY(S.get(&d_stp, N));
             EKZG_TRY(S.get(&d_cellst, 1)); EKZG_TRY(S.get(&d_s1, (size_t)N * 8)); EKZG_TRY(S.get(&d_s2, (size_t)N * 8)); EKZG_TRY(S.get(&d_w, (size_t)M * 8));
             EKZG_TRY(S.get(&d_i, 64 * 8)); EKZG_TRY(S.get(&d_out, 50)); EKZG_TRY(S.get(&a_c, M)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_rpow, N));
-            EKZG_TRY(S.get(&d_interp, (size_t)N * 64)); EKZG_TRY(S.get(&d_mul, std::max(N, 64))); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 4));
+            EKZG_TRY(S.get(&d_interp, (size_t)N * 64)); EKZG_TRY(S.get(&d_mul, std::max(N, 128))); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 4));
             EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_cells, hcells, (size_t)N * BYTES_PER_CELL, cudaMemcpyHostToDevice, st));
@@ -154,20 +155,22 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_CUDA(cudaMemcpyAsync(d_hash, hash, 32, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(launch_powers_from_hash(d_hash, d_rpow, N, st));
             EKZG_CUDA(launch_cell_verify_scalars(d_rpow, d_col, d_s1, d_s2, T_, N, st));
-            // P = sum rho_k pi_k ; W = sum rho_k h_k^64 pi_k
+            // P = sum rho_k pi_k ; W = sum rho_k h_k^64 pi_k: one pass of N scalar multiplications, then per-column sums
+            // and 128 multiplications by fixed roots of unity (kzg_kernels_verify.cu: k_column_sums)
             EKZG_CUDA(launch_scalar_mul(a_p, d_s1, d_mul, N, st));
-            EKZG_CUDA(launch_sum_points(d_mul, N, d_part, &d_sums[0], st));
-            EKZG_CUDA(launch_scalar_mul(a_p, d_s2, d_mul, N, st));
-            EKZG_CUDA(launch_sum_points(d_mul, N, d_part, &d_sums[1], st));
+            EKZG_CUDA(launch_column_sums(d_mul, d_col, d_colsum, d_colsum + N_CELLS, N, st));
+            EKZG_CUDA(launch_sum_points(d_colsum, N_CELLS, d_part, &d_sums[0], st));
+            EKZG_CUDA(launch_sum_points(d_colsum + N_CELLS, N_CELLS, d_part, &d_sums[1], st));
             // Cs = sum w_i C_i
             EKZG_CUDA(launch_commitment_weights(d_rpow, d_row, d_w, N, M, st));
             EKZG_CUDA(launch_scalar_mul(a_c, d_w, d_mul, M, st));
             EKZG_CUDA(launch_sum_points(d_mul, M, d_part, &d_sums[2], st));
-            // Ic = commit(sum rho_k I_k)
+            // Ic = commit(sum rho_k I_k): 64 coefficients on the first 64 monomial SRS points = group 0 of the fixed-base
+            // SRS tables (natural position 0 of a 128-slot row)
             EKZG_CUDA(launch_cell_interp(d_cells, d_col, d_rpow, d_interp, d_cellst, T_, N, st));
             EKZG_CUDA(launch_interp_column_sum(d_interp, d_i, N, st));
-            EKZG_CUDA(launch_scalar_mul(T_.srs_g1, d_i, d_mul, 64, st));
-            EKZG_CUDA(launch_sum_points(d_mul, 64, d_part, &d_sums[3], st));
+            EKZG_CUDA(launch_fixed_msm(d_i, d_mul, T_.srs, 1, 1, st));
+            EKZG_CUDA(cudaMemcpyAsync(&d_sums[3], d_mul, sizeof(G1Jac), cudaMemcpyDeviceToDevice, st));
             // pairing inputs: (P, [tau^64]_2), (Cs - Ic + W, -[1]_2)
             EKZG_CUDA(launch_pairing_inputs(&d_sums[0], &d_sums[2], &d_sums[3], &d_sums[1], d_out, st));
             EKZG_CUDA(cudaMemcpyAsync(pin, d_out, sizeof pin, cudaMemcpyDeviceToHost, st));
