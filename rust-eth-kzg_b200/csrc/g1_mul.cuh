@@ -191,6 +191,45 @@ EKZG_HD_CALL void jac_mul_u256(G1Jac& out, const G1Jac& p, const uint32_t* k) {
     out = acc;
 }
 
+// |x| * P for the BLS parameter |x| = 0xd201000000010000 (bit 63 set, five more bits): 63 doublings + 5 additions
+EKZG_HD_CALL void jac_mul_bls_x_abs(G1Jac& out, const G1Jac& p) {
+    const uint64_t x = 0xd201000000010000ull;
+    G1Jac acc = p;
+    for (int bit = 62; bit >= 0; bit--) {
+        jac_dbl(acc, acc);
+        if ((x >> bit) & 1) jac_add(acc, p);
+    }
+    out = acc;
+}
+
+// Prime-order subgroup membership of a curve point (the check blstrs' from_compressed performs for
+// crates/serialization/src/lib.rs:69-81): phi acts on G1 as multiplication by lambda = x^2 - 1, and
+//   P in G1  <=>  x^2 * P == phi(P) + P
+// (Scott, "A note on group membership tests for G1, G2 and GT on BLS pairing-friendly curves", eprint 2021/1130, in
+// the form phi^2(P) = -x^2 P with phi^2 + phi + 1 = 0).  Two multiplications by the 64-bit |x| instead of one by the
+// 255-bit r.  a must be on the curve and not the identity.
+EKZG_HD_CALL bool g1a_in_subgroup(const G1Affine& a) {
+    G1Jac p, t;
+    jac_from_affine(p, a);
+    jac_mul_bls_x_abs(t, p);
+    jac_mul_bls_x_abs(t, t);          // x^2 P
+    G1Jac s;
+    jac_endo(s, p);
+    jac_madd(s, a, false);            // phi(P) + P
+    if (jac_is_inf(t) || jac_is_inf(s)) return jac_is_inf(t) && jac_is_inf(s);
+    Fp z1z1, z2z2, l, r;
+    fe_sqr(z1z1, t.z);
+    fe_sqr(z2z2, s.z);
+    fe_mul(l, t.x, z2z2);
+    fe_mul(r, s.x, z1z1);
+    if (!fe_eq(l, r)) return false;
+    fe_mul(z1z1, z1z1, t.z);
+    fe_mul(z2z2, z2z2, s.z);
+    fe_mul(l, t.y, z2z2);
+    fe_mul(r, s.y, z1z1);
+    return fe_eq(l, r);
+}
+
 // op lists of the 128th roots of unity, row e = omega_128^e (host copy; the kernels keep one in __constant__)
 static const uint16_t TWIDDLE_OPS_HOST[128][MULOPS_STRIDE] =
 #include "twiddle_ops.inc"

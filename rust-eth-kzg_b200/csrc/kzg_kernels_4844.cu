@@ -27,20 +27,56 @@ __device__ __forceinline__ Fr fr_from_be_reduce(const uint8_t* p) {
 }
 
 // z = SHA-256("FSBLOBVERIFY_V1_" || u128_be(4096) || blob || commitment) mod r, one thread per blob
-// (crates/eip4844/src/verifier.rs:155-196)
+// (crates/eip4844/src/verifier.rs:155-196).  The chain is sequential per blob, so the kernel is latency-bound: the 64
+// bytes of the next compression are fetched (four 16-byte loads) before the current one is computed.  The 32-byte
+// header shifts the blob by half a block: compression k takes blob bytes [64k-32, 64k+32).
+__device__ __forceinline__ void sha_words_from_u4(uint32_t* w, const uint4& v) {
+    w[0] = __byte_perm(v.x, 0, 0x0123); w[1] = __byte_perm(v.y, 0, 0x0123); w[2] = __byte_perm(v.z, 0, 0x0123); w[3] = __byte_perm(v.w, 0, 0x0123);
+}
 __global__ void __launch_bounds__(32)
 k_blob_challenge(const uint8_t* __restrict__ blobs, const uint8_t* __restrict__ commitments, Fr* __restrict__ z_out, int B) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    Sha256 s;
-    sha256_init(s);
-    uint8_t head[32] = {'F', 'S', 'B', 'L', 'O', 'B', 'V', 'E', 'R', 'I', 'F', 'Y', '_', 'V', '1', '_', 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0x10, 0x00};
-    sha256_update(s, head, 32);
-    sha256_update(s, blobs + (size_t)b * BYTES_PER_BLOB, BYTES_PER_BLOB);
-    sha256_update(s, commitments + (size_t)b * 48, 48);
-    uint8_t h[32];
-    sha256_final(s, h);
-    st_vec(&z_out[b], fr_from_be_reduce(h));
+    const uint4* src = reinterpret_cast<const uint4*>(blobs + (size_t)b * BYTES_PER_BLOB);   // 8192 x 16 B
+    const uint4* com = reinterpret_cast<const uint4*>(commitments + (size_t)b * 48);
+    uint32_t h[8] = {0x6a09e667u, 0xbb67ae85u, 0x3c6ef372u, 0xa54ff53au, 0x510e527fu, 0x9b05688cu, 0x1f83d9abu, 0x5be0cd19u};
+    uint32_t w[16];
+    // "FSBL" "OBVE" "RIFY" "_V1_" then u128_be(4096)
+    w[0] = 0x4653424cu; w[1] = 0x4f425645u; w[2] = 0x52494659u; w[3] = 0x5f56315fu;
+    w[4] = 0; w[5] = 0; w[6] = 0; w[7] = 0x00001000u;
+    uint4 nxt[4];
+    nxt[0] = src[0]; nxt[1] = src[1];
+    sha_words_from_u4(w + 8, nxt[0]);
+    sha_words_from_u4(w + 12, nxt[1]);
+#pragma unroll
+    for (int q = 0; q < 4; q++) nxt[q] = src[2 + q];
+    sha256_compress_words(h, w);
+#pragma unroll 1
+    for (int k = 1; k < 2048; k++) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) sha_words_from_u4(w + 4 * q, nxt[q]);
+        if (k < 2047) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) nxt[q] = src[4 * (k + 1) - 2 + q];
+        } else {  // compression 2048: last 32 blob bytes + first 32 commitment bytes
+            nxt[0] = src[8190]; nxt[1] = src[8191]; nxt[2] = com[0]; nxt[3] = com[1];
+        }
+        sha256_compress_words(h, w);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; q++) sha_words_from_u4(w + 4 * q, nxt[q]);
+    sha256_compress_words(h, w);
+    // tail: last 16 commitment bytes, 0x80, zeros, bit length of 32 + 131072 + 48 bytes
+    sha_words_from_u4(w, com[2]);
+    w[4] = 0x80000000u;
+#pragma unroll
+    for (int q = 5; q < 15; q++) w[q] = 0;
+    w[15] = (32u + (uint32_t)BYTES_PER_BLOB + 48u) * 8u;
+    sha256_compress_words(h, w);
+    uint8_t hb[32];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { hb[4 * i] = (uint8_t)(h[i] >> 24); hb[4 * i + 1] = (uint8_t)(h[i] >> 16); hb[4 * i + 2] = (uint8_t)(h[i] >> 8); hb[4 * i + 3] = (uint8_t)h[i]; }
+    st_vec(&z_out[b], fr_from_be_reduce(hb));
 }
 
 // user-supplied evaluation points (compute_kzg_proof): 32 BE bytes -> Fr, status |= 2 if not canonical
@@ -60,38 +96,71 @@ __global__ void k_scalars_from_be(const uint8_t* __restrict__ in, Fr* __restrict
     st_vec(&out[i], x);
 }
 
-// Quotient by (X - z) with Ruffini's rule, one thread per blob (kzg_single_open/src/prover.rs:48-65):
-// t_i = c_i + z*t_{i+1};  q_{i-1} = t_i (i = 4095..1);  y = t_0.  q is written as plain integers in the MSM
+// Quotient by (X - z) with Ruffini's rule (kzg_single_open/src/prover.rs:48-65):
+// t_i = c_i + z*t_{i+1};  q_{i-1} = t_i (i = 4095..1);  y = t_0.  The reference runs the recurrence serially; here it
+// is a weighted suffix scan, one CTA of 256 threads per blob: thread s owns coefficients 16s..16s+15, computes the
+// local suffix sums l_j, the 256 segment heads are combined by a Hillis-Steele scan with multipliers z^(16*2^k), and
+// t_i = l_i + z^(16(s+1)-i) * (value entering the segment from above).  q is written as plain integers in the MSM
 // scalar layout [i][B]; q_4095 = 0 so the 4096-point MSM is the reference's 4095-point one.
-__global__ void __launch_bounds__(32)
+constexpr int QT_THREADS = 256, QT_SEG = N_BLOB / QT_THREADS;
+__global__ void __launch_bounds__(QT_THREADS)
 k_quotient(const Fr* __restrict__ coeffs, const Fr* __restrict__ z_in, uint32_t* __restrict__ scalars, uint8_t* __restrict__ y_out, int B) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    __shared__ Fr T[QT_THREADS];
+    const int b = blockIdx.x, s = threadIdx.x, base = QT_SEG * s;
     const Fr* c = coeffs + (size_t)b * N_BLOB;
     const Fr z = ld_vec(&z_in[b]);
-    Fr t;
-    fe_set_zero(t);
-    {
-        uint4* d4 = reinterpret_cast<uint4*>(scalars + ((size_t)(N_BLOB - 1) * B + b) * 8);
-        d4[0] = make_uint4(0, 0, 0, 0);
-        d4[1] = make_uint4(0, 0, 0, 0);
+    Fr l[QT_SEG];
+    Fr acc;
+    fe_set_zero(acc);
+#pragma unroll
+    for (int j = QT_SEG - 1; j >= 0; j--) {
+        Fr cj = ld_vec(&c[base + j]);
+        fe_mul(acc, acc, z);
+        fe_add(acc, acc, cj);
+        l[j] = acc;
     }
-    for (int i = N_BLOB - 1; i >= 0; i--) {
-        Fr ci = ld_vec(&c[i]);
-        fe_mul(t, t, z);
-        fe_add(t, t, ci);
+    Fr mult = z;   // z^16
+#pragma unroll
+    for (int q = 0; q < 4; q++) fe_sqr(mult, mult);
+    static_assert(QT_SEG == 16, "z^SEG by four squarings");
+    T[s] = l[0];
+    __syncthreads();
+    for (int d = 1; d < QT_THREADS; d <<= 1) {
+        Fr v = T[s];
+        if (s + d < QT_THREADS) {
+            Fr o = T[s + d];
+            fe_mul(o, o, mult);
+            fe_add(v, v, o);
+        }
+        __syncthreads();
+        T[s] = v;
+        __syncthreads();
+        fe_sqr(mult, mult);
+    }
+    Fr tin;
+    if (s + 1 < QT_THREADS) tin = T[s + 1]; else fe_set_zero(tin);
+    Fr zpow = z;
+#pragma unroll
+    for (int j = QT_SEG - 1; j >= 0; j--) {
+        Fr t;
+        fe_mul(t, zpow, tin);
+        fe_add(t, t, l[j]);
+        if (j) fe_mul(zpow, zpow, z);
+        const int i = base + j;
+        Fr p;
+        fe_from_mont(p, t);
         if (i >= 1) {
-            Fr p;
-            fe_from_mont(p, t);
             uint4* d4 = reinterpret_cast<uint4*>(scalars + ((size_t)(i - 1) * B + b) * 8);
             d4[0] = make_uint4(p.v[0], p.v[1], p.v[2], p.v[3]);
             d4[1] = make_uint4(p.v[4], p.v[5], p.v[6], p.v[7]);
+        } else if (y_out) {
+            fr_store_be(y_out + (size_t)b * 32, p);
         }
     }
-    if (y_out) {
-        Fr y;
-        fe_from_mont(y, t);
-        fr_store_be(y_out + (size_t)b * 32, y);
+    if (s == QT_THREADS - 1) {
+        uint4* d4 = reinterpret_cast<uint4*>(scalars + ((size_t)(N_BLOB - 1) * B + b) * 8);
+        d4[0] = make_uint4(0, 0, 0, 0);
+        d4[1] = make_uint4(0, 0, 0, 0);
     }
 }
 
@@ -140,12 +209,7 @@ k_g1_validate(const uint8_t* __restrict__ in, G1Affine* __restrict__ out, uint32
         g1a_set_inf(a);
         st = 1;
     } else if (check_subgroup && !g1a_is_inf(a)) {
-        G1Jac p, q;
-        jac_from_affine(p, a);
-        uint32_t k[8];
-        fr_modulus(k);
-        jac_mul_u256(q, p, k);
-        if (!jac_is_inf(q)) st = 2;
+        if (!g1a_in_subgroup(a)) st = 2;
     }
     status[i] = st;
     st_vec(&out[i], a);
@@ -164,7 +228,7 @@ cudaError_t launch_scalars_from_be(const uint8_t* in, Fr* out, uint32_t* status,
     return cudaSuccess;
 }
 cudaError_t launch_quotient(const Fr* coeffs, const Fr* z, uint32_t* scalars, uint8_t* y_out, int B, cudaStream_t st) {
-    k_quotient<<<(B + 31) / 32, 32, 0, st>>>(coeffs, z, scalars, y_out, B);
+    k_quotient<<<B, QT_THREADS, 0, st>>>(coeffs, z, scalars, y_out, B);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }

@@ -585,17 +585,24 @@ Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const 
     TraceClock tr(mode == Mode4844::Commit ? "blob_to_kzg_commitment_batch" : "compute_(blob_)kzg_proof_batch");
     const bool in_pinned = host_range_is_pinned(blobs);
     auto body = [&](uint64_t first, int cnt) -> Status {
+        if (mode == Mode4844::BlobProof) {
+            // commitment validation (decompress + subgroup check) is independent of the blob pipeline: side stream
+            EKZG_CUDA(cudaMemsetAsync(ws.d_status2, 0, sizeof(uint32_t) * cnt, st));
+            EKZG_CUDA(cudaMemcpyAsync(ws.d_c48, aux_in + first * 48, (size_t)cnt * 48, cudaMemcpyHostToDevice, st));
+            EKZG_CUDA(cudaEventRecord(ws.sub_ready[0], st));
+            EKZG_CUDA(cudaStreamWaitEvent(ws.copy_stream, ws.sub_ready[0], 0));
+            EKZG_CUDA(launch_g1_validate(ws.d_c48, ws.d_aff, ws.d_status2, cnt, true, ws.copy_stream));
+            EKZG_CUDA(cudaEventRecord(ws.sub_out[0], ws.copy_stream));
+        }
         EKZG_TRY(upload_blobs(ws, blobs + first * BYTES_PER_BLOB, cnt, in_pinned));
         tr.mark("stage + enqueue H2D of the blobs");
         EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * cnt, st));
-        EKZG_CUDA(cudaMemsetAsync(ws.d_status2, 0, sizeof(uint32_t) * cnt, st));
+        if (mode != Mode4844::BlobProof) EKZG_CUDA(cudaMemsetAsync(ws.d_status2, 0, sizeof(uint32_t) * cnt, st));
         EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs, ws.d_coeffs, nullptr, ws.d_status, T_, cnt, false, st));
         if (mode == Mode4844::Commit) {
             EKZG_CUDA(launch_coeffs_to_scalars(ws.d_coeffs, ws.d_scalars, cnt, st));
         } else {
             if (mode == Mode4844::BlobProof) {
-                EKZG_CUDA(cudaMemcpyAsync(ws.d_c48, aux_in + first * 48, (size_t)cnt * 48, cudaMemcpyHostToDevice, st));
-                EKZG_CUDA(launch_g1_validate(ws.d_c48, ws.d_aff, ws.d_status2, cnt, true, st));
                 EKZG_CUDA(launch_blob_challenge(ws.d_blobs, ws.d_c48, ws.d_z, cnt, st));
             } else {
                 EKZG_CUDA(cudaMemcpyAsync(ws.d_z32, aux_in + first * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, st));
@@ -608,6 +615,7 @@ Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const 
         EKZG_CUDA(launch_g1_compress(ws.d_pts, ws.d_out48, 1, cnt, st));
         EKZG_CUDA(cudaMemcpyAsync(out48 + first * 48, ws.d_out48, (size_t)cnt * 48, cudaMemcpyDeviceToHost, st));
         if (mode == Mode4844::PointProof) EKZG_CUDA(cudaMemcpyAsync(out_y32 + first * 32, ws.d_z32, (size_t)cnt * 32, cudaMemcpyDeviceToHost, st));
+        if (mode == Mode4844::BlobProof) EKZG_CUDA(cudaStreamWaitEvent(st, ws.sub_out[0], 0));
         EKZG_CUDA(cudaMemcpyAsync(hs.data(), ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
         EKZG_CUDA(cudaMemcpyAsync(hs2.data(), ws.d_status2, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, st));
         EKZG_CUDA(cudaStreamSynchronize(st));
@@ -621,7 +629,7 @@ Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const 
         return Status::Ok();
     };
     for (uint64_t first = 0; first < n && result.ok; first += cap) result = body(first, (int)std::min<uint64_t>(cap, n - first));
-    if (!result.ok) cudaStreamSynchronize(st);
+    if (!result.ok) { cudaStreamSynchronize(st); cudaStreamSynchronize(ws.copy_stream); }
     give_back(wsp);
     if (!result.ok) return result;
     if (bad_blob) return Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus");

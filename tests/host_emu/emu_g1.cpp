@@ -73,5 +73,11 @@ int emu_g1_mul_twiddle_ops(const uint8_t* p48, int e, uint8_t* out) {
     jac_dbl(j, j);  // make Z != 1; python accounts for the factor 2
     jac_mul_ops(r, j, TWIDDLE_OPS_HOST[e]); out48(out, r); return 0;
 }
+// 0/1 = not in / in the prime-order subgroup, -1 = does not decode to a curve point
+int emu_g1_in_subgroup(const uint8_t* p48) {
+    G1Affine p; if (g1a_decompress(p, p48)) return -1;
+    if (g1a_is_inf(p)) return 1;
+    return g1a_in_subgroup(p) ? 1 : 0;
+}
 int emu_booth_digit(const uint32_t* s, int t, int w) { return booth_digit(s, t, w); }
 }

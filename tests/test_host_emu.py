@@ -184,3 +184,35 @@ def test_booth_digits(emu_g1):
             if s < 2**255:
                 assert sum(d << (t * w) for t, d in enumerate(ds[:nw])) == s
                 assert all(abs(d) <= 1 << (w - 1) for d in ds)
+
+
+def test_subgroup_check_matches_naive(emu_g1):
+    """g1a_in_subgroup (x^2 P == phi(P) + P) against the definition r*P == O, on points of G1, random curve points
+    (almost surely outside G1), pure cofactor-subgroup points r*Q, the order-3 points (0, +-2) and sums of both kinds."""
+    rng = random.Random(11)
+
+    def curve_point():
+        while True:
+            x = rng.randrange(P)
+            y2 = (x * x * x + 4) % P
+            y = pow(y2, (P + 1) // 4, P)
+            if y * y % P == y2:
+                return (x, y if rng.random() < 0.5 else P - y)
+
+    pts = [pyref.G1_GEN, pyref.g1_mul(pyref.G1_GEN, rng.randrange(1, R)), (0, 2), (0, P - 2)]
+    for _ in range(6):
+        q = curve_point()
+        pts.append(q)
+        cof = pyref.g1_mul_raw(q, R)                      # in the cofactor subgroup
+        if cof is not pyref.INF:
+            ca = cof
+            pts.append(ca)
+            pts.append(pyref.g1_add(ca, pyref.g1_mul(pyref.G1_GEN, rng.randrange(1, R))))
+    n_in = n_out = 0
+    for pt in pts:
+        want = 1 if pyref.g1_mul_raw(pt, R) is pyref.INF else 0
+        got = emu_g1.emu_g1_in_subgroup(pyref.g1_compress(pt))
+        assert got == want, pt
+        n_in += want
+        n_out += 1 - want
+    assert n_in >= 2 and n_out >= 10
