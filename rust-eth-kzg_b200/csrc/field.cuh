@@ -275,6 +275,38 @@ EKZG_HD void fe_sqr_inline(Fe<P>& out, const Fe<P>& a_) {
     for (int j = 0; j < N; j++) out.v[j] = r[j];
 }
 
+}  // namespace ekzg
+#include "fp_dfma.cuh"
+namespace ekzg {
+
+// EKZG_FP_DFMA=1 routes Fp products to the FP64 pipe (fp_dfma.cuh).  Default 0: measured on B200 the DFMA variant is
+// bit-exact but 1.4-1.6x SLOWER than the IMAD carry chains at the 2 warps per sub-partition these kernels run at
+// (860 instead of 330 instructions per product; profiles/r1_v4_dfma_experiment.md).  Kept as a tested alternative.
+#ifndef EKZG_FP_DFMA
+#define EKZG_FP_DFMA 0
+#endif
+EKZG_HD void fp_mul_impl(Fp& r, const Fp& a, const Fp& b) {
+#if EKZG_FP_DFMA
+    fp_mul_dfma_inline(r, a, b);
+#else
+    fe_mul_inline(r, a, b);
+#endif
+}
+EKZG_HD void fp_sqr_impl(Fp& r, const Fp& a) {
+#if EKZG_FP_DFMA
+    fp_sqr_dfma_inline(r, a);
+#else
+    fe_sqr_inline(r, a);
+#endif
+}
+EKZG_HD void fp_mul2_impl(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#if EKZG_FP_DFMA
+    fp_mul2_dfma_inline(r, a, b, c, d);
+#else
+    fe_mul2_inline(r, a, b, c, d);
+#endif
+}
+
 // The ~620-instruction Fp multiplication is ONE subroutine per kernel image on the device: operands and result
 // travel in registers (by-value aggregates; ptxas keeps them out of memory), so a point operation is a short
 // sequence of calls and the hot code of every kernel fits the 32 KB L1.5 instruction cache.  Fully inlined,
@@ -283,7 +315,7 @@ EKZG_HD void fe_sqr_inline(Fe<P>& out, const Fe<P>& a_) {
 #if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
 static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) {
     Fp r;
-    fe_mul_inline(r, a, b);
+    fp_mul_impl(r, a, b);
     return r;
 }
 #endif
@@ -291,18 +323,12 @@ static __device__ __noinline__ Fp fp_mul_call(Fp a, Fp b) {
 #if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
 static __device__ __noinline__ Fp fp_mul2_call(Fp a, Fp b, Fp c, Fp d) {
     Fp r;
-    fe_mul2_inline(r, a, b, c, d);
+    fp_mul2_impl(r, a, b, c, d);
     return r;
 }
 #endif
 // out = a*b + c*d  (Fp only, see fe_mul2_inline)
-EKZG_HD void fp_mul2_add(Fp& out, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
-#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
-    out = fp_mul2_call(a, b, c, d);
-#else
-    fe_mul2_inline(out, a, b, c, d);
-#endif
-}
+EKZG_HD void fp_mul2_add(Fp& out, const Fp& a, const Fp& b, const Fp& c, const Fp& d);
 
 template <class P>
 EKZG_HD void fe_mul(Fe<P>& out, const Fe<P>& a, const Fe<P>& b) {
@@ -312,14 +338,14 @@ EKZG_HD void fe_mul(Fp& out, const Fp& a, const Fp& b) {
 #if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
     out = fp_mul_call(a, b);
 #else
-    fe_mul_inline(out, a, b);
+    fp_mul_impl(out, a, b);
 #endif
 }
 
 #if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
 static __device__ __noinline__ Fp fp_sqr_call(Fp a) {
     Fp r;
-    fe_sqr_inline(r, a);
+    fp_sqr_impl(r, a);
     return r;
 }
 #endif
@@ -332,7 +358,7 @@ EKZG_HD void fe_sqr(Fp& out, const Fp& a) {
 #if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
     out = fp_sqr_call(a);
 #else
-    fe_sqr_inline(out, a);
+    fp_sqr_impl(out, a);
 #endif
 }
 
@@ -363,6 +389,22 @@ EKZG_HD void fe_sub(Fe<P>& out, const Fe<P>& a, const Fe<P>& b) {
     r[N - 1] = addc(r[N - 1], P::mod(N - 1) & mask);
 #pragma unroll
     for (int j = 0; j < N; j++) out.v[j] = r[j];
+}
+
+EKZG_HD void fp_mul2_add(Fp& out, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
+#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
+#if EKZG_FP_DFMA && defined(EKZG_DFMA_NO_FUSED_MUL2)
+    // a third unrolled FP64 subroutine (~20 KB) would push the hot code of K4/K5 past the instruction cache
+    Fp t, u;
+    fe_mul(t, a, b);
+    fe_mul(u, c, d);
+    fe_add(out, t, u);
+#else
+    out = fp_mul2_call(a, b, c, d);
+#endif
+#else
+    fp_mul2_impl(out, a, b, c, d);
+#endif
 }
 
 template <class P>

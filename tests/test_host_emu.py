@@ -17,12 +17,12 @@ CSRC = os.path.join(ROOT, "rust-eth-kzg_b200", "csrc")
 P, R = pyref.P, pyref.R
 
 
-def _build(name):
+def _build(name, defines=(), suffix=""):
     src = os.path.join(ROOT, "tests", "host_emu", name + ".cpp")
-    out = os.path.join(ROOT, "tests", "host_emu", name + ".so")
+    out = os.path.join(ROOT, "tests", "host_emu", name + suffix + ".so")
     deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-w", "-x", "c++", "-std=c++17", "-shared", "-fPIC", "-I" + CSRC, "-o", out, src])
+        subprocess.check_call(["g++", "-O2", "-w", "-x", "c++", "-std=c++17", "-shared", "-fPIC", "-I" + CSRC] + ["-D" + d for d in defines] + ["-o", out, src])
     return ctypes.CDLL(out)
 
 
@@ -34,6 +34,25 @@ def emu_field():
 @pytest.fixture(scope="module")
 def emu_g1():
     return _build("emu_g1")
+
+
+def test_fp_dfma_variant():
+    """the FP64-pipe Fp product (fp_dfma.cuh, off by default) against big integers: DFMA.RZ emulated by fma() under FE_TOWARDZERO"""
+    emu = _build("emu_field", defines=["EKZG_FP_DFMA=1"], suffix="_dfma")
+    rng = random.Random(11)
+    Ri = pow(1 << 384, -1, P)
+    out = (ctypes.c_uint32 * 12)()
+    edge = [0, 1, 2, P - 1, P - 2, (1 << 384) % P, (P - 1) // 2, (1 << 380) - 1, (1 << 48) - 1, ((1 << 48) - 1) << 48, sum(((1 << 48) - 1) << (96 * i) for i in range(4)) % P]
+    vals = edge + [rng.randrange(P) for _ in range(150)]
+    for a in vals:
+        emu.emu_fp_sqr(arr(a, 12), out)
+        assert val(out) == a * a * Ri % P
+        for b in edge + rng.sample(vals, 4):
+            emu.emu_fp_mul(arr(a, 12), arr(b, 12), out)
+            assert val(out) == a * b * Ri % P
+            c, d = rng.choice(vals), rng.choice(vals)
+            emu.emu_fp_mul2(arr(a, 12), arr(b, 12), arr(c, 12), arr(d, 12), out)
+            assert val(out) == (a * b + c * d) * Ri % P
 
 
 def arr(x, n):
