@@ -216,13 +216,16 @@ Status Context::init(bool use_precomp) {
     EKZG_CUDA(cudaMemcpy(d_bytes, ts + 16, (size_t)48 * 2 * n_g1, cudaMemcpyHostToDevice));
     G1Affine* srs;
     EKZG_TRY(dev_alloc(allocs_, &srs, 2 * (size_t)n_g1));
-    EKZG_CUDA(launch_g1_decompress(d_bytes, srs, d_st, 2 * n_g1, st));
+    // decompress + on-curve + prime-order-subgroup check of all 8192 G1 points on the device: the same validation
+    // blstrs' from_compressed gives the reference when it parses the ceremony JSON (crates/trusted_setup/src/lib.rs:112-115,
+    // crates/serialization/src/lib.rs:69-81), so a corrupted or substituted setup blob cannot yield a context
+    EKZG_CUDA(launch_g1_validate(d_bytes, srs, d_st, 2 * n_g1, true, st));
     std::vector<uint32_t> hst(2 * n_g1);
     EKZG_CUDA(cudaMemcpy(hst.data(), d_st, sizeof(uint32_t) * 2 * n_g1, cudaMemcpyDeviceToHost));
     cudaFree(d_bytes);
     cudaFree(d_st);
     for (uint32_t v : hst)
-        if (v) return Status::Error("embedded trusted setup: a G1 point failed to decompress");
+        if (v) return Status::Error("embedded trusted setup: a G1 point is malformed, off the curve or outside the prime-order subgroup");
     T_.srs_g1 = srs;
     T_.srs_g1_lagrange = srs + n_g1;
 
