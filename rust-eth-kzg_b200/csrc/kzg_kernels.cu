@@ -129,10 +129,10 @@ constexpr int K2_ROWS = 8;
 constexpr int K2_THREADS = K2_ROWS * 64;
 
 __global__ void __launch_bounds__(K2_THREADS)
-k_toeplitz_scalars(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars, DevTables T, int B) {
+k_toeplitz_scalars(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars, DevTables T, int B, int b0) {
     __shared__ uint32_t sm[8 * K2_ROWS * 128];
     constexpr int STRIDE = K2_ROWS * 128;
-    const int b = blockIdx.x, k0 = blockIdx.y * K2_ROWS, tid = threadIdx.x;
+    const int b = b0 + blockIdx.x, k0 = blockIdx.y * K2_ROWS, tid = threadIdx.x;
     const Fr* cf = coeffs + (size_t)b * N_BLOB;
     const Fr inv128 = fr_inv_128();
     for (int e = tid; e < K2_ROWS * 128; e += K2_THREADS) {
@@ -175,14 +175,14 @@ k_toeplitz_scalars(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars
 // ------------------------------------------------------------------------------------------------
 template <int NSLICE>
 __global__ void __launch_bounds__(128)
-k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTable T, int B) {
+k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTable T, int B, int b0, int b1) {
     // block = 128 threads = NSLICE slices x (128/NSLICE) blobs of one MSM j
     constexpr int BLOBS_PER_CTA = 128 / NSLICE;
     constexpr int KPER = FK20_POINTS / NSLICE;
     const int j = blockIdx.y;
     const int lane_b = threadIdx.x % BLOBS_PER_CTA, slice = threadIdx.x / BLOBS_PER_CTA;
-    const int b = blockIdx.x * BLOBS_PER_CTA + lane_b;
-    const bool active = b < B;
+    const int b = b0 + blockIdx.x * BLOBS_PER_CTA + lane_b;   // this launch covers blobs [b0, b1) of the batch of B
+    const bool active = b < b1;
     G1Xyzz acc;
     xyzz_set_inf(acc);
     if (active) {
@@ -561,19 +561,22 @@ cudaError_t launch_coeffs_to_cells(const Fr* coeffs, uint8_t* cells, const DevTa
     return cudaSuccess;
 }
 
-cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st) {
-    k_toeplitz_scalars<<<dim3(B, FK20_POINTS / K2_ROWS), K2_THREADS, 0, st>>>(coeffs, scalars, T, B);
+cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st, int b0, int cnt) {
+    if (cnt < 0) cnt = B - b0;
+    k_toeplitz_scalars<<<dim3(cnt, FK20_POINTS / K2_ROWS), K2_THREADS, 0, st>>>(coeffs, scalars, T, B, b0);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }
 
-cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st) {
-    // ngroups MSMs of 64 points each per blob (FK20: 128; SRS commitment: 64 partial sums).
+cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st, int b0, int cnt) {
+    // ngroups MSMs of 64 points each per blob (FK20: 128; SRS commitment: 64 partial sums), blobs [b0, b0 + cnt) of the
+    // batch of B (the strides of scalars[][][B] and pts[][B] are those of the whole batch).
     // fewer blobs per launch -> more slices per MSM so the machine still fills
+    if (cnt < 0) cnt = B - b0;
     if ((size_t)B * ngroups >= 512 * 128) {
-        k_fk20_msm<4><<<dim3((B + 31) / 32, ngroups), 128, 0, st>>>(scalars, pts, T, B);
+        k_fk20_msm<4><<<dim3((cnt + 31) / 32, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
     } else {
-        k_fk20_msm<16><<<dim3((B + 7) / 8, ngroups), 128, 0, st>>>(scalars, pts, T, B);
+        k_fk20_msm<16><<<dim3((cnt + 7) / 8, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
     }
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;

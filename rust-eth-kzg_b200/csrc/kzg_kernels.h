@@ -19,8 +19,9 @@ cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_
 cudaError_t launch_blob_to_coeffs_cells(const uint8_t* blobs, Fr* coeffs, uint8_t* cells, uint32_t* status, const DevTables& T,
                                         int B, bool want_cells, cudaStream_t st);
 cudaError_t launch_coeffs_to_cells(const Fr* coeffs, uint8_t* cells, const DevTables& T, int B, cudaStream_t st);
-cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st);
-cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st);
+// blobs [b0, b0 + cnt) of a batch of B (cnt < 0: to the end)
+cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st, int b0 = 0, int cnt = -1);
+cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st, int b0 = 0, int cnt = -1);
 size_t g1_ntt_queue_words(int B);
 cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* queue, cudaStream_t st);
 cudaError_t launch_fk20_g1_ntts(G1Jac* pts, int B, uint32_t* queue, cudaStream_t st);

@@ -46,7 +46,9 @@ Status Workspace::alloc(int cap, bool with_io) {
     capacity = cap;
     EKZG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     EKZG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    EKZG_CUDA(cudaStreamCreateWithFlags(&in_stream, cudaStreamNonBlocking));
     EKZG_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    for (auto& e : piece_in) EKZG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int i = 0; i < MAX_SUB; i++) {
         EKZG_CUDA(cudaEventCreateWithFlags(&sub_ready[i], cudaEventDisableTiming));
         EKZG_CUDA(cudaEventCreateWithFlags(&sub_out[i], cudaEventDisableTiming));
@@ -95,6 +97,8 @@ void Workspace::release() {
         if (sub_ready[i]) cudaEventDestroy(sub_ready[i]);
         if (sub_out[i]) cudaEventDestroy(sub_out[i]);
     }
+    for (auto& e : piece_in) if (e) cudaEventDestroy(e);
+    if (in_stream) cudaStreamDestroy(in_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -387,21 +391,34 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
     constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
     bool any_bad = false;
     Status result = Status::Ok();
+    TraceClock tr("compute_cells_and_kzg_proofs_batch");
+    // EKZG_TRACE: device timeline of the first chunk (timed events on the three streams)
+    std::vector<std::pair<std::string, cudaEvent_t>> tl;
+    auto stamp = [&](const char* what, int idx, cudaStream_t st) {
+        if (!tr.on) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        tl.emplace_back(std::string(what) + (idx >= 0 ? " " + std::to_string(idx) : ""), e);
+    };
     uint64_t pending_first[2] = {0, 0};
-    int pending_cnt[2] = {0, 0}, pending_sub[2] = {0, 0}, pending_nsub[2] = {0, 0};
+    int pending_cnt[2] = {0, 0}, pending_np[2] = {0, 0};
+    int piece_off[2][Workspace::MAX_SUB], piece_len[2][Workspace::MAX_SUB];
     auto drain = [&](int slot) -> Status {
         Workspace& ws = *W[slot];
         if (!pending_cnt[slot]) return Status::Ok();
         const uint64_t first = pending_first[slot];
-        const int cnt = pending_cnt[slot], sub = pending_sub[slot];
+        const int cnt = pending_cnt[slot];
         if (cells) {
-            for (int s = 0; s < pending_nsub[slot]; s++) {
+            for (int s = 0; s < pending_np[slot]; s++) {
                 EKZG_CUDA(cudaEventSynchronize(ws.sub_out[s]));
-                const int o = s * sub, c = std::min(sub, cnt - o);
+                const int o = piece_off[slot][s], c = piece_len[slot][s];
                 if (!cells_pinned) memcpy(cells + (first + o) * CELLS_PER_BLOB, ws.h_cells + (size_t)o * CELLS_PER_BLOB, (size_t)c * CELLS_PER_BLOB);
             }
         }
+        tr.mark("cells of the chunk are in host memory");
         EKZG_CUDA(cudaEventSynchronize(ws.done));
+        tr.mark("kernels + proofs D2H done");
         if (want_proofs && !proofs_pinned) memcpy(proofs + first * PROOFS_PER_BLOB, ws.h_proofs, (size_t)cnt * PROOFS_PER_BLOB);
         for (int i = 0; i < cnt; i++) {
             if (ws.h_status[i]) any_bad = true;
@@ -410,22 +427,47 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
         pending_cnt[slot] = 0;
         return Status::Ok();
     };
+    // One chunk.  Three streams: in_stream carries the blobs to the device piece by piece (50 GB/s: 1024 blobs in 2.6 ms);
+    // ws.stream runs ALL kernels in order -- K1, K2, K4 of the first piece (a quarter of the chunk) as soon as that piece has
+    // arrived, then K1, K2, K4 of the rest, then K5 (which wants the whole chunk for its parallelism) and K6; copy_stream takes
+    // the cells of a piece home as soon as its K1 is done, i.e. underneath the ~90 ms of FK20 kernels.
+    // (K1 must not run on a stream of its own next to K4: its 1024-thread, 128 KiB CTAs do not fit beside K4's resident CTAs and
+    // starve until K4 ends -- measured: K1 of sub-block 5 waited 13 ms, profiles/r1_v4_e2e_timeline.txt.)
     auto submit = [&](int slot, uint64_t first, int cnt) -> Status {
         Workspace& ws = *W[slot];
-        const int nsub = std::min(Workspace::MAX_SUB, (cnt + 63) / 64);
-        const int sub = (cnt + nsub - 1) / nsub;
+        int np = 0;
+        int* off = piece_off[slot];
+        int* len = piece_len[slot];
+        if (want_proofs) {
+            const int q = cnt >= 512 ? ((cnt / 4 + 31) & ~31) : cnt;
+            off[np] = 0; len[np++] = q;
+            if (q < cnt) { off[np] = q; len[np++] = cnt - q; }
+        } else {   // cells only: nothing but copies and K1, finer pieces keep both copy engines busy
+            const int n_p = std::min(Workspace::MAX_SUB, (cnt + 127) / 128), per = (cnt + n_p - 1) / n_p;
+            for (int o = 0; o < cnt; o += per) { off[np] = o; len[np++] = std::min(per, cnt - o); }
+        }
+        EKZG_CUDA(cudaStreamWaitEvent(ws.in_stream, ws.done, 0));   // (the previous chunk of this workspace has left the buffers)
+        stamp("start", -1, ws.in_stream);
         EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * cnt, ws.stream));
-        int used = 0;
-        for (int s = 0; s * sub < cnt; s++, used++) {
-            const int o = s * sub, c = std::min(sub, cnt - o);
-            const uint8_t* src = blobs + (first + o) * BYTES_PER_BLOB;
-            if (!in_pinned) {
-                memcpy(ws.h_blobs + (size_t)o * BYTES_PER_BLOB, src, (size_t)c * BYTES_PER_BLOB);
-                src = ws.h_blobs + (size_t)o * BYTES_PER_BLOB;
+        for (int s = 0; s < np; s++) {
+            const int o = off[s], c = len[s];
+            if (in_pinned) {
+                EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs + (size_t)o * BYTES_PER_BLOB, blobs + (first + o) * BYTES_PER_BLOB, (size_t)c * BYTES_PER_BLOB,
+                                          cudaMemcpyHostToDevice, ws.in_stream));
+            } else {   // pageable caller memory: through the pinned staging buffer in slices, each slice's DMA under the next host copy
+                for (int i = 0; i < c; i += 64) {
+                    const int cc = std::min(64, c - i);
+                    uint8_t* stage = ws.h_blobs + (size_t)(o + i) * BYTES_PER_BLOB;
+                    memcpy(stage, blobs + (first + o + i) * BYTES_PER_BLOB, (size_t)cc * BYTES_PER_BLOB);
+                    EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs + (size_t)(o + i) * BYTES_PER_BLOB, stage, (size_t)cc * BYTES_PER_BLOB, cudaMemcpyHostToDevice, ws.in_stream));
+                }
             }
-            EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs + (size_t)o * BYTES_PER_BLOB, src, (size_t)c * BYTES_PER_BLOB, cudaMemcpyHostToDevice, ws.stream));
+            stamp("H2D done, piece", s, ws.in_stream);
+            EKZG_CUDA(cudaEventRecord(ws.piece_in[s], ws.in_stream));
+            EKZG_CUDA(cudaStreamWaitEvent(ws.stream, ws.piece_in[s], 0));
             EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs + (size_t)o * BYTES_PER_BLOB, ws.d_coeffs + (size_t)o * N_BLOB,
                                                   cells ? ws.d_cells + (size_t)o * CELLS_PER_BLOB : nullptr, ws.d_status + o, T_, c, cells != nullptr, ws.stream));
+            stamp("K1 done, piece", s, ws.stream);
             if (cells) {
                 EKZG_CUDA(cudaEventRecord(ws.sub_ready[s], ws.stream));
                 EKZG_CUDA(cudaStreamWaitEvent(ws.copy_stream, ws.sub_ready[s], 0));
@@ -433,18 +475,26 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
                 EKZG_CUDA(cudaMemcpyAsync(dst, ws.d_cells + (size_t)o * CELLS_PER_BLOB, (size_t)c * CELLS_PER_BLOB, cudaMemcpyDeviceToHost, ws.copy_stream));
                 EKZG_CUDA(cudaEventRecord(ws.sub_out[s], ws.copy_stream));
             }
+            if (want_proofs) {
+                EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, cnt, ws.stream, o, c));
+                EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, cnt, ws.stream, o, c));
+                stamp("K4 done, piece", s, ws.stream);
+            }
         }
         if (want_proofs) {
-            EKZG_TRY(fk20_from_coeffs_device(ws, cnt, ws.d_cells, ws.d_proofs, ws.stream));
+            EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, cnt, ws.d_queue, ws.stream));
+            stamp("K5 done", -1, ws.stream);
+            EKZG_CUDA(launch_g1_compress(ws.d_pts, ws.d_proofs, N_CELLS, cnt, ws.stream));
             EKZG_CUDA(cudaMemcpyAsync(proofs_pinned ? proofs + first * PROOFS_PER_BLOB : ws.h_proofs, ws.d_proofs, (size_t)cnt * PROOFS_PER_BLOB,
                                       cudaMemcpyDeviceToHost, ws.stream));
+            stamp("K6 + proofs D2H done", -1, ws.stream);
         }
         EKZG_CUDA(cudaMemcpyAsync(ws.h_status, ws.d_status, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ws.stream));
         EKZG_CUDA(cudaEventRecord(ws.done, ws.stream));
         pending_first[slot] = first;
         pending_cnt[slot] = cnt;
-        pending_sub[slot] = sub;
-        pending_nsub[slot] = used;
+        pending_np[slot] = np;
+        tr.mark("chunk enqueued");
         return Status::Ok();
     };
     for (uint64_t c = 0; c < nchunks && result.ok; c++) {
@@ -457,8 +507,18 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
     for (int slot = 0; slot < 2; slot++) {
         if (!W[slot]) continue;
         if (result.ok) result = drain(slot);
-        if (!result.ok) { cudaStreamSynchronize(W[slot]->stream); cudaStreamSynchronize(W[slot]->copy_stream); }
+        if (!result.ok) { cudaStreamSynchronize(W[slot]->in_stream); cudaStreamSynchronize(W[slot]->stream); cudaStreamSynchronize(W[slot]->copy_stream); }
         give_back(W[slot]);
+    }
+    if (tr.on && !tl.empty()) {
+        cudaDeviceSynchronize();
+        for (auto& pe : tl) {
+            float ms = 0;
+            cudaError_t ee = cudaEventElapsedTime(&ms, tl[0].second, pe.second);
+            if (ee == cudaSuccess) fprintf(stderr, "[ekzg timeline] %8.3f ms  %s\n", ms, pe.first.c_str());
+            else fprintf(stderr, "[ekzg timeline] %s: %s\n", pe.first.c_str(), cudaGetErrorString(ee));
+        }
+        for (auto& pe : tl) cudaEventDestroy(pe.second);
     }
     if (!result.ok) return result;
     if (any_bad) return Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus");

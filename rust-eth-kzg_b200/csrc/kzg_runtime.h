@@ -31,10 +31,12 @@ struct Workspace {
     int capacity = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // D2H of the cells while the FK20 kernels run on `stream`
+    cudaStream_t in_stream = nullptr;            // H2D of the blobs, piece by piece, ahead of the kernels on `stream`
     cudaEvent_t done = nullptr;
-    static constexpr int MAX_SUB = 16;           // sub-blocks of a chunk for copy / K1 / copy-out pipelining
-    cudaEvent_t sub_ready[MAX_SUB] = {};         // K1 of sub-block s finished (recorded on `stream`)
-    cudaEvent_t sub_out[MAX_SUB] = {};           // cells of sub-block s are in host memory (recorded on `copy_stream`)
+    static constexpr int MAX_SUB = 16;           // pieces of a chunk for copy-in / K1 / copy-out pipelining
+    cudaEvent_t piece_in[MAX_SUB] = {};          // blobs of piece s are on the device (recorded on `in_stream`)
+    cudaEvent_t sub_ready[MAX_SUB] = {};         // K1 of piece s finished (recorded on `stream`)
+    cudaEvent_t sub_out[MAX_SUB] = {};           // cells of piece s are in host memory (recorded on `copy_stream`)
     // device
     uint8_t* d_blobs = nullptr;
     Fr* d_coeffs = nullptr;
