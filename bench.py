@@ -284,12 +284,16 @@ def main():
     value = total_blobs / (dev_ms / 1000)
     e2e = total_blobs / (e2e_ms / 1000)
     w, nw = ctx.window, 255 // ctx.window + 1
+    # merged top window (MsmTable::mg in csrc/kzg_device.cuh): nw - 1 + 1/mg table additions per scalar
+    rtop = (1 << (255 - w * (nw - 1))) + 1
+    mg = next((m for m in (4, 2) if rtop ** m - 1 <= 1 << (w - 1)), 1)
+    adds_per_scalar = nw - 1 + 1.0 / mg
     names = ["K1_blob_to_coeffs_cells", "K2_toeplitz_scalars", "K4_fk20_msm", "K5_g1_ntt", "K6_compress"]
     stages = {nm: ms / max(nb, 1) for nm, ms in zip(names, stage_ms)}
     tot = sum(stages.values()) or 1.0
     # dominant kernel = K4 (one launch per batch).  HBM view: table gathers + scalar reads + point writes.
     msm_ms = stages["K4_fk20_msm"]
-    msm_bytes = n * (128 * 64 * nw * 96 + 128 * 64 * 32 + 128 * 144)
+    msm_bytes = int(n * (128 * 64 * adds_per_scalar * 96 + 128 * 64 * 32 + 128 * 144))
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -297,7 +301,7 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     ach = msm_bytes / (msm_ms / 1000) / 1e9 if msm_ms else 0.0
-    msm_imad = n * 128 * 64 * nw * OP_XYZZ_MADD
+    msm_imad = int(n * 128 * 64 * adds_per_scalar * OP_XYZZ_MADD)
     k5_imad, k5_heavy = k5_imad_per_blob()
     ntt_imad = n * k5_imad
     roofline = {"bound": "hbm", "kernel": "k_fk20_msm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,

@@ -186,19 +186,34 @@ k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTab
     G1Xyzz acc;
     xyzz_set_inf(acc);
     if (active) {
-        const int w = T.w, nw = T.nw;
+        const int w = T.w, nw = T.nw, mg = T.mg;
+        const int nreg = mg > 1 ? nw - 1 : nw;   // windows with a slice of their own
+        int comb = 0, radix = 1;                 // merged top digits of the current group of mg points (MsmTable)
         for (int kk = 0; kk < KPER; kk++) {
             const int k = slice * KPER + kk;
             const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)(j * FK20_POINTS + k) * B + b) * 8);
             uint4 s0 = sp[0], s1 = sp[1];
             uint32_t s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
             const G1Affine* tb = T.table + (size_t)(j * FK20_POINTS + k) * T.nw * T.half;
-            for (int t = 0; t < nw; t++) {
+            for (int t = 0; t < nreg; t++) {
                 int d = booth_digit(s, t, w);
                 if (d != 0) {
                     int m = (d < 0 ? -d : d) - 1;
                     G1Affine e = ld_vec(&tb[(size_t)t * T.half + m]);
                     xyzz_madd(acc, e, d < 0);
+                }
+            }
+            if (mg > 1) {
+                comb += booth_digit(s, nw - 1, w) * radix;   // in [0, rtop): scalars are < 2^255
+                radix *= T.rtop;
+                if ((kk & (mg - 1)) == mg - 1) {
+                    if (comb != 0) {
+                        const G1Affine* tg = tb - (size_t)(mg - 1) * T.nw * T.half;   // top slice of the group's first point
+                        G1Affine e = ld_vec(&tg[(size_t)(nw - 1) * T.half + comb - 1]);
+                        xyzz_madd(acc, e, false);
+                    }
+                    comb = 0;
+                    radix = 1;
                 }
             }
         }
@@ -529,6 +544,38 @@ k_fk20_table_fill(const G1Affine* __restrict__ qaff, G1Affine* __restrict__ tabl
     }
 }
 
+// FK20 setup, step 4: merged top-window slices (MsmTable::mg).  For every group of mg consecutive points, entry c - 1 of the
+// top slice of the group's first point becomes sum_i d_i * Q_i, c = sum_i d_i * rtop^i, Q_i = 2^(w(nw-1)) * P_i (qaff).
+// One thread per entry; the d_i are at most 2^tb <= 2^(w-1), a plain double-and-add each.
+__global__ void __launch_bounds__(128)
+k_fk20_top_merge_fill(const G1Affine* __restrict__ qaff, G1Affine* __restrict__ table, int nw, int half, int rtop, int mg, int ncomb, size_t ngroups) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= ngroups * (size_t)(ncomb - 1)) return;
+    const size_t g = gid / (ncomb - 1);
+    int c = (int)(gid % (ncomb - 1)) + 1;
+    const int c0 = c;
+    G1Jac acc;
+    jac_set_inf(acc);
+    for (int i = 0; i < mg; i++) {
+        const int d = c % rtop;
+        c /= rtop;
+        if (!d) continue;
+        const G1Affine q = ld_vec(&qaff[(g * mg + i) * nw + (nw - 1)]);
+        G1Jac t;
+        jac_set_inf(t);
+        for (int bit = 31 - __clz((unsigned)d); bit >= 0; bit--) {
+            jac_dbl(t, t);
+            if ((d >> bit) & 1) jac_madd(t, q, false);
+        }
+        jac_add(acc, t);
+    }
+    Fp zi;
+    fp_inv(zi, acc.z);   // a non-trivial combination of independent points of prime order is never the identity
+    G1Affine a;
+    jac_to_affine_with_inv(a, acc, zi);
+    st_vec(&table[((g * mg) * nw + (nw - 1)) * (size_t)half + (c0 - 1)], a);
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch wrappers
 // ------------------------------------------------------------------------------------------------
@@ -644,6 +691,14 @@ static cudaError_t fill_table(const G1Jac* pts, const G1Affine* aff, int npoints
     size_t nthreads = nbases * chunks;
     k_fk20_table_fill<<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(qaff, table, T.half, nbases);
     EKZG_LAUNCH_CHECK();
+    if (T.mg > 1) {
+        if (npoints % T.mg) return cudaErrorInvalidValue;
+        int ncomb = 1;
+        for (int i = 0; i < T.mg; i++) ncomb *= T.rtop;
+        const size_t ngroups = (size_t)npoints / T.mg, n = ngroups * (size_t)(ncomb - 1);
+        k_fk20_top_merge_fill<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(qaff, table, T.nw, T.half, T.rtop, T.mg, ncomb, ngroups);
+        EKZG_LAUNCH_CHECK();
+    }
     return cudaSuccess;
 }
 

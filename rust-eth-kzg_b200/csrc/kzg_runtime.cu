@@ -168,15 +168,11 @@ Status Context::init(bool use_precomp) {
         }
     }
     if (w < 4 || w > 16) return Status::Error("EKZG_FK20_WINDOW must be in [4, 16]");
-    T_.fk20.w = w;
-    T_.fk20.nw = 255 / w + 1;
-    T_.fk20.half = 1 << (w - 1);
+    T_.fk20.set_window(w);
     int ws = use_precomp ? 12 : 8;   // w = 12: 17.7 GiB of tables for the 4096 monomial points, 22 additions per scalar
     if (const char* e = getenv("EKZG_SRS_WINDOW")) ws = atoi(e);
     if (ws < 4 || ws > 16) return Status::Error("EKZG_SRS_WINDOW must be in [4, 16]");
-    T_.srs.w = ws;
-    T_.srs.nw = 255 / ws + 1;
-    T_.srs.half = 1 << (ws - 1);
+    T_.srs.set_window(ws);
 
     cudaStream_t st = 0;
     // twiddles
