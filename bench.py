@@ -305,7 +305,7 @@ def main():
     k5_imad, k5_heavy = k5_imad_per_blob()
     ntt_imad = n * k5_imad
     roofline = {"bound": "hbm", "kernel": "k_fk20_msm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": 26.77e9 * n / 1024 if w == 14 else None, "traffic_source": "ncu --set full, dram__bytes_read+write per launch at 1024 blobs, w=14 (profiles/r1_v3_prof_k4_k5_raw.csv)",
+                "traffic": 27.08e9 * n / 1024 if w == 14 else None, "traffic_source": "ncu --set full, dram__bytes_read+write per launch at 1024 blobs, w=14 (profiles/r1_v4_prof_k4_k5_raw.csv)",
                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "note": "HBM view of the table-streaming MSM: the gathers are far below the HBM roofline; the kernel is bound by the integer multiply (fmaheavy) pipe, see roofline_imad"}
     roofline_imad = {
