@@ -79,6 +79,85 @@ EKZG_HD_CALL void jac_mul_glv16(G1Jac& out, const G1Jac& p, const int8_t* d) {
     out = acc;
 }
 
+// GLV split of a VARIABLE scalar k < r:  k = k1 + k2*lambda with k2 = floor(k / lambda), k1 = k mod lambda.  Because
+// r = lambda^2 + lambda + 1, both halves are non-negative and below 2^128.  The quotient comes from the 129-bit reciprocal
+// floor(2^256 / lambda) (at most 2 too small, fixed up by subtraction), then both halves are recoded into the signed radix-16
+// digits jac_mul_glv16 takes: 128 doublings + 66 additions instead of the 252 + 63 of jac_mul_u256.
+// Used by the verifiers' random-linear-combination scalar multiplications (reference: g1_lincomb -> blst Pippenger,
+// crates/cryptography/bls12_381/src/lincomb.rs:7-30; one multiplication per thread here).
+EKZG_HD void glv_split_digits(int8_t* d /*66*/, const uint32_t* k /*8 limbs, < r*/) {
+    const uint32_t lam[4] = {GLV_LAMBDA[0], GLV_LAMBDA[1], GLV_LAMBDA[2], GLV_LAMBDA[3]};
+    const uint32_t rec[5] = {0xf6cfee30u, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x1u};   // floor(2^256 / lambda)
+    // q = (k * rec) >> 256
+    uint32_t prod[13];
+    for (int i = 0; i < 13; i++) prod[i] = 0;
+    for (int i = 0; i < 8; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 5; j++) {
+            uint64_t t = (uint64_t)k[i] * rec[j] + prod[i + j] + c;
+            prod[i + j] = (uint32_t)t;
+            c = t >> 32;
+        }
+        prod[i + 5] = (uint32_t)c;
+    }
+    uint32_t q[5] = {prod[8], prod[9], prod[10], prod[11], prod[12]};
+    // k1 = k - q*lambda, exact below 3*lambda < 2^130: 5 limbs are enough
+    uint32_t ql[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 5; i++) {
+        uint64_t c = 0;
+        for (int j = 0; j < 4; j++) {
+            uint64_t t = (uint64_t)q[i] * lam[j] + ql[i + j] + c;
+            ql[i + j] = (uint32_t)t;
+            c = t >> 32;
+        }
+        ql[i + 4] = (uint32_t)c;
+    }
+    uint32_t k1[5];
+    {
+        uint64_t b = 0;
+        for (int i = 0; i < 5; i++) {
+            uint64_t t = (uint64_t)k[i] - ql[i] - b;
+            k1[i] = (uint32_t)t;
+            b = (t >> 32) & 1;
+        }
+    }
+    for (int it = 0; it < 3; it++) {
+        // k1 >= lambda ?
+        bool ge = k1[4] != 0;
+        if (!ge) {
+            ge = true;
+            for (int i = 3; i >= 0; i--) {
+                if (k1[i] != lam[i]) { ge = k1[i] > lam[i]; break; }
+            }
+        }
+        if (!ge) break;
+        uint64_t b = 0;
+        for (int i = 0; i < 5; i++) {
+            uint64_t t = (uint64_t)k1[i] - (i < 4 ? lam[i] : 0u) - b;
+            k1[i] = (uint32_t)t;
+            b = (t >> 32) & 1;
+        }
+        uint64_t c = 1;
+        for (int i = 0; i < 5; i++) { uint64_t t = (uint64_t)q[i] + c; q[i] = (uint32_t)t; c = t >> 32; }
+    }
+    // signed radix-16 digits in [-7, 8], least significant first, 33 per half
+    for (int h = 0; h < 2; h++) {
+        const uint32_t* v = h ? q : k1;
+        int carry = 0;
+        for (int i = 0; i < 32; i++) {
+            int x = (int)((v[i >> 3] >> ((i & 7) * 4)) & 15u) + carry;
+            carry = x > 8;
+            d[33 * h + i] = (int8_t)(carry ? x - 16 : x);
+        }
+        d[33 * h + 32] = (int8_t)carry;
+    }
+}
+EKZG_HD_CALL void jac_mul_fr_glv(G1Jac& out, const G1Jac& p, const uint32_t* k /*8 limbs, < r*/) {
+    int8_t d[66];
+    glv_split_digits(d, k);
+    jac_mul_glv16(out, p, d);
+}
+
 // r = a + b for Jacobian a, affine b, a != +-b, neither the identity (madd-2004-hmv: 8M + 3S, Z3 = Z1*H);
 // zr = H = Z3/Z1 is handed back for the common-Z table below.
 EKZG_HD_CALL void jac_madd_zr(G1Jac& r, const G1Jac& a, const G1Affine& b, Fp& zr) {

@@ -143,7 +143,8 @@ k_scalar_mul(const G1Affine* __restrict__ pts, const uint32_t* __restrict__ scal
     const uint4* s4 = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
     uint4 lo = s4[0], hi = s4[1];
     k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
-    jac_mul_u256(r, p, k);
+    if (g1a_is_inf(a)) jac_set_inf(r);
+    else jac_mul_fr_glv(r, p, k);   // scalars are canonical Fr values (< r): GLV halves the doublings
     st_vec(&out[i], r);
 }
 

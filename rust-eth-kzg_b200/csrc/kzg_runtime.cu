@@ -47,6 +47,7 @@ Status Workspace::alloc(int cap, bool with_io) {
     EKZG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     EKZG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     EKZG_CUDA(cudaStreamCreateWithFlags(&in_stream, cudaStreamNonBlocking));
+    EKZG_CUDA(cudaStreamCreateWithFlags(&aux_stream, cudaStreamNonBlocking));
     EKZG_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     for (auto& e : piece_in) EKZG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     for (int i = 0; i < MAX_SUB; i++) {
@@ -98,6 +99,7 @@ void Workspace::release() {
         if (sub_out[i]) cudaEventDestroy(sub_out[i]);
     }
     for (auto& e : piece_in) if (e) cudaEventDestroy(e);
+    if (aux_stream) cudaStreamDestroy(aux_stream);
     if (in_stream) cudaStreamDestroy(in_stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
     if (stream) cudaStreamDestroy(stream);

@@ -32,6 +32,7 @@ struct Workspace {
     cudaStream_t stream = nullptr;
     cudaStream_t copy_stream = nullptr;          // D2H of the cells while the FK20 kernels run on `stream`
     cudaStream_t in_stream = nullptr;            // H2D of the blobs, piece by piece, ahead of the kernels on `stream`
+    cudaStream_t aux_stream = nullptr;           // fourth lane for the verifier's independent latency-bound chains
     cudaEvent_t done = nullptr;
     static constexpr int MAX_SUB = 16;           // pieces of a chunk for copy-in / K1 / copy-out pipelining
     cudaEvent_t piece_in[MAX_SUB] = {};          // blobs of piece s are on the device (recorded on `in_stream`)

@@ -6,6 +6,8 @@
 #include <string>
 #include "host_pairing.h"
 #include "host_sha256.h"
+#include <array>
+#include <future>
 #include <unordered_map>
 #include "kzg_runtime.h"
 #include "sha256.cuh"
@@ -102,8 +104,30 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
     }
     const uint8_t* hcells = cells_contig ? cells[0] : hcells_store.data();
     tr.mark("dedup + pack");
+    // Fiat-Shamir transcript (fk20/verifier.rs:269-328): ONE sequential SHA-256 chain over every input byte (34.6 MB for
+    // 128 x 128 cells, 21 ms with the x86 SHA extensions).  It only needs host data, so it starts now on a helper thread
+    // while this thread stages the copies (the 33 MB of cells are pageable caller memory: a synchronous 3 ms) and the device
+    // validates the points.
+    std::future<std::array<uint8_t, 32>> hash_task = std::async(std::launch::async, [&]() {
+        std::array<uint8_t, 32> out;
+        host::Sha256Stream h;
+        uint8_t head[16 + 32];
+        memcpy(head, "RCKZGCBATCH__V1_", 16);
+        be64(head + 16, N_BLOB); be64(head + 24, CELL_ELEMS); be64(head + 32, (uint64_t)M); be64(head + 40, (uint64_t)N);
+        h.update(head, sizeof head);
+        h.update(hc.data(), hc.size());
+        for (int k = 0; k < N; k++) {
+            uint8_t idx[16];
+            be64(idx, rows[k]); be64(idx + 8, hcol[k]);
+            h.update(idx, 16);
+            h.update(&hcells[(size_t)k * BYTES_PER_CELL], BYTES_PER_CELL);
+            h.update(&hp[(size_t)k * 48], 48);
+        }
+        h.final(out.data());
+        return out;
+    });
     Workspace* wsp = acquire(1, true);
-    if (!wsp) return Status::Error("allocation failed");
+    if (!wsp) { hash_task.wait(); return Status::Error("allocation failed"); }
     cudaStream_t st = wsp->stream;
     Status result = Status::Ok();
     uint32_t pin[50];
@@ -116,13 +140,13 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             uint32_t *d_col, *d_row, *d_stc, *d_stp, *d_cellst, *d_s1, *d_s2, *d_w, *d_i, *d_out;
             G1Affine *a_c, *a_p;
             Fr *d_rpow, *d_interp;
-            G1Jac *d_mul, *d_part, *d_sums, *d_colsum;
+            G1Jac *d_mul, *d_mul_b, *d_mul_c, *d_mul_d, *d_part, *d_part_b, *d_part_d, *d_sums, *d_colsum;
             EKZG_TRY(S.get(&d_colsum, 2 * N_CELLS));
             EKZG_TRY(S.get(&d_c, (size_t)M * 48)); EKZG_TRY(S.get(&d_p, (size_t)N * 48)); EKZG_TRY(S.get(&d_cells, (size_t)N * BYTES_PER_CELL));
             EKZG_TRY(S.get(&d_hash, 32)); EKZG_TRY(S.get(&d_col, N)); EKZG_TRY(S.get(&d_row, N)); EKZG_TRY(S.get(&d_stc, M)); EKZG_TRY(S.get(&d_stp, N));
             EKZG_TRY(S.get(&d_cellst, 1)); EKZG_TRY(S.get(&d_s1, (size_t)N * 8)); EKZG_TRY(S.get(&d_s2, (size_t)N * 8)); EKZG_TRY(S.get(&d_w, (size_t)M * 8));
             EKZG_TRY(S.get(&d_i, 64 * 8)); EKZG_TRY(S.get(&d_out, 50)); EKZG_TRY(S.get(&a_c, M)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_rpow, N));
-            EKZG_TRY(S.get(&d_interp, (size_t)N * 64)); EKZG_TRY(S.get(&d_mul, std::max(N, 128))); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 4));
+            EKZG_TRY(S.get(&d_interp, (size_t)N * 64)); EKZG_TRY(S.get(&d_mul, std::max(N, 128))); EKZG_TRY(S.get(&d_mul_b, std::max(M, 128))); EKZG_TRY(S.get(&d_mul_c, 128)); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_part_b, 148)); EKZG_TRY(S.get(&d_mul_d, std::max(N, 128))); EKZG_TRY(S.get(&d_part_d, 148)); EKZG_TRY(S.get(&d_sums, 4));
             EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_cells, hcells, (size_t)N * BYTES_PER_CELL, cudaMemcpyHostToDevice, st));
@@ -132,45 +156,52 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             // point validation runs while the host hashes the transcript
             EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, M, true, st));
             EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, true, st));
-            // Fiat-Shamir transcript (fk20/verifier.rs:269-328), sequential SHA-256 on the host
             tr.mark("alloc + enqueue copies/validation");
-            uint8_t hash[32];
-            {
-                host::Sha256Stream h;
-                uint8_t head[16 + 32];
-                memcpy(head, "RCKZGCBATCH__V1_", 16);
-                be64(head + 16, N_BLOB); be64(head + 24, CELL_ELEMS); be64(head + 32, (uint64_t)M); be64(head + 40, (uint64_t)N);
-                h.update(head, sizeof head);
-                h.update(hc.data(), hc.size());
-                for (int k = 0; k < N; k++) {
-                    uint8_t idx[16];
-                    be64(idx, rows[k]); be64(idx + 8, hcol[k]);
-                    h.update(idx, 16);
-                    h.update(&hcells[(size_t)k * BYTES_PER_CELL], BYTES_PER_CELL);
-                    h.update(&hp[(size_t)k * 48], 48);
-                }
-                h.final(hash);
-            }
-            tr.mark("transcript sha256");
+            const std::array<uint8_t, 32> hash_arr = hash_task.get();
+            const uint8_t* hash = hash_arr.data();
+            tr.mark("waiting for the transcript sha256");
             EKZG_CUDA(cudaMemcpyAsync(d_hash, hash, 32, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(launch_powers_from_hash(d_hash, d_rpow, N, st));
             EKZG_CUDA(launch_cell_verify_scalars(d_rpow, d_col, d_s1, d_s2, T_, N, st));
-            // P = sum rho_k pi_k ; W = sum rho_k h_k^64 pi_k: one pass of N scalar multiplications, then per-column sums
-            // and 128 multiplications by fixed roots of unity (kzg_kernels_verify.cu: k_column_sums)
-            EKZG_CUDA(launch_scalar_mul(a_p, d_s1, d_mul, N, st));
-            EKZG_CUDA(launch_column_sums(d_mul, d_col, d_colsum, d_colsum + N_CELLS, N, st));
-            EKZG_CUDA(launch_sum_points(d_colsum, N_CELLS, d_part, &d_sums[0], st));
-            EKZG_CUDA(launch_sum_points(d_colsum + N_CELLS, N_CELLS, d_part, &d_sums[1], st));
-            // Cs = sum w_i C_i
-            EKZG_CUDA(launch_commitment_weights(d_rpow, d_row, d_w, N, M, st));
-            EKZG_CUDA(launch_scalar_mul(a_c, d_w, d_mul, M, st));
-            EKZG_CUDA(launch_sum_points(d_mul, M, d_part, &d_sums[2], st));
-            // Ic = commit(sum rho_k I_k): 64 coefficients on the first 64 monomial SRS points = group 0 of the fixed-base
-            // SRS tables (natural position 0 of a 128-slot row)
-            EKZG_CUDA(launch_cell_interp(d_cells, d_col, d_rpow, d_interp, d_cellst, T_, N, st));
-            EKZG_CUDA(launch_interp_column_sum(d_interp, d_i, N, st));
-            EKZG_CUDA(launch_fixed_msm(d_i, d_mul, T_.srs, 1, 1, st));
-            EKZG_CUDA(cudaMemcpyAsync(&d_sums[3], d_mul, sizeof(G1Jac), cudaMemcpyDeviceToDevice, st));
+            // Independent, latency-bound chains follow (a handful of CTAs each: one 255-bit scalar multiplication takes ~3 ms
+            // whatever the count): they run side by side on the workspace's four streams.
+            cudaStream_t sb = wsp->copy_stream, sc = wsp->in_stream, sd = wsp->aux_stream;
+            EKZG_CUDA(cudaEventRecord(wsp->sub_ready[0], st));
+            EKZG_CUDA(cudaStreamWaitEvent(sb, wsp->sub_ready[0], 0));
+            EKZG_CUDA(cudaStreamWaitEvent(sc, wsp->sub_ready[0], 0));
+            // (A)  P = sum rho_k pi_k ; W = sum rho_k h_k^64 pi_k  (verifier.rs:188-213)
+            static const bool force_columns = getenv("EKZG_VERIFY_COLUMN_SUMS") != nullptr;
+            if (N <= 32768 && !force_columns) {
+                // two passes of N scalar multiplications at the same time (the machine holds both; 16384 points are 512 warps)
+                EKZG_CUDA(cudaStreamWaitEvent(sd, wsp->sub_ready[0], 0));
+                EKZG_CUDA(launch_scalar_mul(a_p, d_s1, d_mul, N, st));
+                EKZG_CUDA(launch_sum_points(d_mul, N, d_part, &d_sums[0], st));
+                EKZG_CUDA(launch_scalar_mul(a_p, d_s2, d_mul_d, N, sd));
+                EKZG_CUDA(launch_sum_points(d_mul_d, N, d_part_d, &d_sums[1], sd));
+                EKZG_CUDA(cudaEventRecord(wsp->sub_out[2], sd));
+                EKZG_CUDA(cudaStreamWaitEvent(st, wsp->sub_out[2], 0));
+            } else {
+                // large batches are throughput-bound: ONE pass of N scalar multiplications, then per-column sums and 128
+                // multiplications by fixed roots of unity (kzg_kernels_verify.cu: k_column_sums)
+                EKZG_CUDA(launch_scalar_mul(a_p, d_s1, d_mul, N, st));
+                EKZG_CUDA(launch_column_sums(d_mul, d_col, d_colsum, d_colsum + N_CELLS, N, st));
+                EKZG_CUDA(launch_sum_points(d_colsum, N_CELLS, d_part, &d_sums[0], st));
+                EKZG_CUDA(launch_sum_points(d_colsum + N_CELLS, N_CELLS, d_part, &d_sums[1], st));
+            }
+            // (B, on sb)  Cs = sum w_i C_i
+            EKZG_CUDA(launch_commitment_weights(d_rpow, d_row, d_w, N, M, sb));
+            EKZG_CUDA(launch_scalar_mul(a_c, d_w, d_mul_b, M, sb));
+            EKZG_CUDA(launch_sum_points(d_mul_b, M, d_part_b, &d_sums[2], sb));
+            EKZG_CUDA(cudaEventRecord(wsp->sub_out[0], sb));
+            // (C, on sc)  Ic = commit(sum rho_k I_k): 64 coefficients on the first 64 monomial SRS points = group 0 of the
+            // fixed-base SRS tables (natural position 0 of a 128-slot row)
+            EKZG_CUDA(launch_cell_interp(d_cells, d_col, d_rpow, d_interp, d_cellst, T_, N, sc));
+            EKZG_CUDA(launch_interp_column_sum(d_interp, d_i, N, sc));
+            EKZG_CUDA(launch_fixed_msm(d_i, d_mul_c, T_.srs, 1, 1, sc));
+            EKZG_CUDA(cudaMemcpyAsync(&d_sums[3], d_mul_c, sizeof(G1Jac), cudaMemcpyDeviceToDevice, sc));
+            EKZG_CUDA(cudaEventRecord(wsp->sub_out[1], sc));
+            EKZG_CUDA(cudaStreamWaitEvent(st, wsp->sub_out[0], 0));
+            EKZG_CUDA(cudaStreamWaitEvent(st, wsp->sub_out[1], 0));
             // pairing inputs: (P, [tau^64]_2), (Cs - Ic + W, -[1]_2)
             EKZG_CUDA(launch_pairing_inputs(&d_sums[0], &d_sums[2], &d_sums[3], &d_sums[1], d_out, st));
             EKZG_CUDA(cudaMemcpyAsync(pin, d_out, sizeof pin, cudaMemcpyDeviceToHost, st));
@@ -182,7 +213,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             return Status::Ok();
         };
         result = run();
-        if (!result.ok) cudaStreamSynchronize(st);
+        if (!result.ok) { cudaStreamSynchronize(wsp->copy_stream); cudaStreamSynchronize(wsp->in_stream); cudaStreamSynchronize(wsp->aux_stream); cudaStreamSynchronize(st); }
     }
     give_back(wsp);
     if (!result.ok) return result;

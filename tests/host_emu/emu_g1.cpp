@@ -61,6 +61,12 @@ int emu_g1_mul_u256(const uint8_t* p48, const uint32_t* k, uint8_t* out) {
     G1Affine p; if (g1a_decompress(p, p48)) return 1;
     G1Jac j, r; jac_from_affine(j, p); jac_mul_u256(r, j, k); out48(out, r); return 0;
 }
+int emu_g1_mul_fr_glv(const uint8_t* p48, const uint32_t* k, uint8_t* out) {
+    G1Affine p; if (g1a_decompress(p, p48)) return 1;
+    G1Jac j, r; jac_from_affine(j, p);
+    jac_dbl(j, j);  // make Z != 1; python accounts for the factor 2
+    jac_mul_fr_glv(r, j, k); out48(out, r); return 0;
+}
 int emu_g1_mul_twiddle(const uint8_t* p48, int e, uint8_t* out) {
     G1Affine p; if (g1a_decompress(p, p48)) return 1;
     G1Jac j, r; jac_from_affine(j, p);

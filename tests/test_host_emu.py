@@ -177,6 +177,12 @@ def test_g1_scalar_mul(emu_g1):
     for k in [0, 1, 2, R - 1, rng.randrange(R), rng.randrange(2**256)]:
         assert emu_g1.emu_g1_mul_u256(pb, arr(k, 8), out) == 0
         assert out.raw == pyref.g1_compress(pyref.g1_mul(pt, k % R))
+    # GLV split of a variable scalar (the verifiers' scalar multiplications): edge values around multiples of lambda
+    lam = 0xac45a4010001a40200000000ffffffff
+    for k in [0, 1, 8, 9, lam - 1, lam, lam + 1, 2 * lam - 1, 2 * lam, lam * lam, lam * lam + lam, R - 1, R - 2, (1 << 128) - 1, 1 << 128,
+              0x8888888888888888888888888888888888888888888888888888888888888888 % R] + [rng.randrange(R) for _ in range(6)]:
+        assert emu_g1.emu_g1_mul_fr_glv(pb, arr(k, 8), out) == 0
+        assert out.raw == pyref.g1_compress(pyref.g1_mul(pt, 2 * k % R)), hex(k)
     w128 = pyref.root_of_unity(128)
     for e in [0, 1, 32, 63, 64, 127]:
         assert emu_g1.emu_g1_mul_twiddle(pb, e, out) == 0
