@@ -171,8 +171,16 @@ Status Context::init(bool use_precomp) {
     }
     if (w < 4 || w > 16) return Status::Error("EKZG_FK20_WINDOW must be in [4, 16]");
     T_.fk20.set_window(w);
-    int ws = use_precomp ? 12 : 8;   // w = 12: 17.7 GiB of tables for the 4096 monomial points, 22 additions per scalar
-    if (const char* e = getenv("EKZG_SRS_WINDOW")) ws = atoi(e);
+    // monomial SRS tables: w = 12 is 17.7 GiB for the 4096 points (21.5 additions per scalar), w = 13 is 30 GiB (20 additions)
+    int ws = use_precomp ? 12 : 8;
+    if (const char* e = getenv("EKZG_SRS_WINDOW")) {
+        ws = atoi(e);
+    } else if (use_precomp) {
+        size_t free_b = 0, total_b = 0;
+        EKZG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        auto table_bytes = [](size_t npoints, int wb) { return npoints * (size_t)(255 / wb + 1) * ((size_t)1 << (wb - 1)) * sizeof(G1Affine); };
+        if (table_bytes((size_t)FK20_MSMS * FK20_POINTS, w) + table_bytes(4096, 13) + ((size_t)16 << 30) <= free_b) ws = 13;
+    }
     if (ws < 4 || ws > 16) return Status::Error("EKZG_SRS_WINDOW must be in [4, 16]");
     T_.srs.set_window(ws);
 
