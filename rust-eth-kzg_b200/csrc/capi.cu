@@ -57,7 +57,7 @@ uint64_t eth_kzg_constant_cells_per_ext_blob(void) { return ekzg::N_CELLS; }
 
 CResult eth_kzg_compute_cells_and_kzg_proofs(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells, uint8_t** out_proofs) {
     std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32), proofs((size_t)ekzg::N_CELLS * 48);
-    Status s = cx(ctx).compute_cells_and_kzg_proofs_batch(1, blob, cells.data(), proofs.data(), nullptr, true);
+    Status s = cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), proofs.data());
     if (!s.ok) return c_err(s.msg);
     for (int i = 0; i < ekzg::N_CELLS; i++) {  // pointer_utils.rs:53-62 write_to_2d_slice
         memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
@@ -68,7 +68,7 @@ CResult eth_kzg_compute_cells_and_kzg_proofs(const DASContext* ctx, const uint8_
 
 CResult eth_kzg_compute_cells(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells) {
     std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32);
-    Status s = cx(ctx).compute_cells_and_kzg_proofs_batch(1, blob, cells.data(), nullptr, nullptr, false);
+    Status s = cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), nullptr);
     if (!s.ok) return c_err(s.msg);
     for (int i = 0; i < ekzg::N_CELLS; i++) memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
     return c_ok();

@@ -532,6 +532,80 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
 }
 
 // ------------------------------------------------------------------------------------------------
+// Single-blob entry point with coalescing of concurrent callers (see kzg_runtime.h).
+void Context::run_coalesced(std::vector<CoalesceReq*>& batch, bool want_proofs) const {
+    const size_t n = batch.size();
+    constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
+    if (n == 1) {   // nobody to share with: straight into the caller's buffers
+        CoalesceReq& r = *batch[0];
+        r.st = compute_cells_and_kzg_proofs_batch(1, r.blob, r.cells, want_proofs ? r.proofs : nullptr, nullptr, want_proofs);
+        return;
+    }
+    std::vector<uint8_t> in(n * BYTES_PER_BLOB), cells(n * CELLS_PER_BLOB), proofs(want_proofs ? n * PROOFS_PER_BLOB : 0), status(n, 0);
+    for (size_t i = 0; i < n; i++) memcpy(&in[i * BYTES_PER_BLOB], batch[i]->blob, BYTES_PER_BLOB);
+    Status s = compute_cells_and_kzg_proofs_batch(n, in.data(), cells.data(), want_proofs ? proofs.data() : nullptr, status.data(), want_proofs);
+    bool any_flag = false;
+    for (uint8_t f : status) any_flag |= f != 0;
+    for (size_t i = 0; i < n; i++) {
+        CoalesceReq& r = *batch[i];
+        if (!s.ok && (!any_flag || status[i])) {   // a failure of the whole batch, or this blob is the invalid one
+            r.st = s;
+            continue;
+        }
+        memcpy(r.cells, &cells[i * CELLS_PER_BLOB], CELLS_PER_BLOB);
+        if (want_proofs) memcpy(r.proofs, &proofs[i * PROOFS_PER_BLOB], PROOFS_PER_BLOB);
+        r.st = Status::Ok();
+    }
+}
+
+Status Context::compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs) const {
+    static const bool off = getenv("EKZG_NO_COALESCE") != nullptr;
+    const bool want_proofs = proofs != nullptr;
+    if (off) return compute_cells_and_kzg_proofs_batch(1, blob, cells, proofs, nullptr, want_proofs);
+    const int kind = want_proofs ? 1 : 0;
+    const size_t cap = (size_t)chunk_capacity();
+    CoalesceReq me{blob, cells, proofs};
+    std::unique_lock<std::mutex> lk(co_.mu);
+    co_.q[kind].push_back(&me);
+    co_.cv_leader.notify_one();
+    // A batch takes >= 20 ms whatever its size (14 dependent G1-NTT phases), so the leader first lingers: callers released
+    // together by the previous batch re-enter within microseconds of each other, and without the pause the first of them would
+    // run a batch of one while the other 63 wait for it.  It goes as soon as nobody has joined for linger_us (default 300).
+    static const int linger_us = [] { const char* e = getenv("EKZG_COALESCE_LINGER_US"); return e ? atoi(e) : 300; }();
+    while (!me.done) {
+        if (co_.leader[kind]) {
+            co_.cv.wait(lk);
+            continue;
+        }
+        co_.leader[kind] = true;   // lead batches until my own request has been served (FIFO: normally the first one)
+        while (!me.done) {
+            if (linger_us > 0) {   // until nobody has joined for linger_us, at most 8 x linger_us in all
+                const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(8 * linger_us);
+                while (co_.q[kind].size() < cap) {
+                    const auto gap_end = std::min(t_end, std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us));
+                    const size_t before = co_.q[kind].size();
+                    while (co_.q[kind].size() == before && co_.cv_leader.wait_until(lk, gap_end) != std::cv_status::timeout) {}
+                    if (co_.q[kind].size() == before || std::chrono::steady_clock::now() >= t_end) break;
+                }
+            }
+            std::vector<CoalesceReq*> batch;
+            while (!co_.q[kind].empty() && batch.size() < cap) {
+                batch.push_back(co_.q[kind].front());
+                co_.q[kind].pop_front();
+            }
+            lk.unlock();
+            run_coalesced(batch, want_proofs);
+            lk.lock();
+            for (CoalesceReq* r : batch) r->done = true;
+            co_.cv.notify_all();
+        }
+        co_.leader[kind] = false;
+        co_.cv.notify_all();       // somebody still queued takes over
+    }
+    return me.st;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Erasure recovery.
 static int rev7(int x) {
     int r = 0;

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <condition_variable>
+#include <deque>
 #include <cstdint>
 #include <memory>
 #include <mutex>
@@ -91,6 +92,13 @@ public:
     Status compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* blobs, uint8_t* cells, uint8_t* proofs,
                                               uint8_t* blob_status, bool want_proofs) const;
 
+    // One blob, as the reference's ABI hands them over (bindings/c/src/lib.rs:226-262), from any number of host threads at
+    // once: concurrent callers are coalesced into batches (leader/follower: the first caller to find no batch in flight runs
+    // one for everything queued, callers arriving meanwhile form the next).  This is what replaces the reference's per-call
+    // rayon fan-out (crates/eip7594/src/prover.rs:117-148 over maybe_rayon): a lone blob fills 1 of the 32 lanes of every K5
+    // work unit, 32 coalesced blobs cost the same time.  cells: 128*2048 B, proofs: 128*48 B or nullptr (compute_cells).
+    Status compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs) const;
+
     // EIP-4844 prover side (crates/eip4844/src/prover.rs:17-88), batched.  Host buffers, contiguous.
     // item_status[i]: 0 ok, 1 invalid blob, 2 invalid commitment / z.
     Status blob_to_kzg_commitment_batch(uint64_t n, const uint8_t* blobs, uint8_t* out48, uint8_t* item_status) const;
@@ -132,6 +140,22 @@ private:
     Status run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const uint8_t* aux_in, uint8_t* out48, uint8_t* out_y32,
                     uint8_t* item_status) const;
     Context() = default;
+    struct CoalesceReq {
+        const uint8_t* blob;
+        uint8_t* cells;
+        uint8_t* proofs;
+        bool done = false;
+        Status st = Status::Ok();
+    };
+    struct Coalescer {
+        std::mutex mu;
+        std::condition_variable cv;         // followers: "a batch finished / the leader stepped down"
+        std::condition_variable cv_leader;  // leader: "somebody joined the queue" (during the linger window)
+        std::deque<CoalesceReq*> q[2];      // [0] cells only, [1] cells + proofs
+        bool leader[2] = {false, false};
+    };
+    mutable Coalescer co_;
+    void run_coalesced(std::vector<CoalesceReq*>& batch, bool want_proofs) const;
     Status init(bool use_precomp);
     int device_ = 0;
     DevTables T_{};

@@ -71,3 +71,47 @@ def test_concurrent_batches(das_ctx, pkg):
         t.join(timeout=600)
         assert not t.is_alive()
     assert got == want
+
+
+def test_coalesced_single_blob_callers(das_ctx, pkg):
+    """48 host threads inside eth_kzg_compute_cells_and_kzg_proofs / eth_kzg_compute_cells at once: the library coalesces
+    them into shared batches (kzg_runtime.h compute_cells_and_kzg_proofs_one).  Every caller must get ITS blob's result, and
+    a non-canonical blob among them must fail alone."""
+    syn = _synth(pkg)
+    nthreads = 48
+    blobs = [syn.blob(5000 + i) for i in range(nthreads)]
+    bad = 17
+    blobs[bad] = b"\xff" * 32 + blobs[bad][32:]          # first field element >= r
+    flat = b"".join(b for i, b in enumerate(blobs) if i != bad)
+    cells_flat, proofs_flat, _ = das_ctx.compute_cells_and_kzg_proofs_batch(flat, nthreads - 1)
+    want = {}
+    for pos, i in enumerate(j for j in range(nthreads) if j != bad):
+        want[i] = (cells_flat[pos * 262144:(pos + 1) * 262144], proofs_flat[pos * 6144:(pos + 1) * 6144])
+    results, errors = [None] * nthreads, []
+    start = threading.Barrier(nthreads)
+
+    def worker(i):
+        try:
+            start.wait()
+            for rep in range(2):
+                try:
+                    cells, proofs = das_ctx.compute_cells_and_kzg_proofs(blobs[i])
+                    only_cells = das_ctx.compute_cells(blobs[i])
+                    results[i] = (b"".join(cells), b"".join(proofs), b"".join(only_cells))
+                except pkg.KzgError:
+                    results[i] = "err"
+        except Exception as ex:  # noqa: BLE001
+            errors.append((i, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(nthreads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+        assert not t.is_alive(), "a caller thread hung"
+    assert not errors, errors
+    for i in range(nthreads):
+        if i == bad:
+            assert results[i] == "err"
+        else:
+            assert results[i] == (want[i][0], want[i][1], want[i][0]), i

@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=8)
-    ap.add_argument("--only", default="eip4844,recover,verify")
+    ap.add_argument("--only", default="eip4844,recover,verify,callers")
     args = ap.parse_args()
     only = set(args.only.split(","))
     pkg = __graft_entry__.load_package()
@@ -144,6 +144,44 @@ def main():
         assert okc is True
         emit({"config": "#5 verify_cell_kzg_proof_batch, 128 blobs x 128 cells in one call (the reference's pointer-array C ABI)", "metric": "cells/s",
               "value": N / t, "ms": 1e3 * t, "negative_case_ms": 1e3 * tneg, "cpu_port_cells_per_s_1thread": NCELLS / tc})
+    if "callers" in only:
+        # the reference's own usage pattern: T host threads, each calling the SINGLE-blob ABI function in a loop on one shared
+        # context (bindings/node/src/lib.rs:92-130 calls from the libuv pool).  The library coalesces concurrent callers.
+        import threading
+        T, per = 64, 4
+        blobs = [syn.blob(9000 + i) for i in range(T)]
+
+        def worker(i, barrier, res):
+            cells = [C.create_string_buffer(2048) for _ in range(128)]
+            proofs = [C.create_string_buffer(48) for _ in range(128)]
+            pc = (C.c_void_p * 128)(*[C.addressof(b) for b in cells])
+            pp = (C.c_void_p * 128)(*[C.addressof(b) for b in proofs])
+            barrier.wait()
+            for _ in range(per):
+                r = lib.eth_kzg_compute_cells_and_kzg_proofs(H, blobs[i], pc, pp)
+                if r.status != 0:
+                    res[i] = "err"
+                    return
+            res[i] = proofs[127].raw
+
+        def run_threads():
+            barrier = threading.Barrier(T + 1)
+            res = [None] * T
+            th = [threading.Thread(target=worker, args=(i, barrier, res)) for i in range(T)]
+            for t in th:
+                t.start()
+            barrier.wait()
+            t0 = time.perf_counter()
+            for t in th:
+                t.join()
+            return time.perf_counter() - t0, res
+        run_threads()
+        dt, res = run_threads()
+        _, pf, _ = ctx.compute_cells_and_kzg_proofs_batch(b"".join(blobs), T)
+        assert all(res[i] == pf[i * 6144 + 127 * 48:(i + 1) * 6144] for i in range(T)), "a coalesced caller got a wrong proof"
+        emit({"config": "single-blob ABI calls (eth_kzg_compute_cells_and_kzg_proofs) from %d concurrent host threads on one context, coalesced by the library" % T,
+              "metric": "blobs/s", "value": T * per / dt, "threads": T, "calls_per_thread": per, "ms_per_call_seen_by_a_thread": 1e3 * dt / per,
+              "coalescing": "off" if os.environ.get("EKZG_NO_COALESCE") else "on"})
     ctx.close()
 
 
