@@ -1,5 +1,6 @@
 // Host-emulation harness for the DEVICE curve code (g1.cuh, g1_mul.cuh); see emu_field.cpp.
 #include "g1_mul.cuh"
+#include "msm_table.cuh"
 #include <string.h>
 using namespace ekzg;
 
@@ -60,6 +61,11 @@ int emu_g1_chain(int mode, int n, const uint8_t* pts48, const uint8_t* negs, uin
 int emu_g1_mul_u256(const uint8_t* p48, const uint32_t* k, uint8_t* out) {
     G1Affine p; if (g1a_decompress(p, p48)) return 1;
     G1Jac j, r; jac_from_affine(j, p); jac_mul_u256(r, j, k); out48(out, r); return 0;
+}
+// MsmTable::set_window: out = {nw, half, rtop, mg}
+void emu_set_window(int w, int* out) {
+    MsmTable t; t.table = nullptr; t.set_window(w);
+    out[0] = t.nw; out[1] = t.half; out[2] = t.rtop; out[3] = t.mg;
 }
 int emu_g1_mul_fr_glv(const uint8_t* p48, const uint32_t* k, uint8_t* out) {
     G1Affine p; if (g1a_decompress(p, p48)) return 1;

@@ -113,3 +113,36 @@ def test_full_size_batch_properties(das_ctx, pkg):
     for key in (0, 1, 2, 3, 17, 63):
         c1, p1 = das_ctx.compute_cells_and_kzg_proofs(base[key])
         assert first[key] == (hashlib.sha256(b"".join(c1)).digest(), b"".join(p1))
+
+
+@pytest.mark.parametrize("fk20_w,srs_w", [("14", "13"), ("12", "12"), ("10", "9")])
+def test_precomputed_window_variants(das_ctx, pkg, fk20_w, srs_w, monkeypatch):
+    """use_precomp contexts: per-window tables at several widths incl. the production one (w = 14, four top digits per lookup;
+    SRS w = 13) and the pair-merged one (w = 12).  The session context (use_precomp=False: w = 8, no merged top window) is
+    itself pinned by the consensus vectors and the oracle above, so it serves as the reference here -- plus the vectors
+    again, directly."""
+    monkeypatch.setenv("EKZG_FK20_WINDOW", fk20_w)
+    monkeypatch.setenv("EKZG_SRS_WINDOW", srs_w)
+    ctx = pkg.DASContext(use_precomp=True)
+    try:
+        assert ctx.window == int(fk20_w)
+        syn = _synth(pkg)
+        # edge scalars exercise the top window: all r-1, zero, constant, and the reference's dummy blob
+        n = 40
+        blobs = [syn.blob(300 + i) for i in range(n - 4)] + list(syn.edge_blobs())[:4]
+        flat = b"".join(blobs[:n])
+        want = das_ctx.compute_cells_and_kzg_proofs_batch(flat, len(blobs[:n]))
+        got = ctx.compute_cells_and_kzg_proofs_batch(flat, len(blobs[:n]))
+        assert got[0] == want[0], "cells differ"
+        assert got[1] == want[1], "proofs differ from the w = 8 context"
+        for name, inp, expected in [c for c in vectors.load("compute_cells_and_kzg_proofs") if c[2] is not None][:3]:
+            cells, proofs = ctx.compute_cells_and_kzg_proofs(inp["blob"])
+            assert [cells, proofs] == [list(expected[0]), list(expected[1])], name
+        for b in blobs[:6] + blobs[-4:]:
+            c = ctx.blob_to_kzg_commitment(b)
+            assert c == das_ctx.blob_to_kzg_commitment(b)
+            assert ctx.compute_blob_kzg_proof(b, c) == das_ctx.compute_blob_kzg_proof(b, c)
+        for name, inp, expected in [c for c in vectors.load("blob_to_kzg_commitment") if c[2] is not None][:3]:
+            assert ctx.blob_to_kzg_commitment(inp["blob"]) == expected, name
+    finally:
+        ctx.close()

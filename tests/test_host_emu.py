@@ -241,3 +241,15 @@ def test_subgroup_check_matches_naive(emu_g1):
         n_in += want
         n_out += 1 - want
     assert n_in >= 2 and n_out >= 10
+
+
+def test_msm_table_window_rule(emu_g1):
+    """merged top window (csrc/kzg_device.cuh MsmTable::set_window): rtop = 2^(255 - w(nw-1)) + 1 values of the top digit,
+    mg = largest of 4, 2, 1 points whose combined top digits still index one slice (rtop^mg - 1 <= 2^(w-1))"""
+    out = (ctypes.c_int * 4)()
+    for w, want in {8: (32, 128, 129, 1), 10: (26, 512, 33, 1), 12: (22, 2048, 9, 2), 13: (20, 4096, 257, 1), 14: (19, 8192, 9, 4),
+                    15: (18, 16384, 2, 4), 16: (16, 32768, 32769, 1)}.items():
+        emu_g1.emu_set_window(w, out)
+        assert tuple(out) == want, (w, tuple(out))
+        nw, half, rtop, mg = out
+        assert w * (nw - 1) <= 255 < w * nw + 1 and rtop ** mg - 1 <= half
