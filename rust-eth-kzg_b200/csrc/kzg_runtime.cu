@@ -594,7 +594,11 @@ Status Context::compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* c
                 co_.q[kind].pop_front();
             }
             lk.unlock();
-            run_coalesced(batch, want_proofs);
+            try {
+                run_coalesced(batch, want_proofs);
+            } catch (const std::exception& ex) {   // e.g. bad_alloc of the staging vectors: fail the batch, never the queue
+                for (CoalesceReq* r : batch) r->st = Status::Error(std::string("batch failed: ") + ex.what());
+            }
             lk.lock();
             for (CoalesceReq* r : batch) r->done = true;
             co_.cv.notify_all();
