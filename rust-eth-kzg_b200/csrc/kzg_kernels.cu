@@ -503,7 +503,7 @@ k_fk20_window_bases(const G1Jac* __restrict__ pts, const G1Affine* __restrict__ 
 
 // FK20 setup, step 3 (fixed_base_msm_window.rs:69-82 precompute_points, once per window):
 // table[(j,k,t)][m] = (m+1) * Q_t for m < half, affine.  One thread per chunk of CH consecutive m.
-constexpr int TBL_CH = 16;
+constexpr int TBL_CH = 64;   // entries sharing one inversion (Montgomery trick): 450/64 + ~19 multiplications per entry
 __global__ void __launch_bounds__(128)
 k_fk20_table_fill(const G1Affine* __restrict__ qaff, G1Affine* __restrict__ table, int half, size_t nbases) {
     const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
