@@ -2,7 +2,7 @@
 // Measures, per SM and clock: (A) carry-chained IMAD.WIDE.U32.X, (B) plain IMAD.WIDE.U32 with distinct operands
 // (the gpu_probe "imad_wide" kernel let ptxas fold the product away, so its number was an IADD3 rate),
 // (C) DFMA, (D) IADD3, and the co-run of A with C and of C with D from different warps of the same CTA.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o rust-eth-kzg_b200/lib/pipe_probe tools/pipe_probe.cu
+// Build: make -C rust-eth-kzg_b200 probes
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
