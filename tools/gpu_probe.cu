@@ -2,7 +2,7 @@
 // field-arithmetic kernels: SURVEY.md §8d "IMAD peak ... must be measured first"), (2) Fp/Fr Montgomery
 // multiplication throughput, (3) device-vs-host-emulation cross-check of the arithmetic headers: the
 // same EKZG_HD functions run on the GPU (PTX carry chains) and on the CPU (emulated carry flag) and
-// must agree bit for bit.  Build: make -C tools probe.   Run on the GPU box: tools/gpu_probe [out.json]
+// must agree bit for bit.  Build: make -C rust-eth-kzg_b200 probes.   Run on the GPU box: rust-eth-kzg_b200/lib/gpu_probe [out.json]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
