@@ -44,7 +44,9 @@ __global__ void k_imad_wide(uint32_t* out, uint32_t a, uint32_t b, int iters) {
     for (int i = 0; i < ILP; i++) x[i] = threadIdx.x + i;
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int i = 0; i < ILP; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(x[i]) : "r"(a), "r"(b));
+        // operands that change every iteration: with loop-invariant a, b ptxas folds the product out of the loop and the
+        // kernel measures IADD3 (that is what the first version of this probe reported as "imad_wide": 17.7 T/s)
+        for (int i = 0; i < ILP; i++) x[i] = (unsigned long long)(uint32_t)x[i] * (uint32_t)(x[i] >> 32) + x[(i + 1) % ILP];
     }
     unsigned long long s = 0;
     for (int i = 0; i < ILP; i++) s ^= x[i];
