@@ -277,6 +277,7 @@ EKZG_HD void fe_sqr_inline(Fe<P>& out, const Fe<P>& a_) {
 
 }  // namespace ekzg
 #include "fp_dfma.cuh"
+#include "fp_karatsuba.cuh"
 namespace ekzg {
 
 // EKZG_FP_DFMA=1 routes Fp products to the FP64 pipe (fp_dfma.cuh).  Default 0: measured on B200 the DFMA variant is
@@ -285,9 +286,15 @@ namespace ekzg {
 #ifndef EKZG_FP_DFMA
 #define EKZG_FP_DFMA 0
 #endif
+// EKZG_FP_KARATSUBA=1: the plain product of fe_mul runs through one Karatsuba level (fp_karatsuba.cuh)
+#ifndef EKZG_FP_KARATSUBA
+#define EKZG_FP_KARATSUBA 0
+#endif
 EKZG_HD void fp_mul_impl(Fp& r, const Fp& a, const Fp& b) {
 #if EKZG_FP_DFMA
     fp_mul_dfma_inline(r, a, b);
+#elif EKZG_FP_KARATSUBA
+    fp_mulk_inline(r, a, b);
 #else
     fe_mul_inline(r, a, b);
 #endif

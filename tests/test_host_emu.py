@@ -55,6 +55,22 @@ def test_fp_dfma_variant():
             assert val(out) == (a * b + c * d) * Ri % P
 
 
+def test_fp_karatsuba_variant():
+    """the Karatsuba Fp product (fp_karatsuba.cuh) against big integers"""
+    emu = _build("emu_field", defines=["EKZG_FP_KARATSUBA=1"], suffix="_karatsuba")
+    rng = random.Random(12)
+    Ri = pow(1 << 384, -1, P)
+    out = (ctypes.c_uint32 * 12)()
+    lo, hi = (1 << 192) - 1, ((1 << 192) - 1) << 192
+    edge = [0, 1, 2, P - 1, P - 2, (1 << 384) % P, (P - 1) // 2, lo, hi % P, (lo ^ (1 << 191)), (1 << 380) + lo, (1 << 192), (1 << 191) | (1 << 383 - 3),
+            sum(0xffffffff << (64 * i) for i in range(6)) % P, sum(0xffffffff << (64 * i + 32) for i in range(6)) % P]
+    vals = edge + [rng.randrange(P) for _ in range(200)]
+    for a in vals:
+        for b in edge + rng.sample(vals, 6):
+            emu.emu_fp_mul(arr(a, 12), arr(b, 12), out)
+            assert val(out) == a * b * Ri % P, (hex(a), hex(b))
+
+
 def arr(x, n):
     return (ctypes.c_uint32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
 
