@@ -125,16 +125,18 @@ EKZG_HD void mul12_karatsuba(uint32_t* t, const uint32_t* a, const uint32_t* b) 
     t[23] = addc(z2[11], 0u);
 }
 
-// out[0..11] = t / B^12 mod p, fully reduced  (t < p*B^12: any sum of a few products of values < p)
+// out[0..11] = t / B^12 mod p, fully reduced  (t < p*B^12: any sum of a few products of values < p).
+// The running total is t + ev + od*B.  t is kept apart from the accumulators on purpose: a chain's last carry then always
+// lands in a limb that holds 0 or 1, never in a full 32-bit limb of t where it could ripple further.
 EKZG_HD void mont_reduce24(uint32_t* out, const uint32_t* t) {
     using P = FpParams;
-    uint32_t ev[24], od[24];   // running total = ev + od*B; ev starts as t
+    uint32_t ev[24], od[24];
 #pragma unroll
-    for (int k = 0; k < 24; k++) { ev[k] = t[k]; od[k] = 0; }
-    uint32_t cin = 0;          // carry of the (zeroed) limbs below row i into limb i
+    for (int k = 0; k < 24; k++) { ev[k] = 0; od[k] = 0; }
+    uint32_t cin = 0;          // carry of the (zeroed) limbs below row i into limb i, at most 3
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        const uint32_t lo = ev[i] + (i ? od[i - 1] : 0u) + cin;
+        const uint32_t lo = t[i] + ev[i] + (i ? od[i - 1] : 0u) + cin;
         const uint32_t mm = mul_lo(lo, P::M0);
         if (i & 1) {
             // odd j -> even positions i+j: ev[i+1 .. i+12]
@@ -177,10 +179,12 @@ EKZG_HD void mont_reduce24(uint32_t* out, const uint32_t* t) {
             od[i + 12] = addc(od[i + 12], 0u);
         }
         // limb i of the total is now 0 mod B; its carry goes into limb i+1
-        uint32_t s = add_cc(ev[i], i ? od[i - 1] : 0u);
-        const uint32_t c1 = addc(0u, 0u);
+        uint32_t s = add_cc(t[i], ev[i]);
+        uint32_t c = addc(0u, 0u);
+        s = add_cc(s, i ? od[i - 1] : 0u);
+        c = addc(c, 0u);
         s = add_cc(s, cin);
-        cin = addc(c1, 0u);
+        cin = addc(c, 0u);
         (void)s;
     }
     uint32_t r[12];
@@ -188,6 +192,10 @@ EKZG_HD void mont_reduce24(uint32_t* out, const uint32_t* t) {
 #pragma unroll
     for (int k = 1; k < 11; k++) r[k] = addc_cc(ev[12 + k], od[11 + k]);
     r[11] = addc(ev[23], od[22]);
+    r[0] = add_cc(r[0], t[12]);
+#pragma unroll
+    for (int k = 1; k < 11; k++) r[k] = addc_cc(r[k], t[12 + k]);
+    r[11] = addc(r[11], t[23]);
     r[0] = add_cc(r[0], cin);
 #pragma unroll
     for (int k = 1; k < 11; k++) r[k] = addc_cc(r[k], 0u);

@@ -222,9 +222,10 @@ class DASContext:
         res = self._lib.eth_kzg_b200_compute_cells_and_kzg_proofs_batch(C.c_void_p(self._ctx), C.c_uint64(n), blobs_flat, cells, proofs, status)
         st = list(status.raw[:n])
         if res.status != 0:
+            msg = C.string_at(res.error_msg).decode("utf-8", "replace") if res.error_msg else ""
             self._lib.eth_kzg_free_error_message(res.error_msg)
             if not any(st):
-                raise KzgError("batch failed")
+                raise KzgError("batch failed: " + msg)
         return cells.raw, (proofs.raw if want_proofs else None), st
 
     def blob_to_kzg_commitment_batch(self, blobs_flat, n):

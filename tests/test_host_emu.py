@@ -69,6 +69,20 @@ def test_fp_karatsuba_variant():
         for b in edge + rng.sample(vals, 6):
             emu.emu_fp_mul(arr(a, 12), arr(b, 12), out)
             assert val(out) == a * b * Ri % P, (hex(a), hex(b))
+    # the two halves on their own, with limb patterns random products never produce: runs of all-ones limbs make every carry
+    # ripple (a carry lost into a 0xffffffff limb is a 2^-32 event per row on random data -- it showed up on the GPU only)
+    t24 = (ctypes.c_uint32 * 24)()
+    B = 1 << 32
+    pats = [0xFFFFFFFF, 0, 0xFFFFFFFE, 1, 0x80000000]
+    for trial in range(400):
+        limbs = [rng.choice(pats) if rng.random() < 0.7 else rng.randrange(B) for _ in range(24)]
+        t = sum(l << (32 * i) for i, l in enumerate(limbs)) % (P << 384)
+        emu.emu_fp_mont_reduce24(arr(t, 24), out)
+        assert val(out) == t * Ri % P, hex(t)
+        a = sum((rng.choice(pats) if rng.random() < 0.7 else rng.randrange(B)) << (32 * i) for i in range(12))
+        b = sum((rng.choice(pats) if rng.random() < 0.7 else rng.randrange(B)) << (32 * i) for i in range(12))
+        emu.emu_fp_mul12(arr(a, 12), arr(b, 12), t24)
+        assert val(t24) == a * b, (hex(a), hex(b))
 
 
 def arr(x, n):
@@ -269,3 +283,32 @@ def test_msm_table_window_rule(emu_g1):
         assert tuple(out) == want, (w, tuple(out))
         nw, half, rtop, mg = out
         assert w * (nw - 1) <= 255 < w * nw + 1 and rtop ** mg - 1 <= half
+
+
+@pytest.mark.parametrize("mod,n,pre", [(P, 12, "fp"), (R, 8, "fr")])
+def test_field_mul_adversarial_limbs(emu_field, mod, n, pre):
+    """the shipped multipliers on limb patterns that random operands never produce (all-ones / zero / top-bit limbs): every
+    carry of the interleaved Montgomery rows ripples as far as it can.  A carry lost into a full limb is a 2^-32 event per
+    row on random data, invisible to random tests and to a few hundred parity blobs."""
+    rng = random.Random(77)
+    Ri = pow(1 << (32 * n), -1, mod)
+    B = 1 << 32
+    pats = [0xFFFFFFFF, 0, 0xFFFFFFFE, 1, 0x80000000, 0x7FFFFFFF]
+    out = (ctypes.c_uint32 * n)()
+
+    def operand():
+        return sum((rng.choice(pats) if rng.random() < 0.75 else rng.randrange(B)) << (32 * i) for i in range(n)) % mod
+
+    for _ in range(1500):
+        a, b, c, d = operand(), operand(), operand(), operand()
+        getattr(emu_field, "emu_%s_mul" % pre)(arr(a, n), arr(b, n), out)
+        assert val(out) == a * b * Ri % mod, (hex(a), hex(b))
+        getattr(emu_field, "emu_%s_sqr" % pre)(arr(a, n), out)
+        assert val(out) == a * a * Ri % mod, hex(a)
+        if pre == "fp":
+            emu_field.emu_fp_mul2(arr(a, n), arr(b, n), arr(c, n), arr(d, n), out)
+            assert val(out) == (a * b + c * d) * Ri % mod, (hex(a), hex(b), hex(c), hex(d))
+        getattr(emu_field, "emu_%s_add" % pre)(arr(a, n), arr(b, n), out)
+        assert val(out) == (a + b) % mod
+        getattr(emu_field, "emu_%s_sub" % pre)(arr(a, n), arr(b, n), out)
+        assert val(out) == (a - b) % mod
