@@ -275,44 +275,13 @@ EKZG_HD void fe_sqr_inline(Fe<P>& out, const Fe<P>& a_) {
     for (int j = 0; j < N; j++) out.v[j] = r[j];
 }
 
-}  // namespace ekzg
-#include "fp_dfma.cuh"
-#include "fp_karatsuba.cuh"
-namespace ekzg {
-
-// EKZG_FP_DFMA=1 routes Fp products to the FP64 pipe (fp_dfma.cuh).  Default 0: measured on B200 the DFMA variant is
-// bit-exact but 1.4-1.6x SLOWER than the IMAD carry chains at the 2 warps per sub-partition these kernels run at
-// (860 instead of 330 instructions per product; profiles/r1_v4_dfma_experiment.md).  Kept as a tested alternative.
-#ifndef EKZG_FP_DFMA
-#define EKZG_FP_DFMA 0
-#endif
-// EKZG_FP_KARATSUBA=1: the plain product of fe_mul runs through one Karatsuba level (fp_karatsuba.cuh)
-#ifndef EKZG_FP_KARATSUBA
-#define EKZG_FP_KARATSUBA 0
-#endif
-EKZG_HD void fp_mul_impl(Fp& r, const Fp& a, const Fp& b) {
-#if EKZG_FP_DFMA
-    fp_mul_dfma_inline(r, a, b);
-#elif EKZG_FP_KARATSUBA
-    fp_mulk_inline(r, a, b);
-#else
-    fe_mul_inline(r, a, b);
-#endif
-}
-EKZG_HD void fp_sqr_impl(Fp& r, const Fp& a) {
-#if EKZG_FP_DFMA
-    fp_sqr_dfma_inline(r, a);
-#else
-    fe_sqr_inline(r, a);
-#endif
-}
-EKZG_HD void fp_mul2_impl(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
-#if EKZG_FP_DFMA
-    fp_mul2_dfma_inline(r, a, b, c, d);
-#else
-    fe_mul2_inline(r, a, b, c, d);
-#endif
-}
+// Alternative Fp multipliers were built and measured on B200 -- 14 x 28-bit limbs with carry-free IMAD.WIDE column sums,
+// 8 x 48-bit limbs in doubles with the DFMA.RZ high/low split, one Karatsuba level on the plain product -- and all three lose
+// to the interleaved carry chains above at the 2-3 warps per sub-partition these kernels run at
+// (profiles/r1_v4_dfma_experiment.md; the code of the last two is in the history up to commit 5b26d49).
+EKZG_HD void fp_mul_impl(Fp& r, const Fp& a, const Fp& b) { fe_mul_inline(r, a, b); }
+EKZG_HD void fp_sqr_impl(Fp& r, const Fp& a) { fe_sqr_inline(r, a); }
+EKZG_HD void fp_mul2_impl(Fp& r, const Fp& a, const Fp& b, const Fp& c, const Fp& d) { fe_mul2_inline(r, a, b, c, d); }
 
 // The ~620-instruction Fp multiplication is ONE subroutine per kernel image on the device: operands and result
 // travel in registers (by-value aggregates; ptxas keeps them out of memory), so a point operation is a short
@@ -400,15 +369,7 @@ EKZG_HD void fe_sub(Fe<P>& out, const Fe<P>& a, const Fe<P>& b) {
 
 EKZG_HD void fp_mul2_add(Fp& out, const Fp& a, const Fp& b, const Fp& c, const Fp& d) {
 #if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
-#if EKZG_FP_DFMA && defined(EKZG_DFMA_NO_FUSED_MUL2)
-    // a third unrolled FP64 subroutine (~20 KB) would push the hot code of K4/K5 past the instruction cache
-    Fp t, u;
-    fe_mul(t, a, b);
-    fe_mul(u, c, d);
-    fe_add(out, t, u);
-#else
     out = fp_mul2_call(a, b, c, d);
-#endif
 #else
     fp_mul2_impl(out, a, b, c, d);
 #endif

@@ -18,8 +18,6 @@ void emu_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y, z;
 void emu_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fe_add(z, x, y); memcpy(r, z.v, 32); }
 void emu_fr_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y, z; memcpy(x.v, a, 32); memcpy(y.v, b, 32); fe_sub(z, x, y); memcpy(r, z.v, 32); }
 void emu_fr_inv(const uint32_t* a, uint32_t* r) { Fr x, z; memcpy(x.v, a, 32); fr_inv(z, x); memcpy(r, z.v, 32); }
-void emu_fp_mont_reduce24(const uint32_t* t, uint32_t* r) { fpk::mont_reduce24(r, t); }
-void emu_fp_mul12(const uint32_t* a, const uint32_t* b, uint32_t* t) { fpk::mul12_karatsuba(t, a, b); }
 int emu_fr_ge_mod(const uint32_t* a) { Fr x; memcpy(x.v, a, 32); return fe_plain_ge_mod(x); }
 int emu_fp_gt_half(const uint32_t* a) { Fp x; memcpy(x.v, a, 48); return fe_plain_gt_half(x); }
 }

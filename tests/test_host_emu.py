@@ -36,55 +36,6 @@ def emu_g1():
     return _build("emu_g1")
 
 
-def test_fp_dfma_variant():
-    """the FP64-pipe Fp product (fp_dfma.cuh, off by default) against big integers: DFMA.RZ emulated by fma() under FE_TOWARDZERO"""
-    emu = _build("emu_field", defines=["EKZG_FP_DFMA=1"], suffix="_dfma")
-    rng = random.Random(11)
-    Ri = pow(1 << 384, -1, P)
-    out = (ctypes.c_uint32 * 12)()
-    edge = [0, 1, 2, P - 1, P - 2, (1 << 384) % P, (P - 1) // 2, (1 << 380) - 1, (1 << 48) - 1, ((1 << 48) - 1) << 48, sum(((1 << 48) - 1) << (96 * i) for i in range(4)) % P]
-    vals = edge + [rng.randrange(P) for _ in range(150)]
-    for a in vals:
-        emu.emu_fp_sqr(arr(a, 12), out)
-        assert val(out) == a * a * Ri % P
-        for b in edge + rng.sample(vals, 4):
-            emu.emu_fp_mul(arr(a, 12), arr(b, 12), out)
-            assert val(out) == a * b * Ri % P
-            c, d = rng.choice(vals), rng.choice(vals)
-            emu.emu_fp_mul2(arr(a, 12), arr(b, 12), arr(c, 12), arr(d, 12), out)
-            assert val(out) == (a * b + c * d) * Ri % P
-
-
-def test_fp_karatsuba_variant():
-    """the Karatsuba Fp product (fp_karatsuba.cuh) against big integers"""
-    emu = _build("emu_field", defines=["EKZG_FP_KARATSUBA=1"], suffix="_karatsuba")
-    rng = random.Random(12)
-    Ri = pow(1 << 384, -1, P)
-    out = (ctypes.c_uint32 * 12)()
-    lo, hi = (1 << 192) - 1, ((1 << 192) - 1) << 192
-    edge = [0, 1, 2, P - 1, P - 2, (1 << 384) % P, (P - 1) // 2, lo, hi % P, (lo ^ (1 << 191)), (1 << 380) + lo, (1 << 192), (1 << 191) | (1 << 383 - 3),
-            sum(0xffffffff << (64 * i) for i in range(6)) % P, sum(0xffffffff << (64 * i + 32) for i in range(6)) % P]
-    vals = edge + [rng.randrange(P) for _ in range(200)]
-    for a in vals:
-        for b in edge + rng.sample(vals, 6):
-            emu.emu_fp_mul(arr(a, 12), arr(b, 12), out)
-            assert val(out) == a * b * Ri % P, (hex(a), hex(b))
-    # the two halves on their own, with limb patterns random products never produce: runs of all-ones limbs make every carry
-    # ripple (a carry lost into a 0xffffffff limb is a 2^-32 event per row on random data -- it showed up on the GPU only)
-    t24 = (ctypes.c_uint32 * 24)()
-    B = 1 << 32
-    pats = [0xFFFFFFFF, 0, 0xFFFFFFFE, 1, 0x80000000]
-    for trial in range(400):
-        limbs = [rng.choice(pats) if rng.random() < 0.7 else rng.randrange(B) for _ in range(24)]
-        t = sum(l << (32 * i) for i, l in enumerate(limbs)) % (P << 384)
-        emu.emu_fp_mont_reduce24(arr(t, 24), out)
-        assert val(out) == t * Ri % P, hex(t)
-        a = sum((rng.choice(pats) if rng.random() < 0.7 else rng.randrange(B)) << (32 * i) for i in range(12))
-        b = sum((rng.choice(pats) if rng.random() < 0.7 else rng.randrange(B)) << (32 * i) for i in range(12))
-        emu.emu_fp_mul12(arr(a, 12), arr(b, 12), t24)
-        assert val(t24) == a * b, (hex(a), hex(b))
-
-
 def arr(x, n):
     return (ctypes.c_uint32 * n)(*[(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)])
 
