@@ -188,7 +188,7 @@ CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t cells_l
     for (uint64_t i = 0; i < cells_length; i++) memcpy(flat.data() + i * ekzg::BYTES_PER_CELL, cells[i], ekzg::BYTES_PER_CELL);
     std::vector<uint8_t> oc((size_t)ekzg::N_EXT * 32), op((size_t)ekzg::N_CELLS * 48);
     uint64_t cnt = cells_length;
-    Status s = c.recover_cells_and_kzg_proofs_batch(1, &cnt, cell_indices, flat.data(), oc.data(), op.data(), nullptr);
+    Status s = c.recover_cells_and_kzg_proofs_one(cnt, cell_indices, flat.data(), oc.data(), op.data());
     if (!s.ok) return c_err(s.msg);
     for (int i = 0; i < ekzg::N_CELLS; i++) {
         memcpy(out_cells[i], oc.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);

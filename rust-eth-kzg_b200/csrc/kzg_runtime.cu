@@ -532,81 +532,126 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
 }
 
 // ------------------------------------------------------------------------------------------------
-// Single-blob entry point with coalescing of concurrent callers (see kzg_runtime.h).
-void Context::run_coalesced(std::vector<CoalesceReq*>& batch, bool want_proofs) const {
+// Single-item entry points with coalescing of concurrent callers (see kzg_runtime.h).
+void Context::run_coalesced(int which, std::vector<CoalesceReq*>& batch) const {
     const size_t n = batch.size();
     constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
-    if (n == 1) {   // nobody to share with: straight into the caller's buffers
+    const bool want_proofs = which != CQ_CELLS;
+    if (n == 1) {   // nobody to share with: straight into the caller's buffers, the batch call's own error text
         CoalesceReq& r = *batch[0];
-        r.st = compute_cells_and_kzg_proofs_batch(1, r.blob, r.cells, want_proofs ? r.proofs : nullptr, nullptr, want_proofs);
+        r.st = which == CQ_RECOVER ? recover_cells_and_kzg_proofs_batch(1, &r.count, r.indices, r.in, r.cells, r.proofs, nullptr)
+                                   : compute_cells_and_kzg_proofs_batch(1, r.in, r.cells, want_proofs ? r.proofs : nullptr, nullptr, want_proofs);
         return;
     }
-    std::vector<uint8_t> in(n * BYTES_PER_BLOB), cells(n * CELLS_PER_BLOB), proofs(want_proofs ? n * PROOFS_PER_BLOB : 0), status(n, 0);
-    for (size_t i = 0; i < n; i++) memcpy(&in[i * BYTES_PER_BLOB], batch[i]->blob, BYTES_PER_BLOB);
-    Status s = compute_cells_and_kzg_proofs_batch(n, in.data(), cells.data(), want_proofs ? proofs.data() : nullptr, status.data(), want_proofs);
+    std::vector<uint8_t> cells(n * CELLS_PER_BLOB), proofs(want_proofs ? n * PROOFS_PER_BLOB : 0), status(n, 0);
+    Status s = Status::Ok();
+    if (which == CQ_RECOVER) {
+        std::vector<uint64_t> counts(n), idx;
+        size_t total = 0;
+        for (size_t i = 0; i < n; i++) { counts[i] = batch[i]->count; total += batch[i]->count; }
+        std::vector<uint8_t> in(total * BYTES_PER_CELL);
+        idx.reserve(total);
+        size_t o = 0;
+        for (size_t i = 0; i < n; i++) {
+            memcpy(&in[o * BYTES_PER_CELL], batch[i]->in, (size_t)batch[i]->count * BYTES_PER_CELL);
+            idx.insert(idx.end(), batch[i]->indices, batch[i]->indices + batch[i]->count);
+            o += batch[i]->count;
+        }
+        s = recover_cells_and_kzg_proofs_batch(n, counts.data(), idx.data(), in.data(), cells.data(), proofs.data(), status.data());
+    } else {
+        std::vector<uint8_t> in(n * BYTES_PER_BLOB);
+        for (size_t i = 0; i < n; i++) memcpy(&in[i * BYTES_PER_BLOB], batch[i]->in, BYTES_PER_BLOB);
+        s = compute_cells_and_kzg_proofs_batch(n, in.data(), cells.data(), want_proofs ? proofs.data() : nullptr, status.data(), want_proofs);
+    }
     bool any_flag = false;
     for (uint8_t f : status) any_flag |= f != 0;
     for (size_t i = 0; i < n; i++) {
         CoalesceReq& r = *batch[i];
-        if (!s.ok && (!any_flag || status[i])) {   // a failure of the whole batch, or this blob is the invalid one
+        if (!s.ok && !any_flag) {   // the batch as a whole failed (CUDA error, allocation)
             r.st = s;
-            continue;
+        } else if (status[i]) {     // this item is the invalid one; the others are served
+            r.st = which != CQ_RECOVER ? Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus")
+                 : status[i] == 1 ? Status::Error("Serialization(ScalarNotCanonical): a cell field element is >= the scalar modulus")
+                 : status[i] == 4 ? Status::Error("ReedSolomon(PolynomialHasInvalidLength): recovered polynomial has degree >= 4096")
+                                  : Status::Error("Recovery: invalid cell indices");
+        } else {
+            memcpy(r.cells, &cells[i * CELLS_PER_BLOB], CELLS_PER_BLOB);
+            if (want_proofs) memcpy(r.proofs, &proofs[i * PROOFS_PER_BLOB], PROOFS_PER_BLOB);
+            r.st = Status::Ok();
         }
-        memcpy(r.cells, &cells[i * CELLS_PER_BLOB], CELLS_PER_BLOB);
-        if (want_proofs) memcpy(r.proofs, &proofs[i * PROOFS_PER_BLOB], PROOFS_PER_BLOB);
-        r.st = Status::Ok();
     }
 }
 
-Status Context::compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs) const {
-    static const bool off = getenv("EKZG_NO_COALESCE") != nullptr;
-    const bool want_proofs = proofs != nullptr;
-    if (off) return compute_cells_and_kzg_proofs_batch(1, blob, cells, proofs, nullptr, want_proofs);
-    const int kind = want_proofs ? 1 : 0;
+Status Context::coalesce(int which, CoalesceReq& me) const {
+    CoalesceQueue& Q = co_[which];
     const size_t cap = (size_t)chunk_capacity();
-    CoalesceReq me{blob, cells, proofs};
-    std::unique_lock<std::mutex> lk(co_.mu);
-    co_.q[kind].push_back(&me);
-    co_.cv_leader.notify_one();
     // A batch takes >= 20 ms whatever its size (14 dependent G1-NTT phases), so the leader first lingers: callers released
     // together by the previous batch re-enter within microseconds of each other, and without the pause the first of them would
     // run a batch of one while the other 63 wait for it.  It goes as soon as nobody has joined for linger_us (default 300).
     static const int linger_us = [] { const char* e = getenv("EKZG_COALESCE_LINGER_US"); return e ? atoi(e) : 300; }();
+    std::unique_lock<std::mutex> lk(Q.mu);
+    Q.q.push_back(&me);
+    Q.cv_leader.notify_one();
     while (!me.done) {
-        if (co_.leader[kind]) {
-            co_.cv.wait(lk);
+        if (Q.leader) {
+            Q.cv.wait(lk);
             continue;
         }
-        co_.leader[kind] = true;   // lead batches until my own request has been served (FIFO: normally the first one)
+        Q.leader = true;   // lead batches until my own request has been served (FIFO: normally the first one)
         while (!me.done) {
             if (linger_us > 0) {   // until nobody has joined for linger_us, at most 8 x linger_us in all
                 const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(8 * linger_us);
-                while (co_.q[kind].size() < cap) {
+                while (Q.q.size() < cap) {
                     const auto gap_end = std::min(t_end, std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us));
-                    const size_t before = co_.q[kind].size();
-                    while (co_.q[kind].size() == before && co_.cv_leader.wait_until(lk, gap_end) != std::cv_status::timeout) {}
-                    if (co_.q[kind].size() == before || std::chrono::steady_clock::now() >= t_end) break;
+                    const size_t before = Q.q.size();
+                    while (Q.q.size() == before && Q.cv_leader.wait_until(lk, gap_end) != std::cv_status::timeout) {}
+                    if (Q.q.size() == before || std::chrono::steady_clock::now() >= t_end) break;
                 }
             }
             std::vector<CoalesceReq*> batch;
-            while (!co_.q[kind].empty() && batch.size() < cap) {
-                batch.push_back(co_.q[kind].front());
-                co_.q[kind].pop_front();
+            while (!Q.q.empty() && batch.size() < cap) {
+                batch.push_back(Q.q.front());
+                Q.q.pop_front();
             }
             lk.unlock();
             try {
-                run_coalesced(batch, want_proofs);
+                run_coalesced(which, batch);
             } catch (const std::exception& ex) {   // e.g. bad_alloc of the staging vectors: fail the batch, never the queue
                 for (CoalesceReq* r : batch) r->st = Status::Error(std::string("batch failed: ") + ex.what());
             }
             lk.lock();
             for (CoalesceReq* r : batch) r->done = true;
-            co_.cv.notify_all();
+            Q.cv.notify_all();
         }
-        co_.leader[kind] = false;
-        co_.cv.notify_all();       // somebody still queued takes over
+        Q.leader = false;
+        Q.cv.notify_all();       // somebody still queued takes over
     }
     return me.st;
+}
+
+static bool coalescing_off() {
+    static const bool off = getenv("EKZG_NO_COALESCE") != nullptr;
+    return off;
+}
+
+Status Context::compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs) const {
+    const bool want_proofs = proofs != nullptr;
+    if (coalescing_off()) return compute_cells_and_kzg_proofs_batch(1, blob, cells, proofs, nullptr, want_proofs);
+    CoalesceReq me;
+    me.in = blob; me.cells = cells; me.proofs = proofs;
+    return coalesce(want_proofs ? CQ_CELLS_PROOFS : CQ_CELLS, me);
+}
+
+Status Context::recover_cells_and_kzg_proofs_one(uint64_t count, const uint64_t* indices, const uint8_t* cells, uint8_t* out_cells,
+                                                 uint8_t* out_proofs) const {
+    // index errors are decided here, in the reference's order (recovery.rs:90-146), so that a caller gets the exact error and a
+    // malformed request never joins a shared batch
+    bool bad = count < (uint64_t)N_CELLS / 2 || count > (uint64_t)N_CELLS;
+    for (uint64_t k = 0; k < count && !bad; k++) bad = indices[k] >= (uint64_t)N_CELLS || (k && !(indices[k - 1] < indices[k]));
+    if (bad || coalescing_off()) return recover_cells_and_kzg_proofs_batch(1, &count, indices, cells, out_cells, out_proofs, nullptr);
+    CoalesceReq me;
+    me.in = cells; me.indices = indices; me.count = count; me.cells = out_cells; me.proofs = out_proofs;
+    return coalesce(CQ_RECOVER, me);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -98,6 +98,9 @@ public:
     // rayon fan-out (crates/eip7594/src/prover.rs:117-148 over maybe_rayon): a lone blob fills 1 of the 32 lanes of every K5
     // work unit, 32 coalesced blobs cost the same time.  cells: 128*2048 B, proofs: 128*48 B or nullptr (compute_cells).
     Status compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs) const;
+    // the same for eth_kzg_recover_cells_and_proofs: `count` cells (contiguous) at `indices`
+    Status recover_cells_and_kzg_proofs_one(uint64_t count, const uint64_t* indices, const uint8_t* cells, uint8_t* out_cells,
+                                            uint8_t* out_proofs) const;
 
     // EIP-4844 prover side (crates/eip4844/src/prover.rs:17-88), batched.  Host buffers, contiguous.
     // item_status[i]: 0 ok, 1 invalid blob, 2 invalid commitment / z.
@@ -140,22 +143,28 @@ private:
     Status run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const uint8_t* aux_in, uint8_t* out48, uint8_t* out_y32,
                     uint8_t* item_status) const;
     Context() = default;
+    // Leader/follower coalescing of concurrent single-item callers into shared batches (see compute_cells_and_kzg_proofs_one).
     struct CoalesceReq {
-        const uint8_t* blob;
-        uint8_t* cells;
-        uint8_t* proofs;
+        // compute: blob -> cells (+ proofs);   recover: count cells at `indices` -> cells + proofs
+        const uint8_t* in = nullptr;        // blob (131072 B) / the given cells, contiguous (count * 2048 B)
+        const uint64_t* indices = nullptr;  // recover only
+        uint64_t count = 0;                 // recover only
+        uint8_t* cells = nullptr;           // 128 * 2048 B out
+        uint8_t* proofs = nullptr;          // 128 * 48 B out (nullptr: compute_cells)
         bool done = false;
         Status st = Status::Ok();
     };
-    struct Coalescer {
+    struct CoalesceQueue {
         std::mutex mu;
         std::condition_variable cv;         // followers: "a batch finished / the leader stepped down"
         std::condition_variable cv_leader;  // leader: "somebody joined the queue" (during the linger window)
-        std::deque<CoalesceReq*> q[2];      // [0] cells only, [1] cells + proofs
-        bool leader[2] = {false, false};
+        std::deque<CoalesceReq*> q;
+        bool leader = false;
     };
-    mutable Coalescer co_;
-    void run_coalesced(std::vector<CoalesceReq*>& batch, bool want_proofs) const;
+    enum { CQ_CELLS = 0, CQ_CELLS_PROOFS = 1, CQ_RECOVER = 2 };
+    mutable CoalesceQueue co_[3];
+    Status coalesce(int which, CoalesceReq& me) const;
+    void run_coalesced(int which, std::vector<CoalesceReq*>& batch) const;
     Status init(bool use_precomp);
     int device_ = 0;
     DevTables T_{};

@@ -115,3 +115,52 @@ def test_coalesced_single_blob_callers(das_ctx, pkg):
             assert results[i] == "err"
         else:
             assert results[i] == (want[i][0], want[i][1], want[i][0]), i
+
+
+def test_coalesced_recover_callers(das_ctx, pkg):
+    """32 host threads inside eth_kzg_recover_cells_and_proofs at once, each with its own blob and erasure pattern; one of them
+    hands in a non-canonical cell and must fail alone, one has shuffled indices and must get the index error without ever
+    joining a batch."""
+    syn = _synth(pkg)
+    nthreads = 32
+    flat = b"".join(syn.blob(7000 + i) for i in range(nthreads))
+    cells_flat, proofs_flat, _ = das_ctx.compute_cells_and_kzg_proofs_batch(flat, nthreads)
+    want = [(cells_flat[i * 262144:(i + 1) * 262144], proofs_flat[i * 6144:(i + 1) * 6144]) for i in range(nthreads)]
+    patterns = [list(range(64)), list(range(64, 128)), list(range(0, 128, 2)), list(range(1, 128, 2)), list(range(20, 100)), list(range(128))]
+    bad_cell, bad_idx = 9, 21
+    results, errors = [None] * nthreads, []
+    start = threading.Barrier(nthreads)
+
+    def worker(i):
+        try:
+            idx = list(patterns[i % len(patterns)])
+            cells = [want[i][0][j * 2048:(j + 1) * 2048] for j in idx]
+            if i == bad_cell:
+                cells[3] = b"\xff" * 32 + cells[3][32:]
+            if i == bad_idx:
+                idx[0], idx[1] = idx[1], idx[0]
+                cells[0], cells[1] = cells[1], cells[0]
+            start.wait()
+            for rep in range(2):
+                try:
+                    rc, rp = das_ctx.recover_cells_and_kzg_proofs(idx, cells)
+                    results[i] = (b"".join(rc), b"".join(rp))
+                except pkg.KzgError as ex:
+                    results[i] = "err:" + str(ex)
+        except Exception as ex:  # noqa: BLE001
+            errors.append((i, repr(ex)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(nthreads)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=600)
+        assert not t.is_alive(), "a caller thread hung"
+    assert not errors, errors
+    for i in range(nthreads):
+        if i == bad_cell:
+            assert isinstance(results[i], str) and "ScalarNotCanonical" in results[i], results[i]
+        elif i == bad_idx:
+            assert isinstance(results[i], str) and "NotUniquelyOrdered" in results[i], results[i]
+        else:
+            assert results[i] == want[i], i
