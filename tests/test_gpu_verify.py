@@ -89,3 +89,27 @@ def test_verify_blob_proof_batch_synthetic(das_ctx, pkg):
     assert all(das_ctx.verify_blob_kzg_proof(blobs[i], cl[i], pl[i]) for i in range(3))
     pl[4], pl[5] = pl[5], pl[4]
     assert das_ctx.verify_blob_kzg_proof_batch(blobs, cl, pl) is False
+
+
+def test_verify_cell_batch_column_sum_path():
+    """EKZG_VERIFY_COLUMN_SUMS=1 selects the throughput form of the two random-linear-combination sums (one scalar-multiplication
+    pass + per-column sums + 128 fixed-twiddle multiplications) that batches above 32 768 cells use.  The switch is read once
+    per process, so the vectors run in a child process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import __graft_entry__ as g\n"
+        "from tests import vectors\n"
+        "pkg = g.load_package(); ctx = pkg.DASContext(use_precomp=False)\n"
+        "bad = 0\n"
+        "for name, inp, exp in vectors.load('verify_cell_kzg_proof_batch'):\n"
+        "    try: got = ctx.verify_cell_kzg_proof_batch(inp['commitments'], inp['cell_indices'], inp['cells'], inp['proofs'])\n"
+        "    except pkg.KzgError: got = None\n"
+        "    bad += got != exp\n"
+        "ctx.close(); print('mismatches', bad); sys.exit(1 if bad else 0)\n" % root)
+    env = dict(os.environ, EKZG_VERIFY_COLUMN_SUMS="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
