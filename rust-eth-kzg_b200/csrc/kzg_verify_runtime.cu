@@ -108,7 +108,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
     // 128 x 128 cells, 21 ms with the x86 SHA extensions).  It only needs host data, so it starts now on a helper thread
     // while this thread stages the copies (the 33 MB of cells are pageable caller memory: a synchronous 3 ms) and the device
     // validates the points.
-    std::future<std::array<uint8_t, 32>> hash_task = std::async(std::launch::async, [&]() {
+    auto hash_transcript = [&]() {
         std::array<uint8_t, 32> out;
         host::Sha256Stream h;
         uint8_t head[16 + 32];
@@ -125,7 +125,13 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
         }
         h.final(out.data());
         return out;
-    });
+    };
+    std::future<std::array<uint8_t, 32>> hash_task;
+    try {
+        hash_task = std::async(std::launch::async, hash_transcript);
+    } catch (const std::exception&) {   // no thread to be had: hash on this one, when the value is needed
+        hash_task = std::async(std::launch::deferred, hash_transcript);
+    }
     Workspace* wsp = acquire(1, true);
     if (!wsp) { hash_task.wait(); return Status::Error("allocation failed"); }
     cudaStream_t st = wsp->stream;
