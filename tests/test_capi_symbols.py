@@ -56,3 +56,28 @@ def test_no_cpu_fallback(pkg):
         pytest.skip("a GPU is present")
     with pytest.raises(pkg.KzgError):
         pkg.DASContext()
+
+
+def _build_consumer(pkg):
+    import subprocess
+    libdir = os.path.dirname(pkg.library_path())
+    exe = os.path.join(ROOT, "tests", "capi", "consumer")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-o", exe,
+                           os.path.join(ROOT, "tests", "capi", "consumer.c"), "-L" + libdir, "-lc_eth_kzg_b200", "-Wl,-rpath," + libdir])
+    return exe
+
+
+def test_c_consumer_builds_and_runs_without_gpu(lib, pkg):
+    """the header is valid C99 and a C program links against the library; without a device the context is refused (no fallback)"""
+    import subprocess
+    exe = _build_consumer(pkg)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_c_consumer_on_gpu(lib, pkg):
+    import subprocess
+    exe = _build_consumer(pkg)
+    r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "gpu path ok" in r.stdout, r.stdout + r.stderr
