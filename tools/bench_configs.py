@@ -29,7 +29,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=8)
-    ap.add_argument("--only", default="eip4844,recover,verify,callers")
+    ap.add_argument("--only", default="eip4844,recover,verify,callers,pageable")
     args = ap.parse_args()
     only = set(args.only.split(","))
     pkg = __graft_entry__.load_package()
@@ -144,6 +144,27 @@ def main():
         assert okc is True
         emit({"config": "#5 verify_cell_kzg_proof_batch, 128 blobs x 128 cells in one call (the reference's pointer-array C ABI)", "metric": "cells/s",
               "value": N / t, "ms": 1e3 * t, "negative_case_ms": 1e3 * tneg, "cpu_port_cells_per_s_1thread": NCELLS / tc})
+    if "pageable" in only:
+        # config #3 through the batch entry point with PAGEABLE caller buffers (what a binding that does not pin its memory hands
+        # over): the library stages through its own pinned memory, 64 blobs at a time, under the kernels
+        n = 1024
+        src = bytearray(syn.blobs(n))
+        cells = bytearray(n * 262144)
+        proofs = bytearray(n * 6144)
+        status = bytearray(n)
+        cb = (C.c_char * len(src)).from_buffer(src)
+        cc = (C.c_char * len(cells)).from_buffer(cells)
+        cp = (C.c_char * len(proofs)).from_buffer(proofs)
+        cs = (C.c_char * len(status)).from_buffer(status)
+
+        def call():
+            ok(lib.eth_kzg_b200_compute_cells_and_kzg_proofs_batch(H, C.c_uint64(n), cb, cc, cp, cs))
+            return True
+        call()
+        t, _ = best(call, args.reps)
+        assert bytes(cells[:131072]) == bytes(src[:131072])
+        emit({"config": "#3 compute_cells_and_kzg_proofs, batch of 1024 blobs, PAGEABLE host buffers through the C ABI", "metric": "blobs/s",
+              "value": n / t, "ms": 1e3 * t})
     if "callers" in only:
         # the reference's own usage pattern: T host threads, each calling the SINGLE-blob ABI function in a loop on one shared
         # context (bindings/node/src/lib.rs:92-130 calls from the libuv pool).  The library coalesces concurrent callers.
