@@ -133,7 +133,7 @@ CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blo
     if (launch_g1_compress(ws->d_pts, ws->d_proofs, 128, 1, st) != cudaSuccess) return fail("k6");
     uint8_t tmp[128 * 48];
     if (cudaMemcpyAsync(tmp, ws->d_proofs, sizeof(tmp), cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("d2h msm");
-    if (launch_g1_ntt_phases(ws->d_pts, 1, 0, 7, ws->d_queue, st) != cudaSuccess) return fail("k5");
+    if (launch_g1_ntt_phases(ws->d_pts, 1, 0, 7, ws->d_queue, ws->d_ntt_scratch, st) != cudaSuccess) return fail("k5");
     if (launch_g1_compress(ws->d_pts, ws->d_proofs, 64, 1, st) != cudaSuccess) return fail("k6b");
     if (cudaMemcpyAsync(out_h, ws->d_proofs, 64 * 48, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("d2h h");
     cudaError_t e = cudaStreamSynchronize(st);

@@ -11,6 +11,7 @@
 //   proofs  [B][128*48]  bytes as on the wire
 #include "kzg_kernels.h"
 #include "fr_ntt.cuh"
+#include "fpvm.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -235,6 +236,183 @@ k_fk20_msm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTab
 }
 
 // ------------------------------------------------------------------------------------------------
+// The Fp interpreter shared by the hot kernels (fpvm.cuh): the ONLY copy of the Montgomery multiplier, the squarer and
+// the fused two-product multiplier in their instruction stream.  `base` = shared-space address of the calling thread's
+// chunk of slot 0; runs instructions [pc, pc + n) of the program table `reps` times; bit i of the result is set when
+// instruction i produced zero (the callers test the H / R differences of the addition formulas with it).
+// ------------------------------------------------------------------------------------------------
+__constant__ uint32_t c_fpvm_prog[fpvm::FPVM_PROG_WORDS] = FPVM_PROG_INIT;
+
+static __device__ __noinline__ uint32_t fpvm_run(uint32_t base, int pc, int n, int reps) {
+    fpvm::Smem m{base};
+    uint32_t z = 0;
+#pragma unroll 1
+    for (int r = 0; r < reps; r++) {
+#pragma unroll 1
+        for (int i = 0; i < n; i++) z |= fpvm::step(m, c_fpvm_prog[pc + i]) << i;
+    }
+    return z;
+}
+#define FPVM_RUN(base, NAME) fpvm_run(base, fpvm::PROG_##NAME, fpvm::PROG_##NAME##_LEN, 1)
+
+__device__ __forceinline__ Fp fp_one() {
+    Fp r;
+    fe_set_one(r);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4, shared-memory-operand form (the production kernel; the register form above is kept for A/B runs, EKZG_K4=reg).
+//   Same thread mapping and table walk as k_fk20_msm.  The XYZZ accumulator of a thread lives in slots 0..3, the table
+//   entry is staged into slots 4..5 and slots 6..7 are scratch; one mixed addition = 9 interpreter instructions.
+//   The Booth digits come off the low end of the scalar, which is shifted right one window at a time (funnel shifts on
+//   statically indexed registers -- the register form indexed its limbs dynamically, which put the scalar in local memory).
+//   The entry of the NEXT window is prefetched into L2 before the current one is accumulated, so the 96-byte gather from
+//   the 144 GiB of tables is in flight during the ~5000 pipe clocks of an addition (holding it in registers instead
+//   would not fit: the interpreter owns 96 of the 128 registers).
+// ------------------------------------------------------------------------------------------------
+// rare: acc and the entry have the same x.  Same point -> double the entry; opposite -> identity.
+static __device__ __noinline__ bool k4_same_x(uint32_t base, const G1Affine* p, bool neg, bool r_is_zero) {
+    if (!r_is_zero) return true;          // acc == -e: the sum is the identity
+    G1Affine e = ld_vec(p);
+    fe_cneg(e.y, e.y, neg);
+    G1Xyzz d;
+    xyzz_dbl_affine(d, e);
+    fpvm::Smem M{base};
+    M.st(0, d.x); M.st(1, d.y); M.st(2, d.zz); M.st(3, d.zzz);
+    return false;
+}
+// acc (slots 0..3; `inf`: nothing there yet) += (neg ? -*p : *p)
+__device__ __forceinline__ bool k4_accumulate(uint32_t base, const G1Affine* p, bool neg, bool inf) {
+    const fpvm::Smem M{base};
+    G1Affine e = ld_vec(p);
+    if (g1a_is_inf(e)) return inf;
+    fe_cneg(e.y, e.y, neg);
+    if (inf) {
+        M.st(0, e.x); M.st(1, e.y); M.st(2, fp_one()); M.st(3, fp_one());
+        return false;
+    }
+    M.st(4, e.x); M.st(5, e.y);
+    const uint32_t z = FPVM_RUN(base, K4_XYZZ_MADD_A);
+    if (z & 1u) return k4_same_x(base, p, neg, (z & 2u) != 0);
+    FPVM_RUN(base, K4_XYZZ_MADD_B);
+    return false;
+}
+__device__ __forceinline__ void prefetch_entry_l2(const G1Affine* p) {   // 96 bytes, 32-byte aligned: one or two 128-byte lines
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p) + 80));
+}
+// rare: the two accumulators of a slice reduction have the same x.  Equal points: the sum is twice the OTHER thread's
+// accumulator, which still sits untouched in its own slots 0..3.
+static __device__ __noinline__ bool k4_same_x_xyzz(uint32_t base, uint32_t other_base, bool r_is_zero) {
+    if (!r_is_zero) return true;
+    const fpvm::Smem O{other_base};
+    G1Xyzz a, d;
+    a.x = O.ld(0); a.y = O.ld(1); a.zz = O.ld(2); a.zzz = O.ld(3);
+    xyzz_dbl(d, a);
+    fpvm::Smem M{base};
+    M.st(0, d.x); M.st(1, d.y); M.st(2, d.zz); M.st(3, d.zzz);
+    return false;
+}
+
+template <int NSLICE>
+__global__ void __launch_bounds__(fpvm::NT, 4)
+k_fk20_msm_vm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTable T, int B, int b0, int b1) {
+    extern __shared__ uint4 vm_smem[];
+    static_assert(fpvm::NT == 128, "thread mapping below assumes 128-thread CTAs");
+    constexpr int BLOBS_PER_CTA = 128 / NSLICE;
+    constexpr int KPER = FK20_POINTS / NSLICE;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(vm_smem) + threadIdx.x * 16u;
+    const fpvm::Smem M{base};
+    const int j = blockIdx.y;
+    const int lane_b = threadIdx.x % BLOBS_PER_CTA, slice = threadIdx.x / BLOBS_PER_CTA;
+    const int b = b0 + blockIdx.x * BLOBS_PER_CTA + lane_b;
+    const bool active = b < b1;
+    bool inf = true;                       // accumulator is the identity (nothing in slots 0..3 yet)
+    if (active) {
+        const int w = T.w, nw = T.nw, mg = T.mg;
+        const int nreg = mg > 1 ? nw - 1 : nw;
+        const uint32_t vmask = (2u << w) - 1u;
+        // one entry ahead: the next window's table entry is pulled into L2 while the current one is accumulated
+        const G1Affine* pend = nullptr;
+        bool pend_neg = false;
+#define K4_EMIT(ptr, negflag)                                     \
+    do {                                                          \
+        const G1Affine* np_ = (ptr);                              \
+        prefetch_entry_l2(np_);                                   \
+        if (pend) inf = k4_accumulate(base, pend, pend_neg, inf); \
+        pend = np_;                                               \
+        pend_neg = (negflag);                                     \
+    } while (0)
+        int comb = 0, radix = 1;
+        for (int kk = 0; kk < KPER; kk++) {
+            const int k = slice * KPER + kk;
+            const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)(j * FK20_POINTS + k) * B + b) * 8);
+            const uint4 s0 = sp[0], s1 = sp[1];
+            uint32_t s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            uint32_t prev = 0;             // bit t*w - 1 of the scalar
+            const G1Affine* tb = T.table + (size_t)(j * FK20_POINTS + k) * T.nw * T.half;
+            for (int t = 0; t <= nreg; t++) {
+                const uint32_t v = ((s[0] << 1) | prev) & vmask;
+                const int d = (int)((v + 1) >> 1) - (int)((v >> w) << w);   // booth_digit, g1_mul.cuh
+                if (t == nreg) {           // t = nw - 1 when the top window is merged, else one past the top (d == 0)
+                    if (mg > 1) { comb += d * radix; radix *= T.rtop; }
+                    break;
+                }
+                prev = (s[0] >> (w - 1)) & 1u;
+#pragma unroll
+                for (int i = 0; i < 7; i++) s[i] = __funnelshift_r(s[i], s[i + 1], w);
+                s[7] >>= w;
+                if (d != 0) K4_EMIT(&tb[(size_t)t * T.half + ((d < 0 ? -d : d) - 1)], d < 0);
+            }
+            if (mg > 1 && (kk & (mg - 1)) == mg - 1) {
+                if (comb != 0) {
+                    const G1Affine* tg = tb - (size_t)(mg - 1) * T.nw * T.half;   // top slice of the group's first point
+                    K4_EMIT(&tg[(size_t)(nw - 1) * T.half + comb - 1], false);
+                }
+                comb = 0;
+                radix = 1;
+            }
+        }
+        if (pend) inf = k4_accumulate(base, pend, pend_neg, inf);
+#undef K4_EMIT
+    }
+    if (NSLICE > 1) {
+        __shared__ uint8_t s_inf[128];
+        for (int step = NSLICE / 2; step >= 1; step >>= 1) {
+            s_inf[threadIdx.x] = inf ? 1 : 0;
+            __syncthreads();
+            if (slice < step) {
+                const int other = threadIdx.x + step * BLOBS_PER_CTA;
+                if (!s_inf[other]) {
+                    const fpvm::Smem O{base + (uint32_t)(step * BLOBS_PER_CTA) * 16u};
+                    if (inf) {
+                        for (int c = 0; c < 4; c++) M.st(c, O.ld(c));
+                        inf = false;
+                    } else {
+                        for (int c = 0; c < 4; c++) M.st(4 + c, O.ld(c));
+                        const uint32_t z = FPVM_RUN(base, K4_XYZZ_ADD_A);
+                        if (z & 2u) inf = k4_same_x_xyzz(base, O.base, (z & 8u) != 0);
+                        else FPVM_RUN(base, K4_XYZZ_ADD_B);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (active && slice == 0) {
+        G1Jac r;
+        if (inf) {
+            jac_set_inf(r);
+        } else {
+            FPVM_RUN(base, K4_XYZZ_TO_JAC);
+            r.x = M.ld(0); r.y = M.ld(1); r.z = M.ld(2);
+        }
+        st_vec(&pts[(size_t)rev_bits(j, 7) * B + b], r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K5  the two 128-point G1 NTTs of every blob   (HOT LOOP #2)
 //   reference: Domain::ifft_g1_take_n / fft_g1 (polynomial/src/domain.rs:149-194) over the generic
 //   butterfly `dit` (fft.rs:164-177) whose `*b * twiddle` is a full scalar multiplication.
@@ -343,6 +521,271 @@ k_fk20_g1_ntts(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned
         __threadfence();
         __syncwarp();
         if (lane == 0) red_release_inc(cnt + ph);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5, shared-memory-operand form (the production kernel; the register form above stays for A/B runs, EKZG_K5=reg).
+//   Same persistent ticket queue, but
+//   * the whole fixed-scalar ladder (jac_mul_ops, g1_mul.cuh) runs on the Fp interpreter: accumulator, the staged table
+//     entry and three temporaries in the eight shared-memory slots of a lane, 128 registers, four 128-thread CTAs per SM
+//     (the register form: 255 registers, 3136 bytes of stack, two CTAs);
+//   * the eight odd multiples (x, y, beta*x, rescaled to one common Z) live in a per-warp scratch block in global memory
+//     (L2): they are written once and read ~43 times per ladder, while the accumulator is touched by every instruction;
+//   * a unit waits for the TWO butterflies of the previous phase that produced its inputs (one flag per unit) instead
+//     of for all 64 of its blob group, so a blob group's phases overlap and the 4 x 148 x 4 resident warps stay busy.
+// ------------------------------------------------------------------------------------------------
+constexpr int K5_SCRATCH_FP = 26;                                           // per lane: 8 x (x, y, beta*x), zfix, dz
+constexpr size_t K5_SCRATCH_WARP_BYTES = (size_t)K5_SCRATCH_FP * 3 * 32 * 16;
+
+struct GScratch {                 // this lane's view of its warp's scratch block (uint4 granules, lane-interleaved)
+    uint4* p;
+    __device__ __forceinline__ Fp ld(int idx) const {
+        Fp r;
+        uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < 3; q++) d[q] = __ldcg(p + (idx * 3 + q) * 32);
+        return r;
+    }
+    __device__ __forceinline__ void st(int idx, const Fp& v) const {
+        const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+        for (int q = 0; q < 3; q++) __stcg(p + (idx * 3 + q) * 32, s[q]);
+    }
+};
+
+// slots 0..2 (a Jacobian point P of prime order, not the identity) <- k * P for the fixed scalar behind `ops`
+// (twiddle_ops.inc); returns true if the result is the identity.  Mirrors jac_mul_ops step by step.
+static __device__ __noinline__ bool k5_mul_ops_vm(uint32_t base, uint4* gsp, const uint16_t* __restrict__ ops) {
+    using namespace fpvm;
+    const Smem M{base};
+    const GScratch G{gsp};
+    // P aside (in the slots of table entry 7, which is written last), d = 2P
+    G.st(21, M.ld(0)); G.st(22, M.ld(1)); G.st(23, M.ld(2));
+    FPVM_RUN(base, K5_JAC_DBL);
+    M.st(3, G.ld(21)); M.st(4, G.ld(22));
+    FPVM_RUN(base, K5_TBL_ISO);                       // slots 5, 6 = P on the curve isomorphic by Z(2P)
+    G.st(25, M.ld(2));                                // Z(2P)
+    { const Fp dx = M.ld(0), dy = M.ld(1); M.st(3, dx); M.st(4, dy); }   // 2P as an affine point of that curve
+    { const Fp cx = M.ld(5), cy = M.ld(6); M.st(0, cx); M.st(1, cy); G.st(0, cx); G.st(1, cy); }
+    M.st(2, G.ld(23));
+#pragma unroll 1
+    for (int i = 1; i < 8; i++) {                     // (2i+1)P = (2i-1)P + 2P, z-ratio H kept for the rescaling
+        FPVM_RUN(base, K5_TBL_MADDZR_A);
+        G.st(3 * i + 2, M.ld(5));
+        FPVM_RUN(base, K5_TBL_MADDZR_B);
+        G.st(3 * i, M.ld(0)); G.st(3 * i + 1, M.ld(1));
+    }
+    M.st(5, M.ld(2)); M.st(6, G.ld(25));
+    FPVM_RUN(base, K5_MUL_T0_T1);                     // zfix = Z(15P) * Z(2P): maps the ladder's result back
+    G.st(24, M.ld(5));
+    // one common Z for all entries (entry 7 has it already), beta*x beside x
+    M.st(0, G.ld(23));                                // running z-ratio, starts at H_7
+    {
+        Fp beta;
+#pragma unroll
+        for (int l = 0; l < 12; l++) beta.v[l] = FpParams::beta(l);
+        M.st(6, beta);
+    }
+    M.st(3, G.ld(21));
+    FPVM_RUN(base, K5_TBL_BETA);
+    G.st(23, M.ld(7));
+#pragma unroll 1
+    for (int i = 6; i >= 0; i--) {
+        M.st(3, G.ld(3 * i)); M.st(4, G.ld(3 * i + 1));
+        if (i) M.st(5, G.ld(3 * i + 2));
+        FPVM_RUN(base, K5_TBL_RESCALE);
+        G.st(3 * i, M.ld(3)); G.st(3 * i + 1, M.ld(4)); G.st(3 * i + 2, M.ld(7));
+    }
+    // the ladder: mixed additions of table entries (phi applied by taking beta*x), doublings in between
+    bool inf = true;
+    const int n = ops[0];
+#pragma unroll 1
+    for (int c = 1; c <= n; c++) {
+        const uint32_t op = ops[c];
+        const int dbl = (int)(op >> 8);
+        if (dbl && !inf) fpvm_run(base, PROG_K5_JAC_DBL, PROG_K5_JAC_DBL_LEN, dbl);
+        if (op & 0x20u) {
+            const int idx = (int)(op & 7u);
+            const Fp ex = G.ld(3 * idx + ((op & 0x10u) ? 2 : 0));
+            Fp ey = G.ld(3 * idx + 1);
+            fe_cneg(ey, ey, (op & 8u) != 0);
+            if (inf) {
+                M.st(0, ex); M.st(1, ey); M.st(2, fp_one());
+                inf = false;
+            } else {
+                M.st(3, ex); M.st(4, ey);
+                const uint32_t z = FPVM_RUN(base, K5_JAC_MADD_A);
+                if (z & 2u) {                         // same x: cannot happen for a point of prime order, handled all the same
+                    if (z & 8u) FPVM_RUN(base, K5_JAC_DBL); else inf = true;
+                } else {
+                    FPVM_RUN(base, K5_JAC_MADD_B);
+                }
+            }
+        }
+    }
+    if (!inf) {
+        M.st(5, G.ld(24));
+        FPVM_RUN(base, K5_MUL_Z_T0);
+    }
+    return inf;
+}
+
+// slots 0..2 += slots 3..5 (Jacobian, either may be the identity as flagged); returns "the sum is the identity"
+static __device__ __noinline__ bool k5_add_vm(uint32_t base, bool acc_inf, bool q_inf) {
+    using namespace fpvm;
+    const Smem M{base};
+    if (q_inf) return acc_inf;
+    if (acc_inf) {
+        for (int c = 0; c < 3; c++) M.st(c, M.ld(3 + c));
+        return false;
+    }
+    const uint32_t z = FPVM_RUN(base, K5_JAC_ADD_A);
+    if (z & 8u) {                                     // H == 0
+        if (!(z & 0x80u)) return true;                // P1 == -P2
+        FPVM_RUN(base, K5_MUL_Z_QZ);                  // (U1, S1, Z1*Z2) is P1: double it
+        FPVM_RUN(base, K5_JAC_DBL);
+        return false;
+    }
+    FPVM_RUN(base, K5_JAC_ADD_B);
+    return false;
+}
+
+__device__ __forceinline__ void vm_put_pt(const fpvm::Smem& M, int slot0, const G1Jac& p, bool neg_y) {
+    M.st(slot0, p.x);
+    if (neg_y) { Fp ny; fe_neg(ny, p.y); M.st(slot0 + 1, ny); } else M.st(slot0 + 1, p.y);
+    M.st(slot0 + 2, p.z);
+}
+__device__ __forceinline__ G1Jac vm_get_pt(const fpvm::Smem& M, bool inf) {
+    G1Jac r;
+    if (inf) { jac_set_inf(r); return r; }
+    r.x = M.ld(0); r.y = M.ld(1); r.z = M.ld(2);
+    return r;
+}
+
+static __device__ __noinline__ void g1_ntt_butterfly_vm(G1Jac* __restrict__ pts, int B, int b, int t, int ph, uint32_t base, uint4* gsp) {
+    const fpvm::Smem M{base};
+    const int mode = ph >= 7, st = mode ? 13 - ph : ph;
+    const int len = 1 << st;
+    const int pos = t & (len - 1);
+    const int i = ((t >> st) << (st + 1)) + pos, j = i + len;
+    const int e = pos << (6 - st);  // twiddle exponent of omega_128
+    G1Jac* pi = &pts[(size_t)i * B + b];
+    G1Jac* pj = &pts[(size_t)j * B + b];
+    if (mode == 0) {
+        // v' = w^-e * v;  pi <- u + v';  pj <- u - v' (not needed in the last inverse stage)
+        bool v_inf;
+        {
+            const G1Jac v = ld_pt(pj);
+            v_inf = jac_is_inf(v);
+            if (!v_inf) vm_put_pt(M, 0, v, false);
+        }
+        if (!v_inf && e != 0) v_inf = k5_mul_ops_vm(base, gsp, c_twiddle_ops[(128 - e) & 127]);
+        const GScratch G{gsp};
+        if (st != 6 && !v_inf) { G.st(0, M.ld(0)); G.st(1, M.ld(1)); G.st(2, M.ld(2)); }   // v' aside (the table is dead now)
+        bool u_inf;
+        {
+            const G1Jac u = ld_pt(pi);
+            u_inf = jac_is_inf(u);
+            if (!u_inf) vm_put_pt(M, 3, u, false);
+        }
+        const bool s_inf = k5_add_vm(base, v_inf, u_inf);
+        if (st == 6) {
+            st_pt(pi, vm_get_pt(M, s_inf));
+            return;
+        }
+        {
+            const G1Jac u = ld_pt(pi);
+            st_pt(pi, vm_get_pt(M, s_inf));
+            if (!u_inf) vm_put_pt(M, 0, u, false);
+        }
+        if (!v_inf) {
+            M.st(3, G.ld(0));
+            Fp ny = G.ld(1);
+            fe_neg(ny, ny);
+            M.st(4, ny);
+            M.st(5, G.ld(2));
+        }
+        const bool d_inf = k5_add_vm(base, u_inf, v_inf);
+        st_pt(pj, vm_get_pt(M, d_inf));
+    } else if (st == 6) {
+        // first forward stage on (h || O^64):  pj <- w^e * h_i
+        const G1Jac u = ld_pt(pi);
+        bool u_inf = jac_is_inf(u);
+        if (u_inf || e == 0) { st_pt(pj, u); return; }
+        vm_put_pt(M, 0, u, false);
+        u_inf = k5_mul_ops_vm(base, gsp, c_twiddle_ops[e]);
+        st_pt(pj, vm_get_pt(M, u_inf));
+    } else {
+        // pi <- u + v;  pj <- w^e * (u - v)
+        bool u_inf, v_inf;
+        {
+            const G1Jac u = ld_pt(pi);
+            u_inf = jac_is_inf(u);
+            if (!u_inf) vm_put_pt(M, 0, u, false);
+            const G1Jac v = ld_pt(pj);
+            v_inf = jac_is_inf(v);
+            if (!v_inf) vm_put_pt(M, 3, v, false);
+        }
+        const bool s_inf = k5_add_vm(base, u_inf, v_inf);
+        {
+            const G1Jac u = ld_pt(pi);
+            st_pt(pi, vm_get_pt(M, s_inf));
+            if (!u_inf) vm_put_pt(M, 0, u, false);
+            const G1Jac v = ld_pt(pj);
+            if (!v_inf) vm_put_pt(M, 3, v, true);
+        }
+        bool d_inf = k5_add_vm(base, u_inf, v_inf);
+        if (!d_inf && e != 0) d_inf = k5_mul_ops_vm(base, gsp, c_twiddle_ops[e]);
+        st_pt(pj, vm_get_pt(M, d_inf));
+    }
+}
+
+// the butterfly of phase ph - 1 that wrote point x (both transforms are in place: each point belongs to exactly one
+// butterfly per phase, so these are also the only earlier readers of the points a unit is about to overwrite)
+__device__ __forceinline__ int ntt_producer(int ph, int x) {
+    if (ph <= 6) {                      // inverse DIT stage st = ph, producer at stage st - 1
+        const int sp = ph - 1;
+        return ((x >> (sp + 1)) << sp) + (x & ((1 << sp) - 1));
+    }
+    if (ph == 7) return x & 63;         // last inverse stage, butterfly x (x < 64; point x + 64 was only read there)
+    const int sp = 13 - ph + 1;         // forward DIF stage st = 13 - ph, producer at stage st + 1
+    return ((x >> (sp + 1)) << sp) + (x & ((1 << sp) - 1));
+}
+
+// queue[0] = ticket counter, queue[1 + (g*14 + ph)*64 + t] = 1 when unit (blob group g, phase ph, butterfly t) is done
+__global__ void __launch_bounds__(fpvm::NT, 4)
+k_fk20_g1_ntts_vm(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned* __restrict__ queue, uint4* __restrict__ scratch) {
+    extern __shared__ uint4 vm_smem[];
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(vm_smem) + threadIdx.x * 16u;
+    const int lane = threadIdx.x & 31;
+    uint4* gsp = scratch + ((size_t)blockIdx.x * (fpvm::NT / 32) + (threadIdx.x >> 5)) * (K5_SCRATCH_WARP_BYTES / 16) + lane;
+    const unsigned per_phase = (unsigned)G * 64u;
+    const unsigned total = (unsigned)(ph1 - ph0) * per_phase;
+    for (;;) {
+        unsigned id = 0;
+        if (lane == 0) id = atomicAdd(&queue[0], 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= total) break;
+        const unsigned rel = id / per_phase, rem = id - rel * per_phase;
+        const int g = (int)(rem >> 6), t = (int)(rem & 63u), ph = ph0 + (int)rel;
+        unsigned* flags = queue + 1 + (size_t)g * (NTT_PHASES * 64);
+        if (rel > 0) {
+            if (lane < 2) {
+                const int mode = ph >= 7, st = mode ? 13 - ph : ph;
+                const int pos = t & ((1 << st) - 1);
+                const int i = ((t >> st) << (st + 1)) + pos;
+                const int x = lane == 0 ? i : i + (1 << st);
+                const unsigned* f = flags + (ph - 1) * 64 + ntt_producer(ph, x);
+                while (ld_acquire_u32(f) == 0u) __nanosleep(200);
+            }
+            __syncwarp();
+        }
+        const int b = g * 32 + lane;
+        if (b < B) g1_ntt_butterfly_vm(pts, B, b, t, ph, base, gsp);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_inc(flags + ph * 64 + t);
     }
 }
 
@@ -589,8 +1032,20 @@ cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_
     return cudaSuccess;
 }
 
+static bool k4_register_form() {
+    static const bool v = [] { const char* e = getenv("EKZG_K4"); return e && e[0] == 'r'; }();
+    return v;
+}
+
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_blob_to_coeffs_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * N_BLOB * 4);
+    if (e != cudaSuccess) return e;
+    // four 48 KB CTAs of the shared-memory-operand kernels per SM
+    e = cudaFuncSetAttribute(k_fk20_msm_vm<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fk20_msm_vm<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fk20_g1_ntts_vm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_coeffs_to_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * N_BLOB * 4);
 }
@@ -620,10 +1075,13 @@ cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable
     // batch of B (the strides of scalars[][][B] and pts[][B] are those of the whole batch).
     // fewer blobs per launch -> more slices per MSM so the machine still fills
     if (cnt < 0) cnt = B - b0;
-    if ((size_t)B * ngroups >= 512 * 128) {
-        k_fk20_msm<4><<<dim3((cnt + 31) / 32, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
+    const bool wide = (size_t)B * ngroups >= 512 * 128;
+    if (k4_register_form()) {
+        if (wide) k_fk20_msm<4><<<dim3((cnt + 31) / 32, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
+        else k_fk20_msm<16><<<dim3((cnt + 7) / 8, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
     } else {
-        k_fk20_msm<16><<<dim3((cnt + 7) / 8, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
+        if (wide) k_fk20_msm_vm<4><<<dim3((cnt + 31) / 32, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);
+        else k_fk20_msm_vm<16><<<dim3((cnt + 7) / 8, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);
     }
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
@@ -634,25 +1092,47 @@ static int ntt_min_blocks() {
     static int v = [] { const char* e = getenv("EKZG_NTT_OCC"); int x = e ? atoi(e) : 2; return x < 2 ? 2 : (x > 4 ? 4 : x); }();
     return v;
 }
-
-size_t g1_ntt_queue_words(int B) { return 1 + (size_t)((B + 31) / 32) * NTT_PHASES; }
-
-// phases [ph0, ph1) of the two transforms over pts[128][B]; queue: g1_ntt_queue_words(B) words of scratch
-cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* queue, cudaStream_t st) {
-    if (!g_ntt_sms) {
-        int dev = 0;
-        cudaError_t e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&g_ntt_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-    }
-    const int G = (B + 31) / 32;
-    cudaError_t e = cudaMemsetAsync(queue, 0, g1_ntt_queue_words(B) * sizeof(uint32_t), st);
+static bool k5_register_form() {
+    static const bool v = [] { const char* e = getenv("EKZG_K5"); return e && e[0] == 'r'; }();
+    return v;
+}
+static cudaError_t ntt_query_sms() {
+    if (g_ntt_sms) return cudaSuccess;
+    int dev = 0, sms = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    const int mb = ntt_min_blocks();
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    g_ntt_sms = sms;
+    return cudaSuccess;
+}
+constexpr int K5_VM_CTAS_PER_SM = 4;
+
+// ticket counter + one completion flag per (blob group, phase, butterfly)
+size_t g1_ntt_queue_words(int B) { return 1 + (size_t)((B + 31) / 32) * NTT_PHASES * 64; }
+// odd-multiples tables of the resident warps of k_fk20_g1_ntts_vm (one block per warp slot of the persistent grid)
+size_t g1_ntt_scratch_bytes() {
+    if (ntt_query_sms() != cudaSuccess) return 0;
+    return (size_t)g_ntt_sms * K5_VM_CTAS_PER_SM * (fpvm::NT / 32) * K5_SCRATCH_WARP_BYTES;
+}
+
+// phases [ph0, ph1) of the two transforms over pts[128][B]; queue: g1_ntt_queue_words(B) words, scratch: g1_ntt_scratch_bytes()
+cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* queue, void* scratch, cudaStream_t st) {
+    cudaError_t e = ntt_query_sms();
+    if (e != cudaSuccess) return e;
+    const int G = (B + 31) / 32;
+    e = cudaMemsetAsync(queue, 0, g1_ntt_queue_words(B) * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
     const long units = (long)G * 64;                                   // warps that can run at once
-    const int grid = (int)std::min<long>((long)g_ntt_sms * mb, (units + NTT_THREADS / 32 - 1) / (NTT_THREADS / 32));
     unsigned* q = reinterpret_cast<unsigned*>(queue);
+    if (!k5_register_form()) {
+        const int grid = (int)std::min<long>((long)g_ntt_sms * K5_VM_CTAS_PER_SM, (units + fpvm::NT / 32 - 1) / (fpvm::NT / 32));
+        k_fk20_g1_ntts_vm<<<grid, fpvm::NT, fpvm::SMEM_BYTES, st>>>(pts, B, G, ph0, ph1, q, reinterpret_cast<uint4*>(scratch));
+        EKZG_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
+    const int mb = ntt_min_blocks();
+    const int grid = (int)std::min<long>((long)g_ntt_sms * mb, (units + NTT_THREADS / 32 - 1) / (NTT_THREADS / 32));
     if (mb == 2) k_fk20_g1_ntts<2><<<grid, NTT_THREADS, 0, st>>>(pts, B, G, ph0, ph1, q);
     else if (mb == 3) k_fk20_g1_ntts<3><<<grid, NTT_THREADS, 0, st>>>(pts, B, G, ph0, ph1, q);
     else k_fk20_g1_ntts<4><<<grid, NTT_THREADS, 0, st>>>(pts, B, G, ph0, ph1, q);
@@ -660,8 +1140,8 @@ cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* 
     return cudaSuccess;
 }
 
-cudaError_t launch_fk20_g1_ntts(G1Jac* pts, int B, uint32_t* queue, cudaStream_t st) {
-    return launch_g1_ntt_phases(pts, B, 0, NTT_PHASES, queue, st);
+cudaError_t launch_fk20_g1_ntts(G1Jac* pts, int B, uint32_t* queue, void* scratch, cudaStream_t st) {
+    return launch_g1_ntt_phases(pts, B, 0, NTT_PHASES, queue, scratch, st);
 }
 
 cudaError_t launch_g1_compress(const G1Jac* pts, uint8_t* out, int npos, int B, cudaStream_t st) {
@@ -703,11 +1183,11 @@ static cudaError_t fill_table(const G1Jac* pts, const G1Affine* aff, int npoints
 }
 
 cudaError_t launch_fk20_setup(const G1Affine* srs, G1Jac* pts_scratch /*128*64*/, G1Affine* qaff /*8192*nw*/, G1Affine* table,
-                              const DevTables& T, uint32_t* queue /*g1_ntt_queue_words(64)*/, cudaStream_t st) {
+                              const DevTables& T, uint32_t* queue /*g1_ntt_queue_words(64)*/, void* ntt_scratch, cudaStream_t st) {
     k_fk20_setup_vectors<<<(128 * 64 + 127) / 128, 128, 0, st>>>(srs, pts_scratch);
     EKZG_LAUNCH_CHECK();
     // F_k = NTT_128(V_k || O^64) for the 64 vectors at once: the forward half of K5 with "blob" := k
-    cudaError_t e = launch_g1_ntt_phases(pts_scratch, 64, 7, NTT_PHASES, queue, st);
+    cudaError_t e = launch_g1_ntt_phases(pts_scratch, 64, 7, NTT_PHASES, queue, ntt_scratch, st);
     if (e != cudaSuccess) return e;
     return fill_table(pts_scratch, nullptr, FK20_MSMS * FK20_POINTS, qaff, table, T.fk20, st);
 }

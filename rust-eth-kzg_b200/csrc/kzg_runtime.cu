@@ -58,6 +58,7 @@ Status Workspace::alloc(int cap, bool with_io) {
     EKZG_CUDA(cudaMalloc(&d_scalars, (size_t)cap * FK20_MSMS * FK20_POINTS * 32));
     EKZG_CUDA(cudaMalloc(&d_pts, (size_t)cap * 128 * sizeof(G1Jac)));
     EKZG_CUDA(cudaMalloc(&d_queue, g1_ntt_queue_words(cap) * sizeof(uint32_t)));
+    EKZG_CUDA(cudaMalloc(&d_ntt_scratch, g1_ntt_scratch_bytes()));
     if (with_io) {
         EKZG_CUDA(cudaMalloc(&d_blobs, (size_t)cap * BYTES_PER_BLOB));
         EKZG_CUDA(cudaMalloc(&d_cells, (size_t)cap * N_EXT * 32));
@@ -91,7 +92,7 @@ Status Workspace::ensure_recover_buffers() {
 void Workspace::release() {
     cudaFree(d_rcells); cudaFreeHost(h_rcells); cudaFree(d_slotmap); cudaFreeHost(h_slotmap); cudaFree(d_ze); cudaFree(d_czinv);
     cudaFree(d_c48); cudaFree(d_z32); cudaFree(d_out48); cudaFree(d_z); cudaFree(d_aff); cudaFree(d_status2);
-    cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_queue); cudaFree(d_proofs); cudaFree(d_status);
+    cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_queue); cudaFree(d_ntt_scratch); cudaFree(d_proofs); cudaFree(d_status);
     cudaFreeHost(h_blobs); cudaFreeHost(h_cells); cudaFreeHost(h_proofs); cudaFreeHost(h_status);
     if (done) cudaEventDestroy(done);
     for (int i = 0; i < MAX_SUB; i++) {
@@ -251,10 +252,13 @@ Status Context::init(bool use_precomp) {
     EKZG_CUDA(cudaMalloc(&qaff, nbases * sizeof(G1Affine)));
     T_.fk20.table = table;
     uint32_t* setup_queue = nullptr;
+    void* setup_ntt_scratch = nullptr;
     EKZG_CUDA(cudaMalloc(&setup_queue, g1_ntt_queue_words(64) * sizeof(uint32_t)));
-    EKZG_CUDA(launch_fk20_setup(T_.srs_g1, scratch, qaff, table, T_, setup_queue, st));
+    EKZG_CUDA(cudaMalloc(&setup_ntt_scratch, g1_ntt_scratch_bytes()));
+    EKZG_CUDA(launch_fk20_setup(T_.srs_g1, scratch, qaff, table, T_, setup_queue, setup_ntt_scratch, st));
     EKZG_CUDA(cudaDeviceSynchronize());
     cudaFree(setup_queue);
+    cudaFree(setup_ntt_scratch);
     cudaFree(scratch);
     cudaFree(qaff);
     // monomial SRS tables (commitments, single-point proofs)
@@ -322,7 +326,7 @@ Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells
     if (ev) cudaEventRecord((*ev)[2], stream);
     EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, n, stream));
     if (ev) cudaEventRecord((*ev)[3], stream);
-    EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, n, ws.d_queue, stream));
+    EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, n, ws.d_queue, ws.d_ntt_scratch, stream));
     if (ev) cudaEventRecord((*ev)[4], stream);
     EKZG_CUDA(launch_g1_compress(ws.d_pts, d_proofs, N_CELLS, n, stream));
     if (ev) cudaEventRecord((*ev)[5], stream);
@@ -488,7 +492,7 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
             }
         }
         if (want_proofs) {
-            EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, cnt, ws.d_queue, ws.stream));
+            EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, cnt, ws.d_queue, ws.d_ntt_scratch, ws.stream));
             stamp("K5 done", -1, ws.stream);
             EKZG_CUDA(launch_g1_compress(ws.d_pts, ws.d_proofs, N_CELLS, cnt, ws.stream));
             EKZG_CUDA(cudaMemcpyAsync(proofs_pinned ? proofs + first * PROOFS_PER_BLOB : ws.h_proofs, ws.d_proofs, (size_t)cnt * PROOFS_PER_BLOB,

@@ -45,7 +45,8 @@ struct Workspace {
     uint8_t* d_cells = nullptr;
     uint32_t* d_scalars = nullptr;
     G1Jac* d_pts = nullptr;
-    uint32_t* d_queue = nullptr;   // ticket counter + per-(blob group, phase) completion counters of K5
+    uint32_t* d_queue = nullptr;   // ticket counter + per-unit completion flags of K5
+    void* d_ntt_scratch = nullptr; // K5: odd-multiples tables of the resident warps (g1_ntt_scratch_bytes())
     uint8_t* d_proofs = nullptr;
     uint32_t* d_status = nullptr;
     // small per-blob side buffers of the 4844 path

@@ -263,3 +263,47 @@ def test_field_mul_adversarial_limbs(emu_field, mod, n, pre):
         assert val(out) == (a + b) % mod
         getattr(emu_field, "emu_%s_sub" % pre)(arr(a, n), arr(b, n), out)
         assert val(out) == (a - b) % mod
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the shared-memory-operand Fp interpreter of K4 / K5 (csrc/fpvm.cuh) on the CPU: the same `step` the device runs,
+# every program of tools/fpvm_asm.py, against the Python emulation of the programs (tests/test_fpvm_programs.py
+# checks those against the group law)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def emu_fpvm():
+    return _build("emu_fpvm")
+
+
+def test_fpvm_interpreter_matches_program_emulation(emu_fpvm):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import fpvm_asm as A
+    words = [w for p in A.PROGRAMS.values() for w in p]
+    assert emu_fpvm.emu_fpvm_words() == len(words)
+    emu_fpvm.emu_fpvm_word.restype = ctypes.c_uint32
+    assert [emu_fpvm.emu_fpvm_word(i) for i in range(len(words))] == words
+    emu_fpvm.emu_fpvm_run.restype = ctypes.c_uint32
+    rng = random.Random(11)
+    Rm = 1 << 384
+    pc = 0
+    for name, prog in A.PROGRAMS.items():
+        for trial in range(6):
+            # plain values; trial 0 plants equal operands / zeros so the zero masks and the borrow paths are hit
+            vals = [rng.randrange(P) for _ in range(8)]
+            if trial == 0:
+                vals[3] = vals[0]; vals[4] = vals[1]; vals[5] = 0; vals[6] = P - 1
+            exp = list(vals)
+            mask = A.emulate(prog, exp)
+            buf = (ctypes.c_uint32 * 96)()
+            for s in range(8):
+                m = vals[s] * Rm % P
+                for l in range(12):
+                    buf[12 * s + l] = (m >> (32 * l)) & 0xFFFFFFFF
+            got_mask = emu_fpvm.emu_fpvm_run(pc, len(prog), 1, buf)
+            Ri = pow(Rm, -1, P)
+            got = [sum(int(buf[12 * s + l]) << (32 * l) for l in range(12)) for s in range(8)]
+            assert all(g < P for g in got), name
+            assert [g * Ri % P for g in got] == exp, name
+            assert got_mask == mask, name
+        pc += len(prog)
