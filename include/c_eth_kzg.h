@@ -39,9 +39,17 @@ typedef struct CResult {
     char *error_msg;
 } CResult;
 
-/* bindings/c/src/lib.rs:79.  Builds the SRS-derived tables on the current CUDA device (override with
- * EKZG_DEVICE).  use_precomp selects the fixed-base window width: false -> 8 bits, true -> the width in
- * EKZG_FK20_WINDOW (default 8; wider windows trade HBM for fewer point additions per blob).
+/* bindings/c/src/lib.rs:79.  Builds the SRS-derived tables on the calling thread's current CUDA device (override
+ * with EKZG_DEVICE), or on every device named in EKZG_DEVICES ("all" or a comma list of ordinals): batch calls are
+ * then sharded over those devices and single-item calls dealt round-robin, the counterpart of the reference's rayon
+ * fan-out over the cores of the box.  The caller's current device is restored before every entry point returns.
+ * use_precomp selects the fixed-base window widths (the reference's UsePrecomp, fixed_base_msm.rs:83-89):
+ *   false -> 8-bit windows, 3 GiB of tables per device;
+ *   true  -> the WIDEST windows whose tables fit the device's free memory minus a 16 GiB reserve (or minus
+ *            EKZG_HBM_RESERVE_GIB): on an empty 180 GB B200 that is 14-bit FK20 windows (114 GiB) plus 13-bit SRS windows
+ *            (30 GiB), built on the device in about 2 s.  A second context or another tenant on the same GPU gets
+ *            narrower windows (more point additions per blob, up to 1.5x slower) -- EKZG_TRACE=1 prints the widths and
+ *            bytes chosen; EKZG_FK20_WINDOW / EKZG_SRS_WINDOW (4..16) pin them.
  * Returns NULL if no CUDA device is usable: there is no CPU fallback. */
 DASContext *eth_kzg_das_context_new(bool use_precomp);
 
@@ -137,6 +145,14 @@ CResult eth_kzg_b200_recover_cells_and_kzg_proofs_batch(const DASContext *ctx, u
 int eth_kzg_b200_context_device(const DASContext *ctx);
 int eth_kzg_b200_context_window(const DASContext *ctx);
 uint64_t eth_kzg_b200_context_table_bytes(const DASContext *ctx);
+/* window width of the SRS (commitment / proof) tables; how many devices the context spans (EKZG_DEVICES) and the CUDA
+ * ordinal of the i-th of them (-1 if out of range).  The three getters above report the first device. */
+int eth_kzg_b200_context_srs_window(const DASContext *ctx);
+int eth_kzg_b200_context_device_count(const DASContext *ctx);
+int eth_kzg_b200_context_device_at(const DASContext *ctx, int i);
+/* how a batch of n items is cut over `parts` devices: device i works on items [*lo, *lo + *cnt) -- whole groups of 32
+ * (one G1-NTT work unit is 32 blobs wide), sizes differing by at most one group.  Host-only helper. */
+void eth_kzg_b200_debug_shard_bounds(uint64_t n, uint64_t parts, uint64_t i, uint64_t *lo, uint64_t *cnt);
 /* kernels launched by this library in this process so far (launch accounting in benchmarks) */
 uint64_t eth_kzg_b200_kernel_launch_count(void);
 

@@ -5,13 +5,21 @@
 #include <cstdlib>
 #include <cstring>
 #include "../../include/c_eth_kzg.h"
-#include "kzg_runtime.h"
+#include "kzg_multi.h"
 #include "host_pairing.h"
 
 using ekzg::Status;
 
 struct DASContext {
-    std::unique_ptr<ekzg::Context> inner;
+    std::unique_ptr<ekzg::DeviceSet> set;   // one ekzg::Context per device of EKZG_DEVICES (default: the current device)
+};
+
+// Every entry point binds the device(s) of its context on the calling thread; the caller's own current device is put
+// back on return, so the library has no side effect on the CUDA state of the host application.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); } }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 static CResult c_ok() { return CResult{Ok, nullptr}; }
@@ -21,29 +29,33 @@ static CResult c_err(const std::string& m) {
     return CResult{Err, p};
 }
 static CResult to_c(const Status& s) { return s.ok ? c_ok() : c_err(s.msg); }
-static const ekzg::Context& cx(const DASContext* ctx) {
+static const ekzg::DeviceSet& ds(const DASContext* ctx) {
     if (!ctx) {  // the reference asserts (bindings/c/src/lib.rs: `assert!(!ctx.is_null())`) and aborts
         fprintf(stderr, "c_eth_kzg_b200: null DASContext\n");
         abort();
     }
-    return *ctx->inner;
+    return *ctx->set;
 }
+static const ekzg::Context& cx(const DASContext* ctx) { return ds(ctx).primary(); }      // calls that use one device
+static const ekzg::Context& next_cx(const DASContext* ctx) { return ds(ctx).next(); }    // single-item calls: round-robin
 
 extern "C" {
 
 DASContext* eth_kzg_das_context_new(bool use_precomp) {
-    std::unique_ptr<ekzg::Context> c;
-    Status s = ekzg::Context::create(use_precomp, &c);
+    DeviceGuard guard;
+    std::unique_ptr<ekzg::DeviceSet> c;
+    Status s = ekzg::DeviceSet::create(use_precomp, &c);
     if (!s.ok) {
         fprintf(stderr, "c_eth_kzg_b200: context creation failed: %s\n", s.msg.c_str());
         return nullptr;
     }
     DASContext* d = new DASContext();
-    d->inner = std::move(c);
+    d->set = std::move(c);
     return d;
 }
 
 void eth_kzg_das_context_free(DASContext* ctx) {
+    DeviceGuard guard;
     if (ctx) delete ctx;
 }
 
@@ -57,7 +69,8 @@ uint64_t eth_kzg_constant_cells_per_ext_blob(void) { return ekzg::N_CELLS; }
 
 CResult eth_kzg_compute_cells_and_kzg_proofs(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells, uint8_t** out_proofs) {
     std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32), proofs((size_t)ekzg::N_CELLS * 48);
-    Status s = cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), proofs.data());
+    DeviceGuard guard;
+    Status s = next_cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), proofs.data());
     if (!s.ok) return c_err(s.msg);
     for (int i = 0; i < ekzg::N_CELLS; i++) {  // pointer_utils.rs:53-62 write_to_2d_slice
         memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
@@ -68,7 +81,8 @@ CResult eth_kzg_compute_cells_and_kzg_proofs(const DASContext* ctx, const uint8_
 
 CResult eth_kzg_compute_cells(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells) {
     std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32);
-    Status s = cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), nullptr);
+    DeviceGuard guard;
+    Status s = next_cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), nullptr);
     if (!s.ok) return c_err(s.msg);
     for (int i = 0; i < ekzg::N_CELLS; i++) memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
     return c_ok();
@@ -76,34 +90,46 @@ CResult eth_kzg_compute_cells(const DASContext* ctx, const uint8_t* blob, uint8_
 
 CResult eth_kzg_b200_compute_cells_and_kzg_proofs_batch(const DASContext* ctx, uint64_t n, const uint8_t* blobs, uint8_t* out_cells,
                                                         uint8_t* out_proofs, uint8_t* blob_status) {
-    return to_c(cx(ctx).compute_cells_and_kzg_proofs_batch(n, blobs, out_cells, out_proofs, blob_status, out_proofs != nullptr));
+    DeviceGuard guard;
+    return to_c(ds(ctx).compute_cells_and_kzg_proofs_batch(n, blobs, out_cells, out_proofs, blob_status, out_proofs != nullptr));
 }
 
 CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext* ctx, uint64_t n, const void* d_blobs, void* d_cells,
                                                          void* d_proofs, void* d_status, void* cuda_stream) {
-    const ekzg::Context& c = cx(ctx);
-    Status s = c.bind_device();
-    if (!s.ok) return c_err(s.msg);
+    DeviceGuard guard;
     if (n == 0) return c_ok();
     if (n > (1u << 20)) return c_err("batch too large");
+    const ekzg::Context* owner = ds(ctx).size() == 1 ? &cx(ctx) : ds(ctx).owner_of(d_blobs);
+    if (!owner) return c_err("the device buffers are not on a device of this context (EKZG_DEVICES)");
+    const ekzg::Context& c = *owner;
+    Status s = c.bind_device();
+    if (!s.ok) return c_err(s.msg);
     ekzg::Workspace* ws = c.acquire((int)n, false);
     if (!ws) return c_err("device memory allocation failed");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     cudaStreamWaitEvent(st, ws->done, 0);  // the scratch buffers' previous user may have run on another stream
     s = c.fk20_device(*ws, (int)n, (const uint8_t*)d_blobs, (uint8_t*)d_cells, (uint8_t*)d_proofs, (uint32_t*)d_status, st);
-    // the scratch buffers are reused by the next call on this context: order later work after this batch
-    if (s.ok) {
-        cudaEventRecord(ws->done, st);
-        cudaStreamWaitEvent(ws->stream, ws->done, 0);
-    }
+    // the scratch buffers are reused by the next call on this context: order later work after this batch -- also when the
+    // call failed half way, because the kernels enqueued before the failure still run
+    cudaEventRecord(ws->done, st);
+    cudaStreamWaitEvent(ws->stream, ws->done, 0);
+    if (!s.ok) cudaGetLastError();
     c.give_back(ws);
     return to_c(s);
 }
 
 int eth_kzg_b200_context_device(const DASContext* ctx) { return cx(ctx).device(); }
 int eth_kzg_b200_context_window(const DASContext* ctx) { return cx(ctx).tables().fk20.w; }
+int eth_kzg_b200_context_srs_window(const DASContext* ctx) { return cx(ctx).tables().srs.w; }
 uint64_t eth_kzg_b200_context_table_bytes(const DASContext* ctx) { return cx(ctx).table_bytes(); }
+int eth_kzg_b200_context_device_count(const DASContext* ctx) { return (int)ds(ctx).size(); }
+int eth_kzg_b200_context_device_at(const DASContext* ctx, int i) { return i >= 0 && (size_t)i < ds(ctx).size() ? ds(ctx).at(i).device() : -1; }
 uint64_t eth_kzg_b200_kernel_launch_count(void) { return ekzg::g_kernel_launches.load(); }
+
+// Test hook (host only): the contiguous shard [lo, lo + cnt) that device i of `parts` gets from a batch of n items
+void eth_kzg_b200_debug_shard_bounds(uint64_t n, uint64_t parts, uint64_t i, uint64_t* lo, uint64_t* cnt) {
+    ekzg::DeviceSet::shard_bounds(n, (size_t)parts, (size_t)i, lo, cnt);
+}
 
 void eth_kzg_b200_set_profiling(const DASContext* ctx, bool on) { cx(ctx).set_profiling(on); }
 int eth_kzg_b200_collect_stage_times(const DASContext* ctx, double* ms_out) {
@@ -115,6 +141,7 @@ int eth_kzg_b200_collect_stage_times(const DASContext* ctx, double* ms_out) {
 // MSM outputs (natural j order) and h commitments as compressed points.  Synchronous; test hook.
 CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blob, uint32_t* out_scalars, uint8_t* out_msm, uint8_t* out_h) {
     using namespace ekzg;
+    DeviceGuard guard;
     const Context& c = cx(ctx);
     Status s = c.bind_device();
     if (!s.ok) return c_err(s.msg);
@@ -163,24 +190,30 @@ int eth_kzg_b200_debug_pairing_check(int n, const uint8_t* g1_xy, const int* g2_
 }
 
 CResult eth_kzg_blob_to_kzg_commitment(const DASContext* ctx, const uint8_t* blob, uint8_t* out) {
-    return to_c(cx(ctx).blob_to_kzg_commitment_batch(1, blob, out, nullptr));
+    DeviceGuard guard;
+    return to_c(next_cx(ctx).blob_to_kzg_commitment_batch(1, blob, out, nullptr));
 }
 CResult eth_kzg_compute_kzg_proof(const DASContext* ctx, const uint8_t* blob, const uint8_t* z, uint8_t* out_proof, uint8_t* out_y) {
-    return to_c(cx(ctx).compute_kzg_proof_batch(1, blob, z, out_proof, out_y, nullptr));
+    DeviceGuard guard;
+    return to_c(next_cx(ctx).compute_kzg_proof_batch(1, blob, z, out_proof, out_y, nullptr));
 }
 CResult eth_kzg_compute_blob_kzg_proof(const DASContext* ctx, const uint8_t* blob, const uint8_t* commitment, uint8_t* out_proof) {
-    return to_c(cx(ctx).compute_blob_kzg_proof_batch(1, blob, commitment, out_proof, nullptr));
+    DeviceGuard guard;
+    return to_c(next_cx(ctx).compute_blob_kzg_proof_batch(1, blob, commitment, out_proof, nullptr));
 }
 CResult eth_kzg_b200_blob_to_kzg_commitment_batch(const DASContext* ctx, uint64_t n, const uint8_t* blobs, uint8_t* out, uint8_t* item_status) {
-    return to_c(cx(ctx).blob_to_kzg_commitment_batch(n, blobs, out, item_status));
+    DeviceGuard guard;
+    return to_c(ds(ctx).blob_to_kzg_commitment_batch(n, blobs, out, item_status));
 }
 CResult eth_kzg_b200_compute_blob_kzg_proof_batch(const DASContext* ctx, uint64_t n, const uint8_t* blobs, const uint8_t* commitments,
                                                   uint8_t* out_proofs, uint8_t* item_status) {
-    return to_c(cx(ctx).compute_blob_kzg_proof_batch(n, blobs, commitments, out_proofs, item_status));
+    DeviceGuard guard;
+    return to_c(ds(ctx).compute_blob_kzg_proof_batch(n, blobs, commitments, out_proofs, item_status));
 }
 CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t cells_length, const uint8_t* const* cells, uint64_t cell_indices_length,
                                          const uint64_t* cell_indices, uint8_t** out_cells, uint8_t** out_proofs) {
-    const ekzg::Context& c = cx(ctx);
+    DeviceGuard guard;
+    const ekzg::Context& c = next_cx(ctx);
     if (cells_length != cell_indices_length)  // recovery.rs:95-100
         return c_err("Recovery(NumCellIndicesNotEqualToNumCells)");
     if (cells_length > 4096) return c_err("Recovery(TooManyCellsReceived)");
@@ -198,21 +231,25 @@ CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t cells_l
 }
 CResult eth_kzg_b200_recover_cells_and_kzg_proofs_batch(const DASContext* ctx, uint64_t n, const uint64_t* cell_counts, const uint64_t* cell_indices,
                                                         const uint8_t* cells, uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) {
-    return to_c(cx(ctx).recover_cells_and_kzg_proofs_batch(n, cell_counts, cell_indices, cells, out_cells, out_proofs, item_status));
+    DeviceGuard guard;
+    return to_c(ds(ctx).recover_cells_and_kzg_proofs_batch(n, cell_counts, cell_indices, cells, out_cells, out_proofs, item_status));
 }
 
 CResult eth_kzg_verify_cell_kzg_proof_batch(const DASContext* ctx, uint64_t commitments_length, const uint8_t* const* commitments,
                                             uint64_t cell_indices_length, const uint64_t* cell_indices, uint64_t cells_length,
                                             const uint8_t* const* cells, uint64_t proofs_length, const uint8_t* const* proofs, bool* verified) {
-    return to_c(cx(ctx).verify_cell_kzg_proof_batch(commitments_length, commitments, cell_indices_length, cell_indices, cells_length, cells,
+    DeviceGuard guard;
+    return to_c(next_cx(ctx).verify_cell_kzg_proof_batch(commitments_length, commitments, cell_indices_length, cell_indices, cells_length, cells,
                                                     proofs_length, proofs, verified));
 }
 CResult eth_kzg_verify_kzg_proof(const DASContext* ctx, const uint8_t* commitment, const uint8_t* z, const uint8_t* y, const uint8_t* proof,
                                  bool* verified) {
-    return to_c(cx(ctx).verify_kzg_proofs(0, 1, nullptr, &commitment, z, y, &proof, verified));
+    DeviceGuard guard;
+    return to_c(next_cx(ctx).verify_kzg_proofs(0, 1, nullptr, &commitment, z, y, &proof, verified));
 }
 CResult eth_kzg_verify_blob_kzg_proof(const DASContext* ctx, const uint8_t* blob, const uint8_t* commitment, const uint8_t* proof, bool* verified) {
-    return to_c(cx(ctx).verify_kzg_proofs(1, 1, &blob, &commitment, nullptr, nullptr, &proof, verified));
+    DeviceGuard guard;
+    return to_c(next_cx(ctx).verify_kzg_proofs(1, 1, &blob, &commitment, nullptr, nullptr, &proof, verified));
 }
 CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext* ctx, uint64_t blobs_length, const uint8_t* const* blobs, uint64_t commitments_length,
                                             const uint8_t* const* commitments, uint64_t proofs_length, const uint8_t* const* proofs,
@@ -221,7 +258,8 @@ CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext* ctx, uint64_t blob
         *verified = false;
         return c_err("Verifier(BatchVerificationInputsMustHaveSameLength)");
     }
-    return to_c(cx(ctx).verify_kzg_proofs(1, blobs_length, blobs, commitments, nullptr, nullptr, proofs, verified));
+    DeviceGuard guard;
+    return to_c(next_cx(ctx).verify_kzg_proofs(1, blobs_length, blobs, commitments, nullptr, nullptr, proofs, verified));
 }
 
 }  // extern "C"

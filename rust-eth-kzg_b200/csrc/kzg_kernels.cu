@@ -1041,11 +1041,18 @@ cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_blob_to_coeffs_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * N_BLOB * 4);
     if (e != cudaSuccess) return e;
     // four 48 KB CTAs of the shared-memory-operand kernels per SM
+    // (48 KB of dynamic shared memory plus any static bytes is above the 48 KB a kernel gets without opting in)
     e = cudaFuncSetAttribute(k_fk20_msm_vm<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fk20_msm_vm<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpvm::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fk20_msm_vm<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fk20_msm_vm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpvm::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fk20_g1_ntts_vm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fk20_g1_ntts_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, fpvm::SMEM_BYTES);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_coeffs_to_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * N_BLOB * 4);
 }

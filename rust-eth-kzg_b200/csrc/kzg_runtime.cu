@@ -79,13 +79,24 @@ Status Workspace::alloc(int cap, bool with_io) {
 }
 
 Status Workspace::ensure_recover_buffers() {
-    if (d_rcells) return Status::Ok();
-    EKZG_CUDA(cudaMalloc(&d_rcells, (size_t)capacity * N_CELLS * BYTES_PER_CELL));
-    EKZG_CUDA(cudaMallocHost(&h_rcells, (size_t)capacity * N_CELLS * BYTES_PER_CELL));
-    EKZG_CUDA(cudaMalloc(&d_slotmap, (size_t)capacity * 128 * sizeof(int16_t)));
-    EKZG_CUDA(cudaMallocHost(&h_slotmap, (size_t)capacity * 128 * sizeof(int16_t)));
-    EKZG_CUDA(cudaMalloc(&d_ze, (size_t)capacity * 128 * sizeof(Fr)));
-    EKZG_CUDA(cudaMalloc(&d_czinv, (size_t)capacity * 128 * sizeof(Fr)));
+    if (recover_ready) return Status::Ok();
+    auto all = [&]() -> Status {
+        EKZG_CUDA(cudaMalloc(&d_rcells, (size_t)capacity * N_CELLS * BYTES_PER_CELL));
+        EKZG_CUDA(cudaMallocHost(&h_rcells, (size_t)capacity * N_CELLS * BYTES_PER_CELL));
+        EKZG_CUDA(cudaMalloc(&d_slotmap, (size_t)capacity * 128 * sizeof(int16_t)));
+        EKZG_CUDA(cudaMallocHost(&h_slotmap, (size_t)capacity * 128 * sizeof(int16_t)));
+        EKZG_CUDA(cudaMalloc(&d_ze, (size_t)capacity * 128 * sizeof(Fr)));
+        EKZG_CUDA(cudaMalloc(&d_czinv, (size_t)capacity * 128 * sizeof(Fr)));
+        return Status::Ok();
+    };
+    Status s = all();
+    if (!s.ok) {   // all six or none: a half-built set must never be seen by the next borrower of this workspace
+        cudaFree(d_rcells); cudaFreeHost(h_rcells); cudaFree(d_slotmap); cudaFreeHost(h_slotmap); cudaFree(d_ze); cudaFree(d_czinv);
+        d_rcells = nullptr; h_rcells = nullptr; d_slotmap = nullptr; h_slotmap = nullptr; d_ze = nullptr; d_czinv = nullptr;
+        cudaGetLastError();
+        return s;
+    }
+    recover_ready = true;
     return Status::Ok();
 }
 
@@ -112,9 +123,9 @@ Status Context::bind_device() const {
     return Status::Ok();
 }
 
-Status Context::create(bool use_precomp, std::unique_ptr<Context>* out) {
+Status Context::create(bool use_precomp, std::unique_ptr<Context>* out, int device) {
     std::unique_ptr<Context> c(new Context());
-    Status s = c->init(use_precomp);
+    Status s = c->init(use_precomp, device);
     if (!s.ok) return s;
     *out = std::move(c);
     return Status::Ok();
@@ -136,11 +147,22 @@ static Status dev_alloc(std::vector<void*>& allocs, T** p, size_t count) {
 }
 #define EKZG_TRY(expr) do { ::ekzg::Status s_ = (expr); if (!s_.ok) return s_; } while (0)
 
-Status Context::init(bool use_precomp) {
+// device memory the table sizing leaves free for workspaces and other tenants (default 16 GiB)
+static size_t hbm_reserve_bytes() {
+    const char* e = getenv("EKZG_HBM_RESERVE_GIB");
+    const double gib = e ? atof(e) : 16.0;
+    return (size_t)((gib < 1.0 ? 1.0 : gib) * 1073741824.0);
+}
+
+Status Context::init(bool use_precomp, int device) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return Status::Error("no CUDA device: this backend has no CPU fallback");
-    if (const char* e = getenv("EKZG_DEVICE")) {
+    if (device >= 0) {                          // one member of a multi-device set (kzg_multi.cu)
+        if (device >= ndev) return Status::Error("EKZG_DEVICES names device " + std::to_string(device) + " but only " + std::to_string(ndev) + " are visible");
+        device_ = device;
+        EKZG_CUDA(cudaSetDevice(device_));
+    } else if (const char* e = getenv("EKZG_DEVICE")) {
         device_ = atoi(e);
         EKZG_CUDA(cudaSetDevice(device_));
     } else {
@@ -162,7 +184,7 @@ Status Context::init(bool use_precomp) {
         } else {
             size_t free_b = 0, total_b = 0;
             EKZG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            const size_t reserve = ((size_t)16 << 30) + (size_t)4096 * (255 / 12 + 1) * ((size_t)1 << 11) * sizeof(G1Affine);  // workspaces + SRS tables
+            const size_t reserve = hbm_reserve_bytes() + (size_t)4096 * (255 / 12 + 1) * ((size_t)1 << 11) * sizeof(G1Affine);  // workspaces + SRS tables
             for (int cand : {14, 13, 12, 10, 8}) {
                 w = cand;
                 const size_t need = (size_t)FK20_MSMS * FK20_POINTS * (255 / cand + 1) * ((size_t)1 << (cand - 1)) * sizeof(G1Affine);
@@ -180,7 +202,7 @@ Status Context::init(bool use_precomp) {
         size_t free_b = 0, total_b = 0;
         EKZG_CUDA(cudaMemGetInfo(&free_b, &total_b));
         auto table_bytes = [](size_t npoints, int wb) { return npoints * (size_t)(255 / wb + 1) * ((size_t)1 << (wb - 1)) * sizeof(G1Affine); };
-        if (table_bytes((size_t)FK20_MSMS * FK20_POINTS, w) + table_bytes(4096, 13) + ((size_t)16 << 30) <= free_b) ws = 13;
+        if (table_bytes((size_t)FK20_MSMS * FK20_POINTS, w) + table_bytes(4096, 13) + hbm_reserve_bytes() <= free_b) ws = 13;
     }
     if (ws < 4 || ws > 16) return Status::Error("EKZG_SRS_WINDOW must be in [4, 16]");
     T_.srs.set_window(ws);
@@ -274,26 +296,73 @@ Status Context::init(bool use_precomp) {
     return Status::Ok();
 }
 
+// Workspace capacities come in few sizes (powers of two from 32 up to the chunk capacity, then the chunk capacity itself), so
+// callers with varying batch sizes -- the coalescer produces every size from 1 to the cap -- reuse each other's workspaces.
+static int round_capacity(int n) {
+    const int chunk = chunk_capacity();
+    if (n >= chunk) return n;
+    int c = 32;
+    while (c < n) c <<= 1;
+    return std::min(c, chunk);
+}
+
 Workspace* Context::acquire(int min_capacity, bool with_io) const {
     {
         std::lock_guard<std::mutex> g(pool_mu_);
+        int best = -1;   // best fit: a one-blob call must not take the 1024-blob workspace from under a concurrent batch
         for (size_t i = 0; i < pool_.size(); i++) {
             Workspace* w = pool_[i];
-            if (w->capacity >= min_capacity && (!with_io || w->d_blobs)) {
-                pool_.erase(pool_.begin() + i);
-                return w;
-            }
+            if (w->capacity >= min_capacity && (!with_io || w->d_blobs) && (best < 0 || w->capacity < pool_[best]->capacity)) best = (int)i;
+        }
+        if (best >= 0) {
+            Workspace* w = pool_[best];
+            pool_.erase(pool_.begin() + best);
+            return w;
         }
     }
-    Workspace* w = new Workspace();
-    Status s = w->alloc(min_capacity, with_io);
-    if (!s.ok) { w->release(); delete w; return nullptr; }
-    return w;
+    const int cap = round_capacity(min_capacity);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        Workspace* w = new Workspace();
+        Status s = w->alloc(cap, with_io);
+        if (s.ok) return w;
+        w->release();
+        delete w;
+        cudaGetLastError();   // a failed cudaMalloc must not linger as this thread's "last error" into the next launch check
+        if (attempt == 0 && !trim_pool(0)) break;   // out of memory: give the idle workspaces back to the driver and retry once
+    }
+    return nullptr;
+}
+
+// drops idle workspaces until at most `keep` are left; returns how many were released
+size_t Context::trim_pool(size_t keep) const {
+    std::vector<Workspace*> victims;
+    {
+        std::lock_guard<std::mutex> g(pool_mu_);
+        while (pool_.size() > keep) {   // smallest first: the big ones are the expensive ones to rebuild
+            size_t v = 0;
+            for (size_t i = 1; i < pool_.size(); i++) if (pool_[i]->capacity < pool_[v]->capacity) v = i;
+            victims.push_back(pool_[v]);
+            pool_.erase(pool_.begin() + v);
+        }
+    }
+    for (Workspace* w : victims) { w->release(); delete w; }
+    return victims.size();
 }
 
 void Context::give_back(Workspace* ws) const {
-    std::lock_guard<std::mutex> g(pool_mu_);
-    pool_.push_back(ws);
+    {
+        std::lock_guard<std::mutex> g(pool_mu_);
+        pool_.push_back(ws);
+    }
+    static const size_t max_idle = [] { const char* e = getenv("EKZG_POOL_MAX"); int v = e ? atoi(e) : 8; return (size_t)(v < 1 ? 1 : v); }();
+    trim_pool(max_idle);
+}
+
+// a workspace whose buffers could not be completed (allocation failure) is destroyed, not pooled
+void Context::discard(Workspace* ws) const {
+    ws->release();
+    delete ws;
+    cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -695,6 +764,7 @@ Status Context::recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* c
     if (!wsp) return Status::Error("device/pinned memory allocation failed");
     Workspace& ws = *wsp;
     Status result = ws.ensure_recover_buffers();
+    if (!result.ok) { discard(wsp); return result; }
     cudaStream_t st = ws.stream;
     const bool in_pinned = host_range_is_pinned(cells), cells_pinned = host_range_is_pinned(out_cells), proofs_pinned = host_range_is_pinned(out_proofs);
     constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;

@@ -63,6 +63,7 @@ struct Workspace {
     int16_t* h_slotmap = nullptr;
     Fr* d_ze = nullptr;            // [cap][128]
     Fr* d_czinv = nullptr;
+    bool recover_ready = false;    // all six recovery buffers exist
     Status ensure_recover_buffers();
     // pinned host staging (the ABI hands us scattered caller buffers)
     uint8_t* h_blobs = nullptr;
@@ -75,7 +76,8 @@ struct Workspace {
 
 class Context {
 public:
-    static Status create(bool use_precomp, std::unique_ptr<Context>* out);
+    // device < 0: the calling thread's current device (or EKZG_DEVICE)
+    static Status create(bool use_precomp, std::unique_ptr<Context>* out, int device = -1);
     ~Context();
 
     int device() const { return device_; }
@@ -128,6 +130,8 @@ public:
     // workspace pool (calls are re-entrant: concurrent callers each borrow their own workspaces)
     Workspace* acquire(int min_capacity, bool with_io) const;
     void give_back(Workspace* ws) const;
+    void discard(Workspace* ws) const;             // destroy instead of pooling (its buffers are incomplete)
+    size_t trim_pool(size_t keep) const;           // release idle workspaces beyond `keep`
 
     Status bind_device() const;
 
@@ -166,7 +170,7 @@ private:
     mutable CoalesceQueue co_[3];
     Status coalesce(int which, CoalesceReq& me) const;
     void run_coalesced(int which, std::vector<CoalesceReq*>& batch) const;
-    Status init(bool use_precomp);
+    Status init(bool use_precomp, int device);
     int device_ = 0;
     DevTables T_{};
     std::vector<void*> allocs_;

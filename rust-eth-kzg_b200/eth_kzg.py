@@ -55,6 +55,9 @@ def load_library():
     lib.eth_kzg_b200_context_table_bytes.argtypes = [C.c_void_p]
     lib.eth_kzg_b200_context_device.argtypes = [C.c_void_p]
     lib.eth_kzg_b200_context_window.argtypes = [C.c_void_p]
+    lib.eth_kzg_b200_context_srs_window.argtypes = [C.c_void_p]
+    lib.eth_kzg_b200_context_device_count.argtypes = [C.c_void_p]
+    lib.eth_kzg_b200_context_device_at.argtypes = [C.c_void_p, C.c_int]
     for name in ("eth_kzg_blob_to_kzg_commitment", "eth_kzg_compute_cells_and_kzg_proofs", "eth_kzg_compute_cells",
                  "eth_kzg_verify_cell_kzg_proof_batch", "eth_kzg_recover_cells_and_proofs", "eth_kzg_compute_kzg_proof",
                  "eth_kzg_compute_blob_kzg_proof", "eth_kzg_verify_kzg_proof", "eth_kzg_verify_blob_kzg_proof",
@@ -130,6 +133,16 @@ class DASContext:
     @property
     def table_bytes(self):
         return self._lib.eth_kzg_b200_context_table_bytes(self._ctx)
+
+    @property
+    def srs_window(self):
+        return self._lib.eth_kzg_b200_context_srs_window(self._ctx)
+
+    @property
+    def devices(self):
+        """CUDA ordinals this context spans (EKZG_DEVICES; one entry unless that is set)"""
+        n = self._lib.eth_kzg_b200_context_device_count(self._ctx)
+        return [self._lib.eth_kzg_b200_context_device_at(self._ctx, i) for i in range(n)]
 
     # ---- EIP-7594 prover (crates/eip7594/src/prover.rs:100-171) ------------------------------
     def blob_to_kzg_commitment(self, blob):

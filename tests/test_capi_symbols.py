@@ -81,3 +81,25 @@ def test_c_consumer_on_gpu(lib, pkg):
     exe = _build_consumer(pkg)
     r = subprocess.run([exe, "gpu"], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "gpu path ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_device_shard_bounds(lib):
+    """csrc/kzg_multi.cu: the shards of a multi-device batch cover every item once, in order, in whole 32-item groups"""
+    f = lib.eth_kzg_b200_debug_shard_bounds
+    f.argtypes = [ctypes.c_uint64] * 3 + [ctypes.POINTER(ctypes.c_uint64)] * 2
+    f.restype = None
+    for n in (0, 1, 31, 32, 33, 100, 128, 1000, 1024, 4097):
+        for parts in (1, 2, 3, 4, 8):
+            spans = []
+            for i in range(parts):
+                lo, cnt = ctypes.c_uint64(), ctypes.c_uint64()
+                f(n, parts, i, ctypes.byref(lo), ctypes.byref(cnt))
+                spans.append((lo.value, cnt.value))
+            assert spans[0][0] == 0 and sum(c for _, c in spans) == n
+            for (lo, c), (lo2, _) in zip(spans, spans[1:]):
+                assert lo + c == lo2
+            for lo, c in spans[:-1]:
+                assert lo % 32 == 0
+            full = [c for _, c in spans if c and c % 32 == 0]
+            if full:
+                assert max(full) - min(full) <= 32
