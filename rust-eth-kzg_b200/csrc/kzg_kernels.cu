@@ -1100,7 +1100,10 @@ static int ntt_min_blocks() {
     return v;
 }
 static bool k5_register_form() {
-    static const bool v = [] { const char* e = getenv("EKZG_K5"); return e && e[0] == 'r'; }();
+    // measured on the B200 (profiles/r2_a_*): the shared-memory-operand K5 runs 43.6 ms against 34.7 ms for the register form at
+    // 1024 blobs -- a phase holds only 2048 warp-sized units, fewer than the 2368 warps that form keeps resident, so every unit
+    // of a phase runs at once at a quarter of a scheduler's pipe and the 12 dependent ladder phases stretch.  EKZG_K5=vm selects it.
+    static const bool v = [] { const char* e = getenv("EKZG_K5"); return !(e && e[0] == 'v'); }();
     return v;
 }
 static cudaError_t ntt_query_sms() {
