@@ -150,6 +150,9 @@ uint64_t eth_kzg_b200_context_table_bytes(const DASContext *ctx);
 int eth_kzg_b200_context_srs_window(const DASContext *ctx);
 int eth_kzg_b200_context_device_count(const DASContext *ctx);
 int eth_kzg_b200_context_device_at(const DASContext *ctx, int i);
+/* Measured issue rate (multiply-adds per second) of carry-chained IMAD.WIDE.U32 on the context's first device: the
+ * roofline denominator of the point-arithmetic kernels, measured in-process (about 30 ms).  0 on error. */
+double eth_kzg_b200_probe_imad_wide(const DASContext *ctx);
 /* how a batch of n items is cut over `parts` devices: device i works on items [*lo, *lo + *cnt) -- whole groups of 32
  * (one G1-NTT work unit is 32 blobs wide), sizes differing by at most one group.  Host-only helper. */
 void eth_kzg_b200_debug_shard_bounds(uint64_t n, uint64_t parts, uint64_t i, uint64_t *lo, uint64_t *cnt);

@@ -59,6 +59,15 @@ def compute_cells_and_kzg_proofs(blob):
     return ([cells.raw[i * 2048:(i + 1) * 2048] for i in range(CELLS)], [proofs.raw[i * 48:(i + 1) * 48] for i in range(CELLS)])
 
 
+def time_fp_mul(n=2000000):
+    """nanoseconds per Fp Montgomery multiplication of this port on one core (dependent chain of n)"""
+    f = lib().okzg_time_fp_mul
+    f.restype = C.c_double
+    sink = C.create_string_buffer(48)
+    f(20000, sink)
+    return float(f(int(n), sink))
+
+
 def compute_cells(blob):
     _len(blob, BYTES_PER_BLOB, "blob")
     cells = C.create_string_buffer(CELLS * BYTES_PER_CELL)

@@ -16,6 +16,7 @@
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <time.h>
 #include "pairing.h"
 #include "sha256.h"
 #ifdef _OPENMP
@@ -717,6 +718,20 @@ done:
 }
 
 /* ------------------------------------------------------------------ primitive hooks for tests */
+/* n dependent Fp Montgomery multiplications on one core; returns nanoseconds per multiplication (bench.py prints it
+ * beside the CPU baseline so that this port's distance from blst's hand-written assembly is a number, not a guess) */
+double okzg_time_fp_mul(int n, uint8_t sink[48]) {
+    fp_t x, y;
+    memcpy(x.l, FP_R2, 48);
+    memcpy(y.l, FP_R2, 48);
+    y.l[0] ^= 0x9e3779b97f4a7c15ull; y.l[5] &= 0x0fffffffffffffffull;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int i = 0; i < n; i++) fp_mul(&x, &x, &y);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    fp_to_be(sink, &x);
+    return ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / n;
+}
 void okzg_test_fp_mul(const uint8_t a[48], const uint8_t b[48], uint8_t out[48]) {
     fp_t x, y, z; fp_from_be(&x, a); fp_from_be(&y, b); fp_mul(&z, &x, &y); fp_to_be(out, &z);
 }

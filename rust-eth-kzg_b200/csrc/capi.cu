@@ -9,6 +9,7 @@
 #include "host_pairing.h"
 
 using ekzg::Status;
+namespace ekzg { double probe_imad_wide_per_s(int reps); }   // kzg_probe.cu
 
 struct DASContext {
     std::unique_ptr<ekzg::DeviceSet> set;   // one ekzg::Context per device of EKZG_DEVICES (default: the current device)
@@ -68,24 +69,13 @@ uint64_t eth_kzg_constant_bytes_per_proof(void) { return ekzg::BYTES_PER_G1; }
 uint64_t eth_kzg_constant_cells_per_ext_blob(void) { return ekzg::N_CELLS; }
 
 CResult eth_kzg_compute_cells_and_kzg_proofs(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells, uint8_t** out_proofs) {
-    std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32), proofs((size_t)ekzg::N_CELLS * 48);
-    DeviceGuard guard;
-    Status s = next_cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), proofs.data());
-    if (!s.ok) return c_err(s.msg);
-    for (int i = 0; i < ekzg::N_CELLS; i++) {  // pointer_utils.rs:53-62 write_to_2d_slice
-        memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
-        memcpy(out_proofs[i], proofs.data() + (size_t)i * 48, 48);
-    }
-    return c_ok();
+    DeviceGuard guard;   // results go through the 128 + 128 pointers on the caller's own thread (pointer_utils.rs:53-62 write_to_2d_slice)
+    return to_c(next_cx(ctx).compute_cells_and_kzg_proofs_one(blob, nullptr, nullptr, out_cells, out_proofs, true));
 }
 
 CResult eth_kzg_compute_cells(const DASContext* ctx, const uint8_t* blob, uint8_t** out_cells) {
-    std::vector<uint8_t> cells((size_t)ekzg::N_EXT * 32);
     DeviceGuard guard;
-    Status s = next_cx(ctx).compute_cells_and_kzg_proofs_one(blob, cells.data(), nullptr);
-    if (!s.ok) return c_err(s.msg);
-    for (int i = 0; i < ekzg::N_CELLS; i++) memcpy(out_cells[i], cells.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
-    return c_ok();
+    return to_c(next_cx(ctx).compute_cells_and_kzg_proofs_one(blob, nullptr, nullptr, out_cells, nullptr, false));
 }
 
 CResult eth_kzg_b200_compute_cells_and_kzg_proofs_batch(const DASContext* ctx, uint64_t n, const uint8_t* blobs, uint8_t* out_cells,
@@ -125,6 +115,14 @@ uint64_t eth_kzg_b200_context_table_bytes(const DASContext* ctx) { return cx(ctx
 int eth_kzg_b200_context_device_count(const DASContext* ctx) { return (int)ds(ctx).size(); }
 int eth_kzg_b200_context_device_at(const DASContext* ctx, int i) { return i >= 0 && (size_t)i < ds(ctx).size() ? ds(ctx).at(i).device() : -1; }
 uint64_t eth_kzg_b200_kernel_launch_count(void) { return ekzg::g_kernel_launches.load(); }
+
+// Measured issue rate of carry-chained IMAD.WIDE on the context's first device, in multiply-adds per second
+// (the roofline denominator of the point-arithmetic kernels; ~30 ms).  0 on error.
+double eth_kzg_b200_probe_imad_wide(const DASContext* ctx) {
+    DeviceGuard guard;
+    if (!cx(ctx).bind_device().ok) return 0;
+    return ekzg::probe_imad_wide_per_s(3);
+}
 
 // Test hook (host only): the contiguous shard [lo, lo + cnt) that device i of `parts` gets from a batch of n items
 void eth_kzg_b200_debug_shard_bounds(uint64_t n, uint64_t parts, uint64_t i, uint64_t* lo, uint64_t* cnt) {
@@ -219,15 +217,8 @@ CResult eth_kzg_recover_cells_and_proofs(const DASContext* ctx, uint64_t cells_l
     if (cells_length > 4096) return c_err("Recovery(TooManyCellsReceived)");
     std::vector<uint8_t> flat((size_t)cells_length * ekzg::BYTES_PER_CELL);
     for (uint64_t i = 0; i < cells_length; i++) memcpy(flat.data() + i * ekzg::BYTES_PER_CELL, cells[i], ekzg::BYTES_PER_CELL);
-    std::vector<uint8_t> oc((size_t)ekzg::N_EXT * 32), op((size_t)ekzg::N_CELLS * 48);
     uint64_t cnt = cells_length;
-    Status s = c.recover_cells_and_kzg_proofs_one(cnt, cell_indices, flat.data(), oc.data(), op.data());
-    if (!s.ok) return c_err(s.msg);
-    for (int i = 0; i < ekzg::N_CELLS; i++) {
-        memcpy(out_cells[i], oc.data() + (size_t)i * ekzg::BYTES_PER_CELL, ekzg::BYTES_PER_CELL);
-        memcpy(out_proofs[i], op.data() + (size_t)i * 48, 48);
-    }
-    return c_ok();
+    return to_c(c.recover_cells_and_kzg_proofs_one(cnt, cell_indices, flat.data(), nullptr, nullptr, out_cells, out_proofs));
 }
 CResult eth_kzg_b200_recover_cells_and_kzg_proofs_batch(const DASContext* ctx, uint64_t n, const uint64_t* cell_counts, const uint64_t* cell_indices,
                                                         const uint8_t* cells, uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) {

@@ -59,17 +59,19 @@ EKZG_HD int32_t divsteps_30(int32_t zeta, uint32_t f, uint32_t g, Mat& t) {
     return zeta;
 }
 
+// 32 x 32 -> 64 signed product (one IMAD.WIDE on the device; written so that the compiler sees two 32-bit operands)
+EKZG_HD int64_t mul32(int32_t a, int32_t b) { return (int64_t)a * (int64_t)b; }
+
 // (f, g) <- t * (f, g) / 2^30   (exact)
 EKZG_HD void update_fg(S30& f, S30& g, const Mat& t) {
-    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
-    int64_t cf = u * f.v[0] + v * g.v[0];
-    int64_t cg = q * f.v[0] + r * g.v[0];
+    int64_t cf = mul32(t.u, f.v[0]) + mul32(t.v, g.v[0]);
+    int64_t cg = mul32(t.q, f.v[0]) + mul32(t.r, g.v[0]);
     cf >>= 30; cg >>= 30;
 #pragma unroll
     for (int i = 1; i < L; i++) {
-        const int64_t fi = f.v[i], gi = g.v[i];
-        cf += u * fi + v * gi;
-        cg += q * fi + r * gi;
+        const int32_t fi = f.v[i], gi = g.v[i];
+        cf += mul32(t.u, fi) + mul32(t.v, gi);
+        cg += mul32(t.q, fi) + mul32(t.r, gi);
         f.v[i - 1] = (int32_t)cf & M30; cf >>= 30;
         g.v[i - 1] = (int32_t)cg & M30; cg >>= 30;
     }
@@ -79,22 +81,21 @@ EKZG_HD void update_fg(S30& f, S30& g, const Mat& t) {
 
 // (d, e) <- t * (d, e) / 2^30 mod p, both kept in (-2p, p)
 EKZG_HD void update_de(S30& d, S30& e, const Mat& t) {
-    const int64_t u = t.u, v = t.v, q = t.q, r = t.r;
     const int32_t sd = d.v[L - 1] >> 31, se = e.v[L - 1] >> 31;
     int32_t md = (t.u & sd) + (t.v & se);
     int32_t me = (t.q & sd) + (t.r & se);
-    int64_t cd = u * d.v[0] + v * e.v[0];
-    int64_t ce = q * d.v[0] + r * e.v[0];
+    int64_t cd = mul32(t.u, d.v[0]) + mul32(t.v, e.v[0]);
+    int64_t ce = mul32(t.q, d.v[0]) + mul32(t.r, e.v[0]);
     md -= (int32_t)((P_INV30 * (uint32_t)cd + (uint32_t)md) & (uint32_t)M30);   // makes the low 30 bits of cd + p*md vanish
     me -= (int32_t)((P_INV30 * (uint32_t)ce + (uint32_t)me) & (uint32_t)M30);
-    cd += (int64_t)p30(0) * md;
-    ce += (int64_t)p30(0) * me;
+    cd += mul32(p30(0), md);
+    ce += mul32(p30(0), me);
     cd >>= 30; ce >>= 30;
 #pragma unroll
     for (int i = 1; i < L; i++) {
-        const int64_t di = d.v[i], ei = e.v[i];
-        cd += u * di + v * ei + (int64_t)p30(i) * md;
-        ce += q * di + r * ei + (int64_t)p30(i) * me;
+        const int32_t di = d.v[i], ei = e.v[i];
+        cd += mul32(t.u, di) + mul32(t.v, ei) + mul32(p30(i), md);
+        ce += mul32(t.q, di) + mul32(t.r, ei) + mul32(p30(i), me);
         d.v[i - 1] = (int32_t)cd & M30; cd >>= 30;
         e.v[i - 1] = (int32_t)ce & M30; ce >>= 30;
     }

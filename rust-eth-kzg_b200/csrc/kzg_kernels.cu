@@ -12,6 +12,7 @@
 #include "kzg_kernels.h"
 #include "fr_ntt.cuh"
 #include "fpvm.cuh"
+#include "fp_inv_gcd.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -409,6 +410,333 @@ k_fk20_msm_vm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, Msm
             r.x = M.ld(0); r.y = M.ld(1); r.z = M.ld(2);
         }
         st_vec(&pts[(size_t)rev_bits(j, 7) * B + b], r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4a  the fixed-base MSMs with BATCHED AFFINE additions (opt-in: EKZG_K4=a)
+//   reference: the same FixedBaseMSMPrecompWindow::msm, which also adds in affine coordinates and shares inversions
+//   (batch_addition.rs:142-232 multi_batch_addition_binary_tree_stride, batch_inversion.rs) -- there across a tree of
+//   points, here across the WINDOWS of one scalar:
+//     a thread owns one accumulator PER WINDOW (affine, in a per-thread scratch block in global memory / L2).  Round k
+//     adds, for every window t, the table entry picked by digit t of scalar k to accumulator t: ~19 independent
+//     additions whose denominators x_e - x_acc are inverted together (Montgomery's trick: one product chain forward,
+//     ONE inversion by division steps -- fp_inv_gcd.cuh, mostly ALU work -- one chain backward).  An addition then costs
+//     5M + 1S + 1/19 inversion (~2000 wide multiply-adds) instead of the 8M + 2S = 2712 of an XYZZ mixed addition.
+//     After the last round the window accumulators are summed (XYZZ, 18 additions per thread) and the slices of one
+//     (MSM, blob) combined through shared memory as in k_fk20_msm.
+//   Equal-x cases stay complete: accumulator == entry puts 2y / 3x^2 into the same batch (affine doubling),
+//   accumulator == -entry empties the accumulator, digit 0 and empty accumulators take no part in the product chain.
+//   Scratch: [CTA slot][window][x0 x1 x2 y0 y1 y2][thread] and [CTA slot][batch slot][p0 p1 p2][thread] in 16-byte
+//   granules, so a warp's access to one granule is 512 contiguous bytes.
+// ------------------------------------------------------------------------------------------------
+constexpr int K4A_HALF = 16;               // additions of one half-batch (slots that share one inversion per thread)
+constexpr int K4A_THREADS = 128;           // worker threads of a CTA (its fifth warp only inverts)
+constexpr int K4A_CTA = K4A_THREADS + 32;
+
+struct K4aScratch {
+    uint4* acc;     // this thread's granule 0 of window 0
+    uint4* pre;     // this thread's granule 0 of batch slot 0
+    __device__ __forceinline__ Fp ld(const uint4* p) const {
+        Fp r;
+        uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < 3; q++) d[q] = __ldcg(p + q * K4A_THREADS);
+        return r;
+    }
+    __device__ __forceinline__ void st(uint4* p, const Fp& v) const {
+        const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+        for (int q = 0; q < 3; q++) __stcg(p + q * K4A_THREADS, s[q]);
+    }
+    __device__ __forceinline__ void prefetch(const uint4* p) const {   // one element (three granules) towards L2
+#pragma unroll
+        for (int q = 0; q < 3; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + q * K4A_THREADS));
+    }
+    __device__ __forceinline__ uint4* ax(int t) const { return acc + (size_t)t * 6 * K4A_THREADS; }
+    __device__ __forceinline__ uint4* ay(int t) const { return acc + ((size_t)t * 6 + 3) * K4A_THREADS; }
+    __device__ __forceinline__ uint4* pr(int t) const { return pre + (size_t)t * 3 * K4A_THREADS; }
+};
+
+enum : uint32_t { K4A_SKIP = 0, K4A_INIT = 1, K4A_ADD = 2, K4A_DBL = 3, K4A_CANCEL = 4 };
+
+static __device__ __noinline__ Fp k4a_inverse(Fp a) {
+    Fp r;
+    fp_inv_gcd(r, a);
+    return r;
+}
+
+// shared-memory exchange of the per-thread denominator products: element of thread i as three 16-byte granules at
+// [q][i], so a warp's access is conflict-free
+struct K4aXchg {
+    uint4* base;   // granule 0 of thread 0
+    __device__ __forceinline__ Fp ld(int thread) const {
+        Fp r;
+        uint4* d = reinterpret_cast<uint4*>(&r);
+#pragma unroll
+        for (int q = 0; q < 3; q++) d[q] = base[q * K4A_THREADS + thread];
+        return r;
+    }
+    __device__ __forceinline__ void st(int thread, const Fp& v) const {
+        const uint4* s = reinterpret_cast<const uint4*>(&v);
+#pragma unroll
+        for (int q = 0; q < 3; q++) base[q * K4A_THREADS + thread] = s[q];
+    }
+};
+
+// named barriers (0 is __syncthreads): products of half h posted / inverses of half h ready / workers only
+__device__ __forceinline__ void k4a_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void k4a_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+enum { K4A_BAR_POSTED = 1, K4A_BAR_READY = 3, K4A_BAR_WORKERS = 5 };
+
+// forward pass over the slots [lo, hi) of one half-batch: classify, chain the denominators; returns the chain product
+__device__ __forceinline__ Fp k4a_forward(const K4aScratch& S, uint32_t (*info_rows)[K4A_THREADS], int lo, int hi, int nreg, const G1Affine* tb,
+                                          const G1Affine* tg, uint64_t has) {
+    Fp run;
+    bool run_set = false;
+    if (lo < hi) S.prefetch(S.ax(lo));
+    for (int t = lo; t < hi; t++) {
+        const uint32_t info = info_rows[t - lo][threadIdx.x];
+        if (t + 1 < hi) S.prefetch(S.ax(t + 1));
+        if ((info & 7u) == K4A_SKIP) continue;
+        const G1Affine* ep = (t < nreg ? tb : tg) + (info >> 4);
+        const bool neg = (info & 8u) != 0;
+        const Fp ex = ld_vec(&ep->x);
+        bool e_inf = false;
+        if (fe_is_zero(ex)) { const Fp ey = ld_vec(&ep->y); e_inf = fe_is_zero(ey); }
+        uint32_t mode = K4A_ADD;
+        if (e_inf) {
+            mode = K4A_SKIP;
+        } else if (!((has >> t) & 1ull)) {
+            mode = K4A_INIT;
+        } else {
+            Fp den;
+            const Fp ax = S.ld(S.ax(t));
+            fe_sub(den, ex, ax);
+            if (fe_is_zero(den)) {           // same x: the same point (double it) or its negative (cancel)
+                Fp ey = ld_vec(&ep->y);
+                fe_cneg(ey, ey, neg);
+                const Fp ay = S.ld(S.ay(t));
+                if (fe_eq(ey, ay)) { mode = K4A_DBL; fe_dbl(den, ay); } else mode = K4A_CANCEL;
+            }
+            if (mode != K4A_CANCEL) {
+                if (run_set) {
+                    S.st(S.pr(t), run);
+                    fe_mul(run, run, den);
+                } else {
+                    S.st(S.pr(t), fp_one());
+                    run = den;
+                    run_set = true;
+                }
+            }
+        }
+        info_rows[t - lo][threadIdx.x] = (info & ~7u) | mode;
+    }
+    return run_set ? run : fp_one();
+}
+
+// backward pass: peel the slot inverses off `inv` (the inverse of the chain product) and finish the additions
+__device__ __forceinline__ uint64_t k4a_backward(const K4aScratch& S, uint32_t (*info_rows)[K4A_THREADS], int lo, int hi, int nreg, const G1Affine* tb,
+                                                 const G1Affine* tg, uint64_t has, Fp inv) {
+    for (int t = hi - 1; t >= lo; t--) {
+        const uint32_t info = info_rows[t - lo][threadIdx.x];
+        const uint32_t mode = info & 7u;
+        if (t > lo) { S.prefetch(S.pr(t - 1)); S.prefetch(S.ax(t - 1)); S.prefetch(S.ay(t - 1)); }
+        if (mode == K4A_SKIP) continue;
+        if (mode == K4A_CANCEL) { has &= ~(1ull << t); continue; }
+        const G1Affine* ep = (t < nreg ? tb : tg) + (info >> 4);
+        const Fp ex = ld_vec(&ep->x);
+        Fp ey = ld_vec(&ep->y);
+        fe_cneg(ey, ey, (info & 8u) != 0);
+        if (mode == K4A_INIT) {
+            S.st(S.ax(t), ex);
+            S.st(S.ay(t), ey);
+            has |= 1ull << t;
+            continue;
+        }
+        const Fp ax = S.ld(S.ax(t)), ay = S.ld(S.ay(t));
+        Fp den, num, dinv, lam, x3, y3;
+        {
+            const Fp pre = S.ld(S.pr(t));
+            fe_mul(dinv, inv, pre);              // 1 / denominator of this slot
+        }
+        if (mode == K4A_DBL) {
+            fe_dbl(den, ay);
+            fe_sqr(num, ax);
+            fe_dbl(x3, num);
+            fe_add(num, num, x3);                // 3 x^2
+        } else {
+            fe_sub(den, ex, ax);
+            fe_sub(num, ey, ay);
+        }
+        fe_mul(inv, inv, den);                   // inverse of the remaining chain
+        fe_mul(lam, num, dinv);
+        fe_sqr(x3, lam);
+        fe_sub(x3, x3, ax);
+        fe_sub(x3, x3, ex);
+        fe_sub(y3, ax, x3);
+        fe_mul(y3, y3, lam);
+        fe_sub(y3, y3, ay);
+        S.st(S.ax(t), x3);
+        S.st(S.ay(t), y3);
+    }
+    return has;
+}
+
+// Schedule.  The windows of a scalar are split into a low half A and a high half B (the merged top window is in B).  The
+// four worker warps run, per point k:
+//     forward(A_k), post | wait, backward(B_k-1) | forward(B_k), post | wait, backward(A_k)
+// and the fifth warp does nothing but: wait for the 128 posted products of a half, multiply the four of each lane column
+// together, invert (division steps: ALU work, off the multiply pipe the workers saturate), hand the four inverses back.
+// Between posting a product and needing its inverse a worker has ~55 field multiplications of the other half to do, about
+// twice what the inverter needs, so nobody waits; an inversion serves 128 threads x ~10 additions.
+__global__ void __launch_bounds__(K4A_CTA, 3)
+k_fk20_msm_affine(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, MsmTable T, int B, int b0, int b1, int nslice, int nitems_x,
+                  int ngroups, uint4* __restrict__ scratch, size_t scratch_cta_granules) {
+    // slot descriptors of half A, and of half B double-buffered (B of point k is finished after the digits of point k+1 are
+    // taken); the slice reduction at the end of an item reuses the same 24 KB
+    __shared__ __align__(16) uint32_t s_info[3][K4A_HALF][K4A_THREADS];
+    static_assert(sizeof(G1Xyzz) * K4A_THREADS <= sizeof(uint32_t) * 3 * K4A_HALF * K4A_THREADS, "the slice reduction reuses the slot descriptors");
+    uint32_t (*s_info_a)[K4A_THREADS] = s_info[0];
+    G1Xyzz* red = reinterpret_cast<G1Xyzz*>(&s_info[0][0][0]);
+    __shared__ uint4 s_xchg[2][3 * K4A_THREADS];
+    const int w = T.w, nw = T.nw, mg = T.mg;
+    const int nreg = mg > 1 ? nw - 1 : nw;          // windows with a table slice of their own
+    const int nslots = mg > 1 ? nreg + 1 : nreg;    // + the merged top window
+    const int n_a = (nslots + 1) / 2;               // half A = slots [0, n_a), half B = [n_a, nslots)
+    const int blobs_per_cta = K4A_THREADS / nslice, kper = FK20_POINTS / nslice;
+    const int nitems = nitems_x * ngroups;
+    if (threadIdx.x >= K4A_THREADS) {
+        // ---- the inverter warp ----
+        const int lane = threadIdx.x - K4A_THREADS;
+        constexpr int NWARP = K4A_THREADS / 32;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            for (int r = 0; r < 2 * kper; r++) {
+                const int h = r & 1;
+                const K4aXchg X{s_xchg[h]};
+                k4a_bar_sync(K4A_BAR_POSTED + h, K4A_CTA);
+                Fp acc = X.ld(lane);
+                Fp part[NWARP - 1];                  // products of the first 1, 2, .. chains (statically indexed: registers)
+#pragma unroll
+                for (int q = 1; q < NWARP; q++) {
+                    part[q - 1] = acc;
+                    const Fp a = X.ld(q * 32 + lane);
+                    fe_mul(acc, acc, a);
+                }
+                Fp iv = k4a_inverse(acc);
+#pragma unroll
+                for (int q = NWARP - 1; q >= 1; q--) {
+                    const Fp a = X.ld(q * 32 + lane);
+                    Fp mine;
+                    fe_mul(mine, iv, part[q - 1]);   // 1 / chain q
+                    fe_mul(iv, iv, a);
+                    X.st(q * 32 + lane, mine);
+                }
+                X.st(lane, iv);
+                k4a_bar_arrive(K4A_BAR_READY + h, K4A_CTA);
+            }
+        }
+        return;
+    }
+    // ---- the workers ----
+    const int lane_b = threadIdx.x % blobs_per_cta, slice = threadIdx.x / blobs_per_cta;
+    const uint32_t vmask = (2u << w) - 1u;
+    const K4aXchg XA{s_xchg[0]}, XB{s_xchg[1]};
+    K4aScratch S;
+    S.acc = scratch + (size_t)blockIdx.x * scratch_cta_granules + threadIdx.x;
+    S.pre = S.acc + (size_t)nslots * 6 * K4A_THREADS;
+    const size_t point_stride = (size_t)nw * T.half;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int j = item / nitems_x, bx = item - j * nitems_x;
+        const int b = b0 + bx * blobs_per_cta + lane_b;
+        const bool active = b < b1;                  // (inactive threads walk the same loops: the CTA shares its inversions)
+        uint64_t has = 0;                            // bit t: accumulator t holds a point
+        int comb = 0, radix = 1;
+        for (int kk = 0; kk < kper; kk++) {
+            const int k = slice * kper + kk;
+            const G1Affine* tb = T.table + (size_t)(j * FK20_POINTS + k) * point_stride;
+            const G1Affine* tg = tb - (size_t)(mg - 1) * point_stride;   // first point of this point's merge group
+            uint32_t (*info_b)[K4A_THREADS] = s_info[1 + (kk & 1)];
+            {
+                // digits of scalar k -> table offsets of all its windows; the entries start their way in from HBM
+                uint32_t s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                if (active) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)(j * FK20_POINTS + k) * B + b) * 8);
+                    const uint4 s0 = sp[0], s1 = sp[1];
+                    s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
+                }
+                uint32_t prev = 0;                   // bit t*w - 1 of the scalar
+                const bool top_round = mg > 1 && (kk & (mg - 1)) == mg - 1;
+                for (int t = 0; t < nslots; t++) {
+                    const uint32_t v = ((s[0] << 1) | prev) & vmask;
+                    const int d = (int)((v + 1) >> 1) - (int)((v >> w) << w);   // booth_digit, g1_mul.cuh
+                    uint32_t info = K4A_SKIP;        // bits 0..2 mode, bit 3 negate, bits 4.. offset of the entry
+                    if (t < nreg) {
+                        prev = (s[0] >> (w - 1)) & 1u;
+#pragma unroll
+                        for (int i = 0; i < 7; i++) s[i] = __funnelshift_r(s[i], s[i + 1], w);
+                        s[7] >>= w;
+                        if (d != 0) {
+                            const uint32_t off = (uint32_t)t * T.half + (uint32_t)((d < 0 ? -d : d) - 1);
+                            info = K4A_ADD | (d < 0 ? 8u : 0u) | (off << 4);
+                            prefetch_entry_l2(tb + off);
+                        }
+                    } else {                         // merged top window: the digits of mg consecutive points index one entry
+                        comb += d * radix;
+                        radix *= T.rtop;
+                        if (top_round) {
+                            if (comb != 0) {
+                                const uint32_t off = (uint32_t)(nw - 1) * T.half + (uint32_t)(comb - 1);
+                                info = K4A_ADD | (off << 4);
+                                prefetch_entry_l2(tg + off);
+                            }
+                            comb = 0;
+                            radix = 1;
+                        }
+                    }
+                    if (t < n_a) s_info_a[t][threadIdx.x] = info; else info_b[t - n_a][threadIdx.x] = info;
+                }
+            }
+            XA.st(threadIdx.x, k4a_forward(S, s_info_a, 0, n_a, nreg, tb, tg, has));
+            k4a_bar_arrive(K4A_BAR_POSTED + 0, K4A_CTA);
+            if (kk > 0) {                            // finish half B of the previous point
+                k4a_bar_sync(K4A_BAR_READY + 1, K4A_CTA);
+                has = k4a_backward(S, s_info[1 + ((kk - 1) & 1)], n_a, nslots, nreg, tb - point_stride, tg - point_stride, has, XB.ld(threadIdx.x));
+            }
+            XB.st(threadIdx.x, k4a_forward(S, info_b, n_a, nslots, nreg, tb, tg, has));
+            k4a_bar_arrive(K4A_BAR_POSTED + 1, K4A_CTA);
+            k4a_bar_sync(K4A_BAR_READY + 0, K4A_CTA);
+            has = k4a_backward(S, s_info_a, 0, n_a, nreg, tb, tg, has, XA.ld(threadIdx.x));
+        }
+        {
+            const int k = slice * kper + kper - 1;
+            const G1Affine* tb = T.table + (size_t)(j * FK20_POINTS + k) * point_stride;
+            k4a_bar_sync(K4A_BAR_READY + 1, K4A_CTA);
+            has = k4a_backward(S, s_info[1 + ((kper - 1) & 1)], n_a, nslots, nreg, tb, tb - (size_t)(mg - 1) * point_stride, has, XB.ld(threadIdx.x));
+        }
+        // the window accumulators of this thread, then the slices of one (MSM, blob)
+        G1Xyzz acc;
+        xyzz_set_inf(acc);
+        for (int t = 0; t < nslots; t++) {
+            if ((has >> t) & 1ull) {
+                G1Affine e;
+                e.x = S.ld(S.ax(t));
+                e.y = S.ld(S.ay(t));
+                xyzz_madd(acc, e, false);
+            }
+        }
+        if (nslice > 1) k4a_bar_sync(K4A_BAR_WORKERS, K4A_THREADS);   // everybody is done with the slot descriptors `red` overlays
+        for (int step = nslice / 2; step >= 1; step >>= 1) {
+            if (slice >= step && slice < 2 * step) red[threadIdx.x] = acc;
+            k4a_bar_sync(K4A_BAR_WORKERS, K4A_THREADS);
+            if (slice < step) xyzz_add(acc, red[threadIdx.x + step * blobs_per_cta]);
+            k4a_bar_sync(K4A_BAR_WORKERS, K4A_THREADS);
+        }
+        if (active && slice == 0) {
+            G1Jac r;
+            jac_from_xyzz(r, acc);
+            st_vec(&pts[(size_t)rev_bits(j, 7) * B + b], r);
+        }
     }
 }
 
@@ -1032,10 +1360,6 @@ cudaError_t launch_powers(Fr* out, const uint32_t* base_mont, int n, cudaStream_
     return cudaSuccess;
 }
 
-static bool k4_register_form() {
-    static const bool v = [] { const char* e = getenv("EKZG_K4"); return e && e[0] == 'r'; }();
-    return v;
-}
 
 cudaError_t kernels_init() {
     cudaError_t e = cudaFuncSetAttribute(k_blob_to_coeffs_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * N_BLOB * 4);
@@ -1077,13 +1401,66 @@ cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const D
     return cudaSuccess;
 }
 
-cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st, int b0, int cnt) {
+// K4a geometry for a table: granules (16 B) of scratch per resident CTA, and how many CTAs can be resident
+static int g_k4a_ctas = 0;
+static cudaError_t k4a_query() {
+    if (g_k4a_ctas) return cudaSuccess;
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_fk20_msm_affine, K4A_CTA, 0);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    if (const char* env = getenv("EKZG_K4A_OCC")) { const int v = atoi(env); if (v >= 1 && v < per_sm) per_sm = v; }
+    g_k4a_ctas = sms * per_sm;
+    return cudaSuccess;
+}
+static size_t k4a_cta_granules(const MsmTable& T) {
+    const int nreg = T.mg > 1 ? T.nw - 1 : T.nw, nslots = T.mg > 1 ? nreg + 1 : nreg;
+    return (size_t)(nslots * 6 + nslots * 3) * K4A_THREADS;   // accumulators (x, y) and chain prefixes of every window
+}
+size_t fixed_msm_scratch_bytes(const MsmTable& T) {
+    if (k4a_query() != cudaSuccess) return 0;
+    return (size_t)g_k4a_ctas * k4a_cta_granules(T) * 16;
+}
+// 'v' shared-memory-operand XYZZ (default: 50.9 ms per 1024 blobs), 'r' register XYZZ (51.9 ms), 'a' batched affine with
+// the accumulators in a global scratch block (63 ms: latency-bound on the scratch traffic, profiles/r2_e_prof_k4a_*;
+// kept for A/B runs)
+// (the three knobs below are read at every launch, so that a test can switch forms inside one process)
+static char k4_form() {
+    const char* e = getenv("EKZG_K4");
+    return e && (e[0] == 'r' || e[0] == 'a') ? e[0] : 'v';
+}
+static int k4a_slices() {   // slices per (MSM, blob) in the affine kernel: 1 = a thread walks all 64 points
+    const char* e = getenv("EKZG_K4A_SLICES");
+    const int x = e ? atoi(e) : 1;
+    return x == 2 || x == 4 || x == 8 || x == 16 ? x : 1;
+}
+static size_t k4a_min_work() {   // launches with fewer (blob, MSM) pairs use the XYZZ kernels, which slice finer
+    const char* e = getenv("EKZG_K4A_MIN");
+    return e ? (size_t)atoll(e) : (size_t)512 * 128;
+}
+
+cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st, int b0, int cnt,
+                             void* scratch) {
     // ngroups MSMs of 64 points each per blob (FK20: 128; SRS commitment: 64 partial sums), blobs [b0, b0 + cnt) of the
     // batch of B (the strides of scalars[][][B] and pts[][B] are those of the whole batch).
     // fewer blobs per launch -> more slices per MSM so the machine still fills
     if (cnt < 0) cnt = B - b0;
     const bool wide = (size_t)B * ngroups >= 512 * 128;
-    if (k4_register_form()) {
+    const char form = k4_form();
+    const int nslots_a = T.mg > 1 ? T.nw : T.nw;   // (nw - 1 sliced windows + the merged one, or nw sliced windows)
+    if (form == 'a' && scratch && nslots_a <= 2 * K4A_HALF && (size_t)B * ngroups >= k4a_min_work()) {
+        cudaError_t e = k4a_query();
+        if (e != cudaSuccess) return e;
+        const int nslice = k4a_slices(), blobs_per_cta = K4A_THREADS / nslice;
+        const int nitems_x = (cnt + blobs_per_cta - 1) / blobs_per_cta;
+        const int grid = std::min(g_k4a_ctas, nitems_x * ngroups);
+        k_fk20_msm_affine<<<dim3(grid, 1), K4A_CTA, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt, nslice, nitems_x, ngroups,
+                                                                   reinterpret_cast<uint4*>(scratch), k4a_cta_granules(T));
+    } else if (form == 'r') {
         if (wide) k_fk20_msm<4><<<dim3((cnt + 31) / 32, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
         else k_fk20_msm<16><<<dim3((cnt + 7) / 8, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
     } else {

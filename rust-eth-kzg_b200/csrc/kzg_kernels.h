@@ -21,7 +21,10 @@ cudaError_t launch_blob_to_coeffs_cells(const uint8_t* blobs, Fr* coeffs, uint8_
 cudaError_t launch_coeffs_to_cells(const Fr* coeffs, uint8_t* cells, const DevTables& T, int B, cudaStream_t st);
 // blobs [b0, b0 + cnt) of a batch of B (cnt < 0: to the end)
 cudaError_t launch_toeplitz_scalars(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int B, cudaStream_t st, int b0 = 0, int cnt = -1);
-cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st, int b0 = 0, int cnt = -1);
+// scratch: fixed_msm_scratch_bytes(T) bytes for the batched-affine kernel (nullptr: the XYZZ kernels are used)
+cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st, int b0 = 0, int cnt = -1,
+                             void* scratch = nullptr);
+size_t fixed_msm_scratch_bytes(const MsmTable& T);
 size_t g1_ntt_queue_words(int B);
 size_t g1_ntt_scratch_bytes();   // per concurrently running K5 launch (odd-multiples tables of the resident warps); 0 on error
 cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* queue, void* scratch, cudaStream_t st);

@@ -42,7 +42,7 @@ int chunk_capacity() {
 }
 
 // ------------------------------------------------------------------------------------------------
-Status Workspace::alloc(int cap, bool with_io) {
+Status Workspace::alloc(int cap, bool with_io, size_t msm_scratch_bytes) {
     capacity = cap;
     EKZG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     EKZG_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
@@ -59,6 +59,7 @@ Status Workspace::alloc(int cap, bool with_io) {
     EKZG_CUDA(cudaMalloc(&d_pts, (size_t)cap * 128 * sizeof(G1Jac)));
     EKZG_CUDA(cudaMalloc(&d_queue, g1_ntt_queue_words(cap) * sizeof(uint32_t)));
     EKZG_CUDA(cudaMalloc(&d_ntt_scratch, g1_ntt_scratch_bytes()));
+    if (msm_scratch_bytes) EKZG_CUDA(cudaMalloc(&d_msm_scratch, msm_scratch_bytes));
     if (with_io) {
         EKZG_CUDA(cudaMalloc(&d_blobs, (size_t)cap * BYTES_PER_BLOB));
         EKZG_CUDA(cudaMalloc(&d_cells, (size_t)cap * N_EXT * 32));
@@ -103,7 +104,7 @@ Status Workspace::ensure_recover_buffers() {
 void Workspace::release() {
     cudaFree(d_rcells); cudaFreeHost(h_rcells); cudaFree(d_slotmap); cudaFreeHost(h_slotmap); cudaFree(d_ze); cudaFree(d_czinv);
     cudaFree(d_c48); cudaFree(d_z32); cudaFree(d_out48); cudaFree(d_z); cudaFree(d_aff); cudaFree(d_status2);
-    cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_queue); cudaFree(d_ntt_scratch); cudaFree(d_proofs); cudaFree(d_status);
+    cudaFree(d_blobs); cudaFree(d_coeffs); cudaFree(d_cells); cudaFree(d_scalars); cudaFree(d_pts); cudaFree(d_queue); cudaFree(d_ntt_scratch); cudaFree(d_msm_scratch); cudaFree(d_proofs); cudaFree(d_status);
     cudaFreeHost(h_blobs); cudaFreeHost(h_cells); cudaFreeHost(h_proofs); cudaFreeHost(h_status);
     if (done) cudaEventDestroy(done);
     for (int i = 0; i < MAX_SUB; i++) {
@@ -134,6 +135,7 @@ Status Context::create(bool use_precomp, std::unique_ptr<Context>* out, int devi
 Context::~Context() {
     cudaSetDevice(device_);
     for (Workspace* w : pool_) { w->release(); delete w; }
+    for (auto& q : co_) for (CoalesceStaging* st : q.free_staging) { st->release(); delete st; }
     for (void* p : allocs_) cudaFree(p);
 }
 
@@ -206,6 +208,7 @@ Status Context::init(bool use_precomp, int device) {
     }
     if (ws < 4 || ws > 16) return Status::Error("EKZG_SRS_WINDOW must be in [4, 16]");
     T_.srs.set_window(ws);
+    msm_scratch_bytes_ = std::max(fixed_msm_scratch_bytes(T_.fk20), fixed_msm_scratch_bytes(T_.srs));
 
     cudaStream_t st = 0;
     // twiddles
@@ -323,7 +326,7 @@ Workspace* Context::acquire(int min_capacity, bool with_io) const {
     const int cap = round_capacity(min_capacity);
     for (int attempt = 0; attempt < 2; attempt++) {
         Workspace* w = new Workspace();
-        Status s = w->alloc(cap, with_io);
+        Status s = w->alloc(cap, with_io, msm_scratch_bytes_);
         if (s.ok) return w;
         w->release();
         delete w;
@@ -393,7 +396,7 @@ Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells
                                         std::vector<cudaEvent_t>* ev) const {
     EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, n, stream));
     if (ev) cudaEventRecord((*ev)[2], stream);
-    EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, n, stream));
+    EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, n, stream, 0, -1, ws.d_msm_scratch));
     if (ev) cudaEventRecord((*ev)[3], stream);
     EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, n, ws.d_queue, ws.d_ntt_scratch, stream));
     if (ev) cudaEventRecord((*ev)[4], stream);
@@ -556,7 +559,7 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
             }
             if (want_proofs) {
                 EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, cnt, ws.stream, o, c));
-                EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, cnt, ws.stream, o, c));
+                EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, cnt, ws.stream, o, c, ws.d_msm_scratch));
                 stamp("K4 done, piece", s, ws.stream);
             }
         }
@@ -606,100 +609,175 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
 
 // ------------------------------------------------------------------------------------------------
 // Single-item entry points with coalescing of concurrent callers (see kzg_runtime.h).
-void Context::run_coalesced(int which, std::vector<CoalesceReq*>& batch) const {
-    const size_t n = batch.size();
-    constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
-    const bool want_proofs = which != CQ_CELLS;
-    if (n == 1) {   // nobody to share with: straight into the caller's buffers, the batch call's own error text
-        CoalesceReq& r = *batch[0];
-        r.st = which == CQ_RECOVER ? recover_cells_and_kzg_proofs_batch(1, &r.count, r.indices, r.in, r.cells, r.proofs, nullptr)
-                                   : compute_cells_and_kzg_proofs_batch(1, r.in, r.cells, want_proofs ? r.proofs : nullptr, nullptr, want_proofs);
-        return;
-    }
-    std::vector<uint8_t> cells(n * CELLS_PER_BLOB), proofs(want_proofs ? n * PROOFS_PER_BLOB : 0), status(n, 0);
-    Status s = Status::Ok();
-    if (which == CQ_RECOVER) {
-        std::vector<uint64_t> counts(n), idx;
-        size_t total = 0;
-        for (size_t i = 0; i < n; i++) { counts[i] = batch[i]->count; total += batch[i]->count; }
-        std::vector<uint8_t> in(total * BYTES_PER_CELL);
-        idx.reserve(total);
-        size_t o = 0;
-        for (size_t i = 0; i < n; i++) {
-            memcpy(&in[o * BYTES_PER_CELL], batch[i]->in, (size_t)batch[i]->count * BYTES_PER_CELL);
-            idx.insert(idx.end(), batch[i]->indices, batch[i]->indices + batch[i]->count);
-            o += batch[i]->count;
-        }
-        s = recover_cells_and_kzg_proofs_batch(n, counts.data(), idx.data(), in.data(), cells.data(), proofs.data(), status.data());
-    } else {
-        std::vector<uint8_t> in(n * BYTES_PER_BLOB);
-        for (size_t i = 0; i < n; i++) memcpy(&in[i * BYTES_PER_BLOB], batch[i]->in, BYTES_PER_BLOB);
-        s = compute_cells_and_kzg_proofs_batch(n, in.data(), cells.data(), want_proofs ? proofs.data() : nullptr, status.data(), want_proofs);
-    }
-    bool any_flag = false;
-    for (uint8_t f : status) any_flag |= f != 0;
-    for (size_t i = 0; i < n; i++) {
-        CoalesceReq& r = *batch[i];
-        if (!s.ok && !any_flag) {   // the batch as a whole failed (CUDA error, allocation)
-            r.st = s;
-        } else if (status[i]) {     // this item is the invalid one; the others are served
-            r.st = which != CQ_RECOVER ? Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus")
-                 : status[i] == 1 ? Status::Error("Serialization(ScalarNotCanonical): a cell field element is >= the scalar modulus")
-                 : status[i] == 4 ? Status::Error("ReedSolomon(PolynomialHasInvalidLength): recovered polynomial has degree >= 4096")
-                                  : Status::Error("Recovery: invalid cell indices");
-        } else {
-            memcpy(r.cells, &cells[i * CELLS_PER_BLOB], CELLS_PER_BLOB);
-            if (want_proofs) memcpy(r.proofs, &proofs[i * PROOFS_PER_BLOB], PROOFS_PER_BLOB);
-            r.st = Status::Ok();
-        }
-    }
+//
+// A batch is formed in a pinned staging block.  Every caller copies its own input into its slot of the block and, when the
+// batch has run, copies its own results out to wherever its binding wants them (128 + 128 scattered pointers through the C
+// ABI) -- so the host copies of a batch of n callers run on n threads, and the device DMAs straight from / into the block.
+// The first caller of a batch is its leader: it lingers until nobody has joined for a moment (or, when two batches are
+// already on the device, until one of them finishes -- more callers per batch cost nothing then), closes the batch, runs
+// it through the batch entry point and wakes the members.  Callers arriving after the close start the next batch at once,
+// so its staging overlaps the kernels of the batches in flight.
+static int coalesce_capacity() {
+    static const int v = [] {
+        const char* e = getenv("EKZG_COALESCE_MAX");
+        int c = e ? atoi(e) : 512;
+        return c < 1 ? 1 : (c > 4096 ? 4096 : c);
+    }();
+    return std::min(v, chunk_capacity());
+}
+
+Status Context::CoalesceStaging::alloc(int cap, size_t in_bytes_per_item, bool with_proofs, bool with_index) {
+    capacity = cap;
+    in_stride = in_bytes_per_item;
+    EKZG_CUDA(cudaMallocHost(&in, (size_t)cap * in_stride));
+    EKZG_CUDA(cudaMallocHost(&cells, (size_t)cap * N_EXT * 32));
+    if (with_proofs) EKZG_CUDA(cudaMallocHost(&proofs, (size_t)cap * N_CELLS * BYTES_PER_G1));
+    status.assign(cap, 0);
+    if (with_index) { counts.assign(cap, 0); indices.assign((size_t)cap * N_CELLS, 0); }
+    return Status::Ok();
+}
+void Context::CoalesceStaging::release() {
+    cudaFreeHost(in); cudaFreeHost(cells); cudaFreeHost(proofs);
+    in = cells = proofs = nullptr;
+}
+
+static Status item_error(int which_recover, uint8_t code) {
+    if (!which_recover) return Status::Error("Serialization(ScalarNotCanonical): a blob field element is >= the BLS12-381 scalar modulus");
+    if (code == 1) return Status::Error("Serialization(ScalarNotCanonical): a cell field element is >= the scalar modulus");
+    if (code == 4) return Status::Error("ReedSolomon(PolynomialHasInvalidLength): recovered polynomial has degree >= 4096");
+    return Status::Error("Recovery: invalid cell indices");
 }
 
 Status Context::coalesce(int which, CoalesceReq& me) const {
     CoalesceQueue& Q = co_[which];
-    const size_t cap = (size_t)chunk_capacity();
-    // A batch takes >= 20 ms whatever its size (14 dependent G1-NTT phases), so the leader first lingers: callers released
-    // together by the previous batch re-enter within microseconds of each other, and without the pause the first of them would
-    // run a batch of one while the other 63 wait for it.  It goes as soon as nobody has joined for linger_us (default 300).
+    constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
+    const bool recover = which == CQ_RECOVER, want_proofs = which != CQ_CELLS;
+    const int cap = coalesce_capacity();
     static const int linger_us = [] { const char* e = getenv("EKZG_COALESCE_LINGER_US"); return e ? atoi(e) : 300; }();
+    constexpr int MAX_IN_FLIGHT = 2, MAX_STAGING = 4;
     std::unique_lock<std::mutex> lk(Q.mu);
-    Q.q.push_back(&me);
-    Q.cv_leader.notify_one();
-    while (!me.done) {
-        if (Q.leader) {
-            Q.cv.wait(lk);
+    // ---- join the batch being formed, or start one ----
+    CoalesceBatch* Bt = nullptr;
+    bool leader = false;
+    for (;;) {
+        Bt = Q.forming;
+        if (Bt && !Bt->closed && Bt->n < Bt->st->capacity) break;
+        // start a batch: needs a staging block
+        CoalesceStaging* st = nullptr;
+        if (!Q.free_staging.empty()) {
+            st = Q.free_staging.back();
+            Q.free_staging.pop_back();
+        } else if (Q.n_staging < MAX_STAGING) {
+            Q.n_staging++;
+            lk.unlock();
+            st = new CoalesceStaging();
+            Status s = bind_device();
+            if (s.ok) s = st->alloc(cap, recover ? (size_t)N_CELLS * BYTES_PER_CELL : (size_t)BYTES_PER_BLOB, want_proofs, recover);
+            lk.lock();
+            if (!s.ok) {
+                st->release();
+                delete st;
+                cudaGetLastError();
+                Q.n_staging--;
+                return s;
+            }
+        } else {
+            Q.cv.wait(lk);          // all blocks are busy: one comes back when its last member has copied out
             continue;
         }
-        Q.leader = true;   // lead batches until my own request has been served (FIFO: normally the first one)
-        while (!me.done) {
-            if (linger_us > 0) {   // until nobody has joined for linger_us, at most 8 x linger_us in all
-                const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(8 * linger_us);
-                while (Q.q.size() < cap) {
-                    const auto gap_end = std::min(t_end, std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us));
-                    const size_t before = Q.q.size();
-                    while (Q.q.size() == before && Q.cv_leader.wait_until(lk, gap_end) != std::cv_status::timeout) {}
-                    if (Q.q.size() == before || std::chrono::steady_clock::now() >= t_end) break;
-                }
-            }
-            std::vector<CoalesceReq*> batch;
-            while (!Q.q.empty() && batch.size() < cap) {
-                batch.push_back(Q.q.front());
-                Q.q.pop_front();
-            }
-            lk.unlock();
-            try {
-                run_coalesced(which, batch);
-            } catch (const std::exception& ex) {   // e.g. bad_alloc of the staging vectors: fail the batch, never the queue
-                for (CoalesceReq* r : batch) r->st = Status::Error(std::string("batch failed: ") + ex.what());
-            }
-            lk.lock();
-            for (CoalesceReq* r : batch) r->done = true;
-            Q.cv.notify_all();
+        if (Q.forming && !Q.forming->closed && Q.forming->n < Q.forming->st->capacity) {   // somebody else started one meanwhile
+            Q.free_staging.push_back(st);
+            continue;
         }
-        Q.leader = false;
-        Q.cv.notify_all();       // somebody still queued takes over
+        Bt = new CoalesceBatch();
+        Bt->st = st;
+        Q.forming = Bt;
+        leader = true;
+        break;
     }
-    return me.st;
+    const int slot = Bt->n++;
+    Bt->left++;
+    size_t cell_off = 0;
+    if (recover) { cell_off = Bt->cells_total; Bt->cells_total += me.count; }
+    CoalesceStaging& st = *Bt->st;
+    lk.unlock();
+    // ---- copy my input into my slot (all members do this at the same time) ----
+    if (recover) {
+        st.counts[slot] = me.count;
+        // the batch entry point takes the cells of all items concatenated; a slot is 128 cells wide, so items are packed later by
+        // the leader's index list only -- the cell bytes stay where they are and the batch call gets per-item offsets via counts
+        memcpy(st.in + (size_t)slot * st.in_stride, me.in, (size_t)me.count * BYTES_PER_CELL);
+        memcpy(&st.indices[(size_t)slot * N_CELLS], me.indices, (size_t)me.count * sizeof(uint64_t));
+    } else {
+        memcpy(st.in + (size_t)slot * st.in_stride, me.in, BYTES_PER_BLOB);
+    }
+    (void)cell_off;
+    lk.lock();
+    Bt->copied++;
+    Q.cv_leader.notify_all();
+    if (leader) {
+        // ---- linger, close, run ----
+        const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(8 * (linger_us > 0 ? linger_us : 0));
+        while (Bt->n < st.capacity) {
+            if (Q.in_flight >= MAX_IN_FLIGHT) {          // the device is busy anyway: keep collecting until a batch finishes
+                Q.cv_leader.wait_for(lk, std::chrono::microseconds(200));
+                continue;
+            }
+            if (linger_us <= 0) break;
+            const auto gap_end = std::min(t_end, std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us));
+            const int before = Bt->n;
+            while (Bt->n == before && Q.cv_leader.wait_until(lk, gap_end) != std::cv_status::timeout) {}
+            if (Bt->n == before || std::chrono::steady_clock::now() >= t_end) break;
+        }
+        Bt->closed = true;
+        if (Q.forming == Bt) Q.forming = nullptr;
+        while (Bt->copied < Bt->n) Q.cv_leader.wait(lk);
+        const int n = Bt->n;
+        Q.in_flight++;
+        lk.unlock();
+        Status s = Status::Ok();
+        try {
+            std::fill(st.status.begin(), st.status.begin() + n, 0);
+            if (recover) s = recover_cells_and_kzg_proofs_strided(n, st.counts.data(), st.indices.data(), st.in, st.cells, st.proofs, st.status.data());
+            else s = compute_cells_and_kzg_proofs_batch(n, st.in, st.cells, want_proofs ? st.proofs : nullptr, st.status.data(), want_proofs);
+        } catch (const std::exception& ex) {             // fail the batch, never the queue
+            s = Status::Error(std::string("batch failed: ") + ex.what());
+        }
+        lk.lock();
+        Q.in_flight--;
+        Bt->result = s;
+        Bt->done = true;
+        Q.cv.notify_all();
+        Q.cv_leader.notify_all();
+    } else {
+        while (!Bt->done) Q.cv.wait(lk);
+    }
+    lk.unlock();
+    // ---- copy my results out of my slot (again all members at once) ----
+    Status mine = Status::Ok();
+    bool any_flag = false;
+    for (int i = 0; i < Bt->n && !any_flag; i++) any_flag = st.status[i] != 0;
+    if (!Bt->result.ok && !any_flag) {
+        mine = Bt->result;                                // the batch as a whole failed (CUDA error, allocation)
+    } else if (st.status[slot]) {
+        mine = item_error(recover, st.status[slot]);      // this item is the invalid one; the others are served
+    } else {
+        const uint8_t* c = st.cells + (size_t)slot * CELLS_PER_BLOB;
+        if (me.cells_scattered) for (int i = 0; i < N_CELLS; i++) memcpy(me.cells_scattered[i], c + (size_t)i * BYTES_PER_CELL, BYTES_PER_CELL);
+        else memcpy(me.cells, c, CELLS_PER_BLOB);
+        if (want_proofs) {
+            const uint8_t* p = st.proofs + (size_t)slot * PROOFS_PER_BLOB;
+            if (me.proofs_scattered) for (int i = 0; i < N_CELLS; i++) memcpy(me.proofs_scattered[i], p + (size_t)i * BYTES_PER_G1, BYTES_PER_G1);
+            else memcpy(me.proofs, p, PROOFS_PER_BLOB);
+        }
+    }
+    lk.lock();
+    if (--Bt->left == 0) {
+        Q.free_staging.push_back(Bt->st);
+        delete Bt;
+        Q.cv.notify_all();
+    }
+    return mine;
 }
 
 static bool coalescing_off() {
@@ -707,23 +785,44 @@ static bool coalescing_off() {
     return off;
 }
 
-Status Context::compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs) const {
-    const bool want_proofs = proofs != nullptr;
-    if (coalescing_off()) return compute_cells_and_kzg_proofs_batch(1, blob, cells, proofs, nullptr, want_proofs);
+Status Context::compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs, uint8_t* const* cells_scattered,
+                                                 uint8_t* const* proofs_scattered, bool want_proofs) const {
+    if (coalescing_off()) {
+        constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
+        std::vector<uint8_t> tc, tp;
+        if (cells_scattered) { tc.resize(CELLS_PER_BLOB); cells = tc.data(); }
+        if (want_proofs && proofs_scattered) { tp.resize(PROOFS_PER_BLOB); proofs = tp.data(); }
+        Status s = compute_cells_and_kzg_proofs_batch(1, blob, cells, want_proofs ? proofs : nullptr, nullptr, want_proofs);
+        if (!s.ok) return s;
+        if (cells_scattered) for (int i = 0; i < N_CELLS; i++) memcpy(cells_scattered[i], cells + (size_t)i * BYTES_PER_CELL, BYTES_PER_CELL);
+        if (want_proofs && proofs_scattered) for (int i = 0; i < N_CELLS; i++) memcpy(proofs_scattered[i], proofs + (size_t)i * BYTES_PER_G1, BYTES_PER_G1);
+        return s;
+    }
     CoalesceReq me;
-    me.in = blob; me.cells = cells; me.proofs = proofs;
+    me.in = blob; me.cells = cells; me.proofs = proofs; me.cells_scattered = cells_scattered; me.proofs_scattered = proofs_scattered;
     return coalesce(want_proofs ? CQ_CELLS_PROOFS : CQ_CELLS, me);
 }
 
 Status Context::recover_cells_and_kzg_proofs_one(uint64_t count, const uint64_t* indices, const uint8_t* cells, uint8_t* out_cells,
-                                                 uint8_t* out_proofs) const {
+                                                 uint8_t* out_proofs, uint8_t* const* cells_scattered, uint8_t* const* proofs_scattered) const {
     // index errors are decided here, in the reference's order (recovery.rs:90-146), so that a caller gets the exact error and a
     // malformed request never joins a shared batch
     bool bad = count < (uint64_t)N_CELLS / 2 || count > (uint64_t)N_CELLS;
     for (uint64_t k = 0; k < count && !bad; k++) bad = indices[k] >= (uint64_t)N_CELLS || (k && !(indices[k - 1] < indices[k]));
-    if (bad || coalescing_off()) return recover_cells_and_kzg_proofs_batch(1, &count, indices, cells, out_cells, out_proofs, nullptr);
+    if (bad || coalescing_off()) {
+        constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
+        std::vector<uint8_t> tc, tp;
+        if (cells_scattered) { tc.resize(CELLS_PER_BLOB); out_cells = tc.data(); }
+        if (proofs_scattered) { tp.resize(PROOFS_PER_BLOB); out_proofs = tp.data(); }
+        Status s = recover_cells_and_kzg_proofs_batch(1, &count, indices, cells, out_cells, out_proofs, nullptr);
+        if (!s.ok) return s;
+        if (cells_scattered) for (int i = 0; i < N_CELLS; i++) memcpy(cells_scattered[i], out_cells + (size_t)i * BYTES_PER_CELL, BYTES_PER_CELL);
+        if (proofs_scattered) for (int i = 0; i < N_CELLS; i++) memcpy(proofs_scattered[i], out_proofs + (size_t)i * BYTES_PER_G1, BYTES_PER_G1);
+        return s;
+    }
     CoalesceReq me;
     me.in = cells; me.indices = indices; me.count = count; me.cells = out_cells; me.proofs = out_proofs;
+    me.cells_scattered = cells_scattered; me.proofs_scattered = proofs_scattered;
     return coalesce(CQ_RECOVER, me);
 }
 
@@ -737,11 +836,21 @@ static int rev7(int x) {
 
 Status Context::recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
                                                    uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const {
+    return recover_impl(n, counts, indices, cells, out_cells, out_proofs, item_status, false);
+}
+// the same with item i's indices at indices + 128 i and its cells at cells + 128 i * 2048 (the coalescer's staging slots)
+Status Context::recover_cells_and_kzg_proofs_strided(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
+                                                     uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const {
+    return recover_impl(n, counts, indices, cells, out_cells, out_proofs, item_status, true);
+}
+
+Status Context::recover_impl(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells, uint8_t* out_cells,
+                             uint8_t* out_proofs, uint8_t* item_status, bool strided) const {
     if (n == 0) return Status::Ok();
     EKZG_TRY(bind_device());
     // host-side validation in the reference's order (recovery.rs:90-146); invalid items are skipped on the device
     std::vector<uint64_t> offset(n + 1, 0);
-    for (uint64_t i = 0; i < n; i++) offset[i + 1] = offset[i] + counts[i];
+    for (uint64_t i = 0; i < n; i++) offset[i + 1] = strided ? (i + 1) * (uint64_t)N_CELLS : offset[i] + counts[i];
     std::vector<uint8_t> code(n, 0);
     std::string first_err;
     for (uint64_t i = 0; i < n; i++) {
@@ -876,7 +985,7 @@ Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const 
             }
             EKZG_CUDA(launch_quotient(ws.d_coeffs, ws.d_z, ws.d_scalars, mode == Mode4844::PointProof ? ws.d_z32 : nullptr, cnt, st));
         }
-        EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.srs, N_BLOB / FK20_POINTS, cnt, st));
+        EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.srs, N_BLOB / FK20_POINTS, cnt, st, 0, -1, ws.d_msm_scratch));
         EKZG_CUDA(launch_sum_positions(ws.d_pts, cnt, N_BLOB / FK20_POINTS, 2, st));
         EKZG_CUDA(launch_g1_compress(ws.d_pts, ws.d_out48, 1, cnt, st));
         EKZG_CUDA(cudaMemcpyAsync(out48 + first * 48, ws.d_out48, (size_t)cnt * 48, cudaMemcpyDeviceToHost, st));

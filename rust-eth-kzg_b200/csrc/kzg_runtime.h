@@ -47,6 +47,7 @@ struct Workspace {
     G1Jac* d_pts = nullptr;
     uint32_t* d_queue = nullptr;   // ticket counter + per-unit completion flags of K5
     void* d_ntt_scratch = nullptr; // K5: odd-multiples tables of the resident warps (g1_ntt_scratch_bytes())
+    void* d_msm_scratch = nullptr; // K4a: per-window affine accumulators of the resident CTAs (fixed_msm_scratch_bytes())
     uint8_t* d_proofs = nullptr;
     uint32_t* d_status = nullptr;
     // small per-blob side buffers of the 4844 path
@@ -70,7 +71,7 @@ struct Workspace {
     uint8_t* h_cells = nullptr;
     uint8_t* h_proofs = nullptr;
     uint32_t* h_status = nullptr;
-    Status alloc(int cap, bool with_io);
+    Status alloc(int cap, bool with_io, size_t msm_scratch_bytes);
     void release();
 };
 
@@ -100,10 +101,13 @@ public:
     // one for everything queued, callers arriving meanwhile form the next).  This is what replaces the reference's per-call
     // rayon fan-out (crates/eip7594/src/prover.rs:117-148 over maybe_rayon): a lone blob fills 1 of the 32 lanes of every K5
     // work unit, 32 coalesced blobs cost the same time.  cells: 128*2048 B, proofs: 128*48 B or nullptr (compute_cells).
-    Status compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs) const;
+    // Outputs either contiguous (cells / proofs) or, as the C ABI hands them over, through 128 separate pointers each
+    // (cells_scattered / proofs_scattered; bindings/c/src/pointer_utils.rs:53-62) -- the caller's own thread writes them.
+    Status compute_cells_and_kzg_proofs_one(const uint8_t* blob, uint8_t* cells, uint8_t* proofs, uint8_t* const* cells_scattered,
+                                            uint8_t* const* proofs_scattered, bool want_proofs) const;
     // the same for eth_kzg_recover_cells_and_proofs: `count` cells (contiguous) at `indices`
     Status recover_cells_and_kzg_proofs_one(uint64_t count, const uint64_t* indices, const uint8_t* cells, uint8_t* out_cells,
-                                            uint8_t* out_proofs) const;
+                                            uint8_t* out_proofs, uint8_t* const* cells_scattered, uint8_t* const* proofs_scattered) const;
 
     // EIP-4844 prover side (crates/eip4844/src/prover.rs:17-88), batched.  Host buffers, contiguous.
     // item_status[i]: 0 ok, 1 invalid blob, 2 invalid commitment / z.
@@ -154,27 +158,54 @@ private:
         const uint8_t* in = nullptr;        // blob (131072 B) / the given cells, contiguous (count * 2048 B)
         const uint64_t* indices = nullptr;  // recover only
         uint64_t count = 0;                 // recover only
-        uint8_t* cells = nullptr;           // 128 * 2048 B out
-        uint8_t* proofs = nullptr;          // 128 * 48 B out (nullptr: compute_cells)
-        bool done = false;
-        Status st = Status::Ok();
+        uint8_t* cells = nullptr;           // 128 * 2048 B out, contiguous ...
+        uint8_t* proofs = nullptr;          // 128 * 48 B out
+        uint8_t* const* cells_scattered = nullptr;   // ... or through 128 pointers each
+        uint8_t* const* proofs_scattered = nullptr;
+    };
+    // pinned host block a coalesced batch is formed in: slot i holds member i's input, later its outputs
+    struct CoalesceStaging {
+        int capacity = 0;
+        size_t in_stride = 0;
+        uint8_t* in = nullptr;
+        uint8_t* cells = nullptr;
+        uint8_t* proofs = nullptr;
+        std::vector<uint8_t> status;
+        std::vector<uint64_t> counts, indices;   // recover: per slot, indices 128 wide
+        Status alloc(int cap, size_t in_bytes_per_item, bool with_proofs, bool with_index);
+        void release();
+    };
+    struct CoalesceBatch {
+        CoalesceStaging* st = nullptr;
+        int n = 0;          // members that joined
+        int copied = 0;     // members whose input is in the block
+        int left = 0;       // members that have not copied their results out yet
+        size_t cells_total = 0;
+        bool closed = false, done = false;
+        Status result = Status::Ok();
     };
     struct CoalesceQueue {
         std::mutex mu;
-        std::condition_variable cv;         // followers: "a batch finished / the leader stepped down"
-        std::condition_variable cv_leader;  // leader: "somebody joined the queue" (during the linger window)
-        std::deque<CoalesceReq*> q;
-        bool leader = false;
+        std::condition_variable cv;         // members: "my batch is done"; starters: "a staging block is free"
+        std::condition_variable cv_leader;  // leader: "somebody joined / finished copying in / a batch left the device"
+        CoalesceBatch* forming = nullptr;
+        int in_flight = 0;                  // batches handed to the device and not finished
+        int n_staging = 0;
+        std::vector<CoalesceStaging*> free_staging;
     };
     enum { CQ_CELLS = 0, CQ_CELLS_PROOFS = 1, CQ_RECOVER = 2 };
     mutable CoalesceQueue co_[3];
     Status coalesce(int which, CoalesceReq& me) const;
-    void run_coalesced(int which, std::vector<CoalesceReq*>& batch) const;
+    Status recover_impl(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells, uint8_t* out_cells, uint8_t* out_proofs,
+                        uint8_t* item_status, bool strided) const;
+    Status recover_cells_and_kzg_proofs_strided(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
+                                                uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const;
     Status init(bool use_precomp, int device);
     int device_ = 0;
     DevTables T_{};
     std::vector<void*> allocs_;
     uint64_t table_bytes_ = 0;
+    size_t msm_scratch_bytes_ = 0;
     const Fr* coset_shift_fwd_ = nullptr;   // 7^i / 8192
     const Fr* coset_shift_inv_ = nullptr;   // 7^-i / 8192
     mutable bool profiling_ = false;

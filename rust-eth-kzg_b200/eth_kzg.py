@@ -55,6 +55,8 @@ def load_library():
     lib.eth_kzg_b200_context_table_bytes.argtypes = [C.c_void_p]
     lib.eth_kzg_b200_context_device.argtypes = [C.c_void_p]
     lib.eth_kzg_b200_context_window.argtypes = [C.c_void_p]
+    lib.eth_kzg_b200_probe_imad_wide.argtypes = [C.c_void_p]
+    lib.eth_kzg_b200_probe_imad_wide.restype = C.c_double
     lib.eth_kzg_b200_context_srs_window.argtypes = [C.c_void_p]
     lib.eth_kzg_b200_context_device_count.argtypes = [C.c_void_p]
     lib.eth_kzg_b200_context_device_at.argtypes = [C.c_void_p, C.c_int]
@@ -133,6 +135,10 @@ class DASContext:
     @property
     def table_bytes(self):
         return self._lib.eth_kzg_b200_context_table_bytes(self._ctx)
+
+    def probe_imad_wide(self):
+        """measured carry-chained IMAD.WIDE multiply-adds per second on this context's device"""
+        return float(self._lib.eth_kzg_b200_probe_imad_wide(C.c_void_p(self._ctx)))
 
     @property
     def srs_window(self):

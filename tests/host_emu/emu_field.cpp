@@ -2,6 +2,7 @@
 // replaced by their CPU emulation (mp.cuh) and exports them for ctypes (tests/test_host_emu.py).
 // Test scaffolding only.
 #include "field.cuh"
+#include "fp_inv_gcd.cuh"
 #include <string.h>
 using namespace ekzg;
 extern "C" {
@@ -20,4 +21,11 @@ void emu_fr_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y, z;
 void emu_fr_inv(const uint32_t* a, uint32_t* r) { Fr x, z; memcpy(x.v, a, 32); fr_inv(z, x); memcpy(r, z.v, 32); }
 int emu_fr_ge_mod(const uint32_t* a) { Fr x; memcpy(x.v, a, 32); return fe_plain_ge_mod(x); }
 int emu_fp_gt_half(const uint32_t* a) { Fp x; memcpy(x.v, a, 48); return fe_plain_gt_half(x); }
+// inversion by division steps (csrc/fp_inv_gcd.cuh), Montgomery form in and out
+void emu_fp_inv_gcd(const uint32_t* a, uint32_t* r) {
+    Fp x, y;
+    memcpy(x.v, a, 48);
+    fp_inv_gcd(y, x);
+    memcpy(r, y.v, 48);
+}
 }

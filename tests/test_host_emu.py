@@ -307,3 +307,19 @@ def test_fpvm_interpreter_matches_program_emulation(emu_fpvm):
             assert [g * Ri % P for g in got] == exp, name
             assert got_mask == mask, name
         pc += len(prog)
+
+
+def test_fp_inversion_by_division_steps(emu_field):
+    """csrc/fp_inv_gcd.cuh (the shared inversion of the batched-affine MSM): Montgomery form in and out, against pow(-1)"""
+    rng = random.Random(7)
+    Rm = 1 << 384
+    out = (ctypes.c_uint32 * 12)()
+    vals = [1, 2, 3, P - 1, P - 2, (P - 1) // 2, (P + 1) // 2, Rm % P, pow(Rm, -1, P), 1 << 380, (1 << 381) - 1 - P % 7]
+    vals += [1 << k for k in range(0, 381, 13)] + [P - (1 << k) for k in range(0, 380, 17)]
+    vals += [rng.randrange(1, P) for _ in range(2000)]
+    for x in vals:
+        x %= P
+        emu_field.emu_fp_inv_gcd(arr(x * Rm % P, 12), out)
+        assert val(out) == pow(x, -1, P) * Rm % P, hex(x)
+    emu_field.emu_fp_inv_gcd(arr(0, 12), out)
+    assert val(out) == 0
