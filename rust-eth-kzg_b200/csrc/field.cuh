@@ -8,7 +8,8 @@
 // a[j]*b_i with even j land in X (lo at limb j, hi at limb j+1), those with odd j in Y, so each
 // row is two uninterrupted mad.lo.cc / madc.hi.cc chains with no carry fix-ups in the middle.
 // After the Montgomery step X[0] == 0 and the division by 2^32 is a role swap of X and Y.
-// Cost: N*(4N+1) integer multiply-adds  (Fp: 588, Fr: 264).
+// Cost: N*(2N+1) wide multiply-adds (ptxas fuses every mad.lo.cc / madc.hi.cc pair into one IMAD.WIDE.U32.X):
+// Fp 12*25 = 300, Fr 8*17 = 136.
 #pragma once
 #include "constants.cuh"
 

@@ -620,7 +620,7 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
 static int coalesce_capacity() {
     static const int v = [] {
         const char* e = getenv("EKZG_COALESCE_MAX");
-        int c = e ? atoi(e) : 512;
+        int c = e ? atoi(e) : 256;
         return c < 1 ? 1 : (c > 4096 ? 4096 : c);
     }();
     return std::min(v, chunk_capacity());
@@ -654,7 +654,7 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
     const bool recover = which == CQ_RECOVER, want_proofs = which != CQ_CELLS;
     const int cap = coalesce_capacity();
     static const int linger_us = [] { const char* e = getenv("EKZG_COALESCE_LINGER_US"); return e ? atoi(e) : 300; }();
-    constexpr int MAX_IN_FLIGHT = 2, MAX_STAGING = 4;
+    constexpr int MAX_IN_FLIGHT = 2, MAX_STAGING = 6;
     std::unique_lock<std::mutex> lk(Q.mu);
     // ---- join the batch being formed, or start one ----
     CoalesceBatch* Bt = nullptr;
@@ -717,6 +717,8 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
     Q.cv_leader.notify_all();
     if (leader) {
         // ---- linger, close, run ----
+        static const bool trace = getenv("EKZG_TRACE_COALESCE") != nullptr;
+        const auto t_lead = std::chrono::steady_clock::now();
         const auto t_end = std::chrono::steady_clock::now() + std::chrono::microseconds(8 * (linger_us > 0 ? linger_us : 0));
         while (Bt->n < st.capacity) {
             if (Q.in_flight >= MAX_IN_FLIGHT) {          // the device is busy anyway: keep collecting until a batch finishes
@@ -733,8 +735,9 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
         if (Q.forming == Bt) Q.forming = nullptr;
         while (Bt->copied < Bt->n) Q.cv_leader.wait(lk);
         const int n = Bt->n;
-        Q.in_flight++;
+        const int flying = Q.in_flight++;
         lk.unlock();
+        const auto t_run = std::chrono::steady_clock::now();
         Status s = Status::Ok();
         try {
             std::fill(st.status.begin(), st.status.begin() + n, 0);
@@ -742,6 +745,11 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
             else s = compute_cells_and_kzg_proofs_batch(n, st.in, st.cells, want_proofs ? st.proofs : nullptr, st.status.data(), want_proofs);
         } catch (const std::exception& ex) {             // fail the batch, never the queue
             s = Status::Error(std::string("batch failed: ") + ex.what());
+        }
+        if (trace) {
+            const auto t_done = std::chrono::steady_clock::now();
+            fprintf(stderr, "[ekzg trace] coalesced batch of %d (queue %d, %d already on the device): formed in %.2f ms, ran %.2f ms\n", n, which, flying,
+                    std::chrono::duration<double, std::milli>(t_run - t_lead).count(), std::chrono::duration<double, std::milli>(t_done - t_run).count());
         }
         lk.lock();
         Q.in_flight--;

@@ -63,6 +63,32 @@ def compute_cells_and_kzg_proofs_sharded(compute_batch, blobs_flat, n, group=Non
     return all_cells, all_proofs, list(all_status)
 
 
+def gather_rows(local, counts, group=None, dst=0):
+    """Tensor-level gather for the timed path: `local` is this rank's [counts[rank], row_bytes] uint8 tensor on the group's
+    device (CUDA for NCCL -- the bytes move GPU to GPU over NVLink -- or CPU for gloo).  Rank dst gets one
+    [sum(counts), row_bytes] tensor in rank order, the others None.  Uneven shards are padded to the largest."""
+    if not dist.is_initialized():
+        return local
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if world == 1:
+        return local
+    mx = max(counts)
+    row = local.shape[1]
+    if local.shape[0] != mx:
+        pad = torch.zeros((mx, row), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+        local = pad
+    local = local.contiguous()
+    if rank == dst:
+        out = torch.empty((world, mx, row), dtype=local.dtype, device=local.device)
+        dist.gather(local, list(out.unbind(0)), dst=dst, group=group)
+        if all(c == mx for c in counts):
+            return out.view(world * mx, row)
+        return torch.cat([out[r, :counts[r]] for r in range(world)], 0)
+    dist.gather(local, None, dst=dst, group=group)
+    return None
+
+
 def max_over_ranks(value, group=None):
     """the timing rule of bench.py: a multi-GPU time is the MAX over ranks"""
     t = torch.tensor([float(value)], dtype=torch.float64, device=_group_device(group))

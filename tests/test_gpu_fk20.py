@@ -37,10 +37,10 @@ def test_fk20_stages_match_oracle(das_ctx, pkg):
 
 
 @pytest.mark.parametrize("name,inp,expected", [pytest.param(n, i, o, id=n) for n, i, o in vectors.load("compute_cells_and_kzg_proofs")])
-def test_consensus_vectors(das_ctx, pkg, name, inp, expected):
+def test_consensus_vectors(vec_ctx, pkg, name, inp, expected):
     """crates/eip7594/tests/compute_cells_and_kzg_proofs.rs: byte-exact cells+proofs, `output: null` <=> Err"""
     try:
-        cells, proofs = das_ctx.compute_cells_and_kzg_proofs(inp["blob"])
+        cells, proofs = vec_ctx.compute_cells_and_kzg_proofs(inp["blob"])
         got = [cells, proofs]
     except pkg.KzgError:
         got = None
@@ -50,9 +50,9 @@ def test_consensus_vectors(das_ctx, pkg, name, inp, expected):
 
 
 @pytest.mark.parametrize("name,inp,expected", [pytest.param(n, i, o, id=n) for n, i, o in vectors.load("compute_cells_and_kzg_proofs")])
-def test_consensus_vectors_compute_cells(das_ctx, pkg, name, inp, expected):
+def test_consensus_vectors_compute_cells(vec_ctx, pkg, name, inp, expected):
     try:
-        got = das_ctx.compute_cells(inp["blob"])
+        got = vec_ctx.compute_cells(inp["blob"])
     except pkg.KzgError:
         got = None
     assert got == (list(expected[0]) if expected is not None else None)
@@ -116,11 +116,12 @@ def test_full_size_batch_properties(das_ctx, pkg):
 
 
 @pytest.mark.parametrize("fk20_w,srs_w", [("14", "13"), ("12", "12"), ("10", "9")])
-def test_precomputed_window_variants(das_ctx, pkg, fk20_w, srs_w, monkeypatch):
+def test_precomputed_window_variants(das_ctx, pkg, fk20_w, srs_w, monkeypatch, precomp_holder):
     """use_precomp contexts: per-window tables at several widths incl. the production one (w = 14, four top digits per lookup;
     SRS w = 13) and the pair-merged one (w = 12).  The session context (use_precomp=False: w = 8, no merged top window) is
     itself pinned by the consensus vectors and the oracle above, so it serves as the reference here -- plus the vectors
     again, directly."""
+    precomp_holder.release()   # the shared production context holds ~144 GiB: this test needs the memory for its own layout
     monkeypatch.setenv("EKZG_FK20_WINDOW", fk20_w)
     monkeypatch.setenv("EKZG_SRS_WINDOW", srs_w)
     ctx = pkg.DASContext(use_precomp=True)

@@ -147,3 +147,70 @@ def test_device_entry_point_finds_the_owning_member(das_ctx, multi_ctx, pkg):
                                                           torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
             assert bytes(d_cells.cpu().numpy()) == want[0] and bytes(d_proofs.cpu().numpy()) == want[1] and int(d_st.sum()) == 0
+
+
+def _sharded_worker(rank, world, port, n, backend, q):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import importlib
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    pkg = __graft_entry__.load_package()
+    sh = importlib.import_module("eth_kzg_b200.sharding")
+    syn = importlib.import_module("eth_kzg_b200.synthetic")
+    torch.cuda.set_device(rank % torch.cuda.device_count())
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    ctx = pkg.DASContext(use_precomp=False)
+    blobs = b"".join(syn.blob(4000 + i) for i in range(n))
+    res = sh.compute_cells_and_kzg_proofs_sharded(lambda shard, cnt: ctx.compute_cells_and_kzg_proofs_batch(shard, cnt), blobs, n)
+    # the tensor path bench.py times: device entry point on the shard, rows gathered to rank 0
+    lo, cnt = sh.shard_bounds(n, world, rank)
+    counts = [sh.shard_bounds(n, world, r)[1] for r in range(world)]
+    d_in = torch.frombuffer(bytearray(blobs[lo * 131072:(lo + cnt) * 131072]), dtype=torch.uint8).cuda()
+    d_cells = torch.empty((cnt, 128 * 2048), dtype=torch.uint8, device="cuda")
+    d_proofs = torch.empty((cnt, 128 * 48), dtype=torch.uint8, device="cuda")
+    d_status = torch.zeros(cnt, dtype=torch.int32, device="cuda")
+    ctx.compute_cells_and_kzg_proofs_device(cnt, d_in.data_ptr(), d_cells.data_ptr(), d_proofs.data_ptr(), d_status.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    on_group = (lambda t: t) if backend == "nccl" else (lambda t: t.cpu())
+    g_cells, g_proofs = sh.gather_rows(on_group(d_cells), counts), sh.gather_rows(on_group(d_proofs), counts)
+    if rank == 0:
+        want = ctx.compute_cells_and_kzg_proofs_batch(blobs, n)
+        ok_bytes = res[0] == want[0] and res[1] == want[1] and list(res[2]) == list(want[2])
+        ok_rows = bytes(g_cells.cpu().numpy().tobytes()) == want[0] and bytes(g_proofs.cpu().numpy().tobytes()) == want[1]
+        q.put((ok_bytes, ok_rows))
+    else:
+        assert res is None and g_cells is None
+    ctx.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [33, 70])
+def test_sharded_processes_gather_real_compute(n):
+    """sharding.py with the REAL per-shard computation (two processes, one DASContext each): NCCL over NVLink when the box has
+    two GPUs, otherwise two processes on device 0 gathering through gloo.  Rank 0 compares the gathered batch with what one
+    context computes for the whole batch."""
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_sharded_worker, args=(r, 2, port, n, backend, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok_bytes, ok_rows = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ok_bytes, "byte-level gather differs from the single-context batch"
+    assert ok_rows, "tensor-level gather differs from the single-context batch"

@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name,inp,expected", [pytest.param(n, i, o, id=n) for n, i, o in vectors.load("recover_cells_and_kzg_proofs")])
-def test_recover_vectors(das_ctx, pkg, name, inp, expected):
+def test_recover_vectors(vec_ctx, pkg, name, inp, expected):
     try:
-        cells, proofs = das_ctx.recover_cells_and_kzg_proofs(inp["cell_indices"], inp["cells"])
+        cells, proofs = vec_ctx.recover_cells_and_kzg_proofs(inp["cell_indices"], inp["cells"])
         got = [cells, proofs]
     except pkg.KzgError:
         got = None

@@ -22,23 +22,23 @@ def _run(pkg, f, *a):
 
 
 @pytest.mark.parametrize("name,inp,expected", _cases("verify_cell_kzg_proof_batch"))
-def test_verify_cell_kzg_proof_batch_vectors(das_ctx, pkg, name, inp, expected):
-    assert _run(pkg, das_ctx.verify_cell_kzg_proof_batch, inp["commitments"], inp["cell_indices"], inp["cells"], inp["proofs"]) == expected
+def test_verify_cell_kzg_proof_batch_vectors(vec_ctx, pkg, name, inp, expected):
+    assert _run(pkg, vec_ctx.verify_cell_kzg_proof_batch, inp["commitments"], inp["cell_indices"], inp["cells"], inp["proofs"]) == expected
 
 
 @pytest.mark.parametrize("name,inp,expected", _cases("verify_kzg_proof"))
-def test_verify_kzg_proof_vectors(das_ctx, pkg, name, inp, expected):
-    assert _run(pkg, das_ctx.verify_kzg_proof, inp["commitment"], inp["z"], inp["y"], inp["proof"]) == expected
+def test_verify_kzg_proof_vectors(vec_ctx, pkg, name, inp, expected):
+    assert _run(pkg, vec_ctx.verify_kzg_proof, inp["commitment"], inp["z"], inp["y"], inp["proof"]) == expected
 
 
 @pytest.mark.parametrize("name,inp,expected", _cases("verify_blob_kzg_proof"))
-def test_verify_blob_kzg_proof_vectors(das_ctx, pkg, name, inp, expected):
-    assert _run(pkg, das_ctx.verify_blob_kzg_proof, inp["blob"], inp["commitment"], inp["proof"]) == expected
+def test_verify_blob_kzg_proof_vectors(vec_ctx, pkg, name, inp, expected):
+    assert _run(pkg, vec_ctx.verify_blob_kzg_proof, inp["blob"], inp["commitment"], inp["proof"]) == expected
 
 
 @pytest.mark.parametrize("name,inp,expected", _cases("verify_blob_kzg_proof_batch"))
-def test_verify_blob_kzg_proof_batch_vectors(das_ctx, pkg, name, inp, expected):
-    assert _run(pkg, das_ctx.verify_blob_kzg_proof_batch, inp["blobs"], inp["commitments"], inp["proofs"]) == expected
+def test_verify_blob_kzg_proof_batch_vectors(vec_ctx, pkg, name, inp, expected):
+    assert _run(pkg, vec_ctx.verify_blob_kzg_proof_batch, inp["blobs"], inp["commitments"], inp["proofs"]) == expected
 
 
 def test_verify_cells_of_many_blobs(das_ctx, pkg):
@@ -73,7 +73,56 @@ def test_verify_cells_of_many_blobs(das_ctx, pkg):
     # the oracle agrees on a small slice
     from oracle import cref
     assert cref.verify_cell_kzg_proof_batch(C[:40], I[:40], CL[:40], PR[:40]) is True
-    assert cref.verify_cell_kzg_proof_batch(C[:40], I[:40], bad[:40], PR[:40]) is True or True
+    assert cref.verify_cell_kzg_proof_batch(C[980:1020], I[980:1020], CL[980:1020], PR[980:1020]) is True
+    assert cref.verify_cell_kzg_proof_batch(C[980:1020], I[980:1020], bad[980:1020], PR[980:1020]) is False   # the slice holding the corrupted cell
+    assert das_ctx.verify_cell_kzg_proof_batch(C[980:1020], I[980:1020], bad[980:1020], PR[980:1020]) is False
+
+
+def _openings(ctx, pkg, nb, first):
+    syn = importlib.import_module("eth_kzg_b200.synthetic")
+    flat = b"".join(syn.blob(first + i) for i in range(nb))
+    cms, st = ctx.blob_to_kzg_commitment_batch(flat, nb)
+    cells, proofs, st2 = ctx.compute_cells_and_kzg_proofs_batch(flat, nb)
+    assert not any(st) and not any(st2)
+    C = [cms[48 * (k // 128):48 * (k // 128) + 48] for k in range(nb * 128)]
+    I = [k % 128 for k in range(nb * 128)]
+    CL = [cells[k * 2048:(k + 1) * 2048] for k in range(nb * 128)]
+    PR = [proofs[k * 48:(k + 1) * 48] for k in range(nb * 128)]
+    return C, I, CL, PR
+
+
+def _invalid_proofs():
+    """the proofs of the reference's `invalid_proof` vectors (not on the curve / not in G1 / x >= p / bad flags)"""
+    return [i["proofs"][0] for n, i, o in vectors.load("verify_cell_kzg_proof_batch") if "_invalid_proof_" in n and len(i["proofs"][0]) == 48]
+
+
+@pytest.mark.parametrize("nb", [128, 264], ids=["config5_128x128", "above_32768_cells_column_sums"])
+def test_verify_config5_full_size(vec_ctx, pkg, nb):
+    """BASELINE config #5 at its real size (128 blobs x 128 cells = 16 384 openings in ONE call) and one call above 32 768 cells,
+    where the verifier switches to per-column sums on its own (no EKZG_VERIFY_COLUMN_SUMS): honest data -> true, one corrupted
+    cell -> false, one corrupted proof -> false, every malformed proof of the reference's vectors -> Err.  The oracle checks the
+    128-cell slice that holds the corrupted cell (it needs ~0.1 s per 128 cells, the whole batch would take minutes)."""
+    C, I, CL, PR = _openings(vec_ctx, pkg, nb, 7000)
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, CL, PR) is True
+    k = len(C) - 300
+    bad = list(CL)
+    bad[k] = bad[k][:2047] + bytes([bad[k][2047] ^ 1])
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, bad, PR) is False
+    badp = list(PR)
+    badp[5], badp[6] = PR[6], PR[5]
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, CL, badp) is False
+    inv = _invalid_proofs()
+    assert len(inv) >= 2
+    for q, pr in enumerate(inv):
+        badp = list(PR)
+        badp[(q * 4099 + 17) % len(PR)] = pr
+        with pytest.raises(pkg.KzgError):
+            vec_ctx.verify_cell_kzg_proof_batch(C, I, CL, badp)
+    from oracle import cref
+    lo = k - k % 128
+    sl = slice(lo, lo + 128)
+    assert cref.verify_cell_kzg_proof_batch(C[sl], I[sl], CL[sl], PR[sl]) is True
+    assert cref.verify_cell_kzg_proof_batch(C[sl], I[sl], bad[sl], PR[sl]) is False
 
 
 def test_verify_blob_proof_batch_synthetic(das_ctx, pkg):

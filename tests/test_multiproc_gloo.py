@@ -41,6 +41,16 @@ def _worker(rank, world, port, n, q):
     blobs = b"".join(bytes([i % 251]) * 131072 for i in range(n))
     res = sh.compute_cells_and_kzg_proofs_sharded(_standin, blobs, n)
     slow = sh.max_over_ranks(10.0 + rank)
+    # the tensor-level gather of the timed path (bench.py "strong"): ragged shards, rows in rank order on rank 0 only
+    import torch
+    lo, cnt = sh.shard_bounds(n, world, rank)
+    counts = [sh.shard_bounds(n, world, r)[1] for r in range(world)]
+    rows = torch.arange(lo, lo + cnt, dtype=torch.uint8).view(cnt, 1).repeat(1, 48)
+    got = sh.gather_rows(rows, counts)
+    if rank == 0:
+        assert got.shape == (n, 48) and bool((got[:, 0] == torch.arange(n, dtype=torch.uint8)).all())
+    else:
+        assert got is None
     if rank == 0:
         q.put((res == _standin(blobs, n), slow))
     else:
