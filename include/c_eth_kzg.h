@@ -171,6 +171,8 @@ int eth_kzg_b200_collect_stage_times(const DASContext *ctx, double *ms_out);
  * outputs in natural order, 64 compressed h commitments).  Synchronous. */
 CResult eth_kzg_b200_debug_fk20_stages(const DASContext *ctx, const uint8_t *blob, uint32_t *out_scalars, uint8_t *out_msm,
                                        uint8_t *out_h);
+/* Test hook: the 128 points of one blob after the first `phases` (0..14) G1-NTT phases, compressed, in storage order. */
+CResult eth_kzg_b200_debug_g1_ntt_prefix(const DASContext *ctx, const uint8_t *blob, int phases, uint8_t *out128x48);
 
 /* Test hook (host only): prod_i e(P_i, Q_i) == 1.  g1_xy: 96 B per point (x then y, plain little-endian 64-bit limbs,
  * all zero = identity); g2_sel[i]: 0 [1]_2, 1 [tau]_2, 2 [tau^64]_2, +3 for the negated point.  Returns 1/0. */

@@ -172,6 +172,34 @@ CResult eth_kzg_b200_debug_fk20_stages(const DASContext* ctx, const uint8_t* blo
     return c_ok();
 }
 
+// Test hook: the 128 points of one blob after the first `phases` G1-NTT phases (0 = the MSM outputs as K4 stored them), compressed,
+// in storage order.  With EKZG_K5_R4_MAX >= 1 and an even `phases` the radix-4 kernel runs its first phases / 2 super-phases.
+CResult eth_kzg_b200_debug_g1_ntt_prefix(const DASContext* ctx, const uint8_t* blob, int phases, uint8_t* out128x48) {
+    using namespace ekzg;
+    DeviceGuard guard;
+    const Context& c = cx(ctx);
+    Status s = c.bind_device();
+    if (!s.ok) return c_err(s.msg);
+    if (phases < 0 || phases > 14) return c_err("phases out of range");
+    Workspace* ws = c.acquire(1, true);
+    if (!ws) return c_err("allocation failed");
+    cudaStream_t st = ws->stream;
+    const DevTables& T = c.tables();
+    auto fail = [&](const char* m) { c.give_back(ws); return c_err(m); };
+    if (cudaMemcpyAsync(ws->d_blobs, blob, BYTES_PER_BLOB, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail("h2d");
+    cudaMemsetAsync(ws->d_status, 0, 4, st);
+    if (launch_blob_to_coeffs_cells(ws->d_blobs, ws->d_coeffs, ws->d_cells, ws->d_status, T, 1, true, st) != cudaSuccess) return fail("k1");
+    if (launch_toeplitz_scalars(ws->d_coeffs, ws->d_scalars, T, 1, st) != cudaSuccess) return fail("k2");
+    if (launch_fixed_msm(ws->d_scalars, ws->d_pts, T.fk20, FK20_MSMS, 1, st) != cudaSuccess) return fail("k4");
+    if (phases > 0 && launch_g1_ntt_phases(ws->d_pts, 1, 0, phases, ws->d_queue, ws->d_ntt_scratch, st) != cudaSuccess) return fail("k5");
+    if (launch_g1_compress(ws->d_pts, ws->d_proofs, 128, 1, st) != cudaSuccess) return fail("k6");
+    if (cudaMemcpyAsync(out128x48, ws->d_proofs, 128 * 48, cudaMemcpyDeviceToHost, st) != cudaSuccess) return fail("d2h");
+    cudaError_t e = cudaStreamSynchronize(st);
+    c.give_back(ws);
+    if (e != cudaSuccess) return c_err(cudaGetErrorString(e));
+    return c_ok();
+}
+
 // Test hook (host only, needs no GPU): prod e(P_i, Q_i) == 1 for affine G1 points given as 96 bytes each (x then y, plain
 // little-endian 64-bit limbs; all-zero = identity) and G2 selectors 0 [1]_2, 1 [tau]_2, 2 [tau^64]_2, +3 for the negation.
 int eth_kzg_b200_debug_pairing_check(int n, const uint8_t* g1_xy, const int* g2_sel) {

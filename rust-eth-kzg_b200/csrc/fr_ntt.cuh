@@ -13,23 +13,29 @@
 
 namespace ekzg {
 
+// 16-byte vector loads / stores of limb structs.  The LOCAL object is only ever touched through uint32_t lvalues (its own limb
+// type): writing it through a uint4* and reading the limbs afterwards is a strict-aliasing violation, and nvcc does act on it
+// (seen in the radix-4 G1-NTT combination unit: two named points and two temporaries ended up in one stack slot).
 template <class T>
 __device__ __forceinline__ T ld_vec(const T* p) {
     static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
     T r;
     const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint4* d = reinterpret_cast<uint4*>(&r);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
+        const uint4 q = s[i];
+        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+    }
     return r;
 }
 template <class T>
 __device__ __forceinline__ void st_vec(T* p, const T& v) {
     static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
     uint4* d = reinterpret_cast<uint4*>(p);
-    const uint4* s = reinterpret_cast<const uint4*>(&v);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = s[i];
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
 }
 
 __device__ __forceinline__ Fr smem_ld(const uint32_t* s, int stride, int i) {

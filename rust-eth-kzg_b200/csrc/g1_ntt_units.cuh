@@ -1,0 +1,179 @@
+// The work units of the G1-NTT kernels (K5): the radix-2 butterfly of k_fk20_g1_ntts and the multiplication / combination units
+// of the radix-4 latency-mode kernel k_fk20_g1_ntts_r4 (kzg_kernels.cu has the schedules and the write-up).  They live in a header
+// so that tests/host_emu can run the very same code on the CPU, unit by unit in ticket order, on real curve points.
+//   reference: the generic butterfly of polynomial/src/fft.rs:164-177 under Domain::ifft_g1_take_n / fft_g1
+//   (polynomial/src/domain.rs:149-194).
+// `tw` is the table of fixed-scalar op lists, row e = omega_128^e (twiddle_ops.inc): __constant__ on the device.
+#pragma once
+#include <cstddef>
+#include "g1_mul.cuh"
+
+namespace ekzg {
+
+typedef const uint16_t (*TwiddleOps)[MULOPS_STRIDE];
+
+#ifdef __CUDACC__
+#define EKZG_NTT_UNIT static __device__ __noinline__
+#define EKZG_NTT_INL __device__ __forceinline__
+EKZG_NTT_INL G1Jac ld_pt(const G1Jac* p) {  // L2-coherent: the producer ran on another SM
+    G1Jac r;
+    const uint4* s = reinterpret_cast<const uint4*>(p);
+    uint32_t* w = reinterpret_cast<uint32_t*>(&r);   // (uint32_t lvalues only on the local object: see ld_vec, fr_ntt.cuh)
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) {
+        const uint4 q = __ldcg(s + i);
+        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+    }
+    return r;
+}
+EKZG_NTT_INL void st_pt(G1Jac* p, const G1Jac& v) {
+    uint4* d = reinterpret_cast<uint4*>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) __stcg(d + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+}
+#else
+#define EKZG_NTT_UNIT static inline
+#define EKZG_NTT_INL static inline
+EKZG_NTT_INL G1Jac ld_pt(const G1Jac* p) { return *p; }
+EKZG_NTT_INL void st_pt(G1Jac* p, const G1Jac& v) { *p = v; }
+#endif
+
+EKZG_NTT_UNIT void g1_ntt_butterfly(G1Jac* __restrict__ pts, int B, int b, int t, int ph, TwiddleOps tw) {
+    const int mode = ph >= 7, st = mode ? 13 - ph : ph;
+    const int len = 1 << st;
+    const int pos = t & (len - 1);
+    const int i = ((t >> st) << (st + 1)) + pos, j = i + len;
+    const int e = pos << (6 - st);  // twiddle exponent of omega_128
+    G1Jac* pi = &pts[(size_t)i * B + b];
+    G1Jac* pj = &pts[(size_t)j * B + b];
+    if (mode == 0) {
+        G1Jac u = ld_pt(pi), v = ld_pt(pj);
+        if (e != 0 && !jac_is_inf(v)) jac_mul_ops(v, v, tw[(128 - e) & 127]);
+        G1Jac s = u;
+        jac_add(s, v);
+        st_pt(pi, s);
+        if (st != 6) {
+            jac_neg(v, v);
+            jac_add(u, v);
+            st_pt(pj, u);
+        }
+    } else if (st == 6) {
+        G1Jac u = ld_pt(pi);
+        if (e != 0 && !jac_is_inf(u)) jac_mul_ops(u, u, tw[e]);
+        st_pt(pj, u);
+    } else {
+        G1Jac u = ld_pt(pi), v = ld_pt(pj);
+        G1Jac s = u;
+        jac_add(s, v);
+        jac_neg(v, v);
+        jac_add(u, v);
+        if (e != 0 && !jac_is_inf(u)) jac_mul_ops(u, u, tw[e]);
+        st_pt(pi, s);
+        st_pt(pj, u);
+    }
+}
+
+constexpr int R4_SUPER = 7;
+constexpr int R4_UNITS = 192;          // units per blob group and super-phase: 160 + 32, middle 128 + 64
+constexpr int R4_TMP_POINTS = 160;     // products per blob and super-phase
+EKZG_NTT_INL int r4_nmul(int sp) { return sp == 3 ? 128 : 160; }   // (middle: only the first 64 do work, see r4_middle_unit)
+
+// p <- omega_128^tw * p (tw in [0, 128))
+EKZG_NTT_INL void r4_twiddle_mul(G1Jac& p, int e, TwiddleOps tw) {
+    if (e == 0 || jac_is_inf(p)) return;
+    if (e == 64) { jac_neg(p, p); return; }
+    jac_mul_ops(p, p, tw[e]);
+}
+EKZG_NTT_INL void r4_sub(G1Jac& a, const G1Jac& b) {   // a -= b
+    G1Jac n;
+    jac_neg(n, b);
+    jac_add(a, n);
+}
+
+// middle super-phase, unit t < 64: the radix-2 butterflies of inverse stage 6 and forward stage 6 on (pts[t], pts[t+64]) back to
+// back -- two multiplications deep.  (The flat form, products omega^-t x1 and omega^t x0 combined afterwards, is one deep and
+// agrees with this one under host emulation, but its combination step gave other points on the device)
+EKZG_NTT_UNIT void r4_middle_unit(G1Jac* __restrict__ pts, int B, int b, int t, TwiddleOps tw) {
+    g1_ntt_butterfly(pts, B, b, t, 6, tw);
+    g1_ntt_butterfly(pts, B, b, t, 7, tw);
+}
+
+EKZG_NTT_UNIT void r4_mul_unit(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int b, int sp, int u, TwiddleOps tw) {
+    // which point (or combination of points) times which root of unity
+    int i0, i1 = -1, i2 = -1, i3 = -1, e;       // p = pts[i0] - pts[i1] + pts[i2] - pts[i3] (absent terms: -1), then p *= omega^e
+    {
+        const bool fwd = sp > 3;
+        const int s = fwd ? 2 * (6 - sp) : 2 * sp, len = 1 << s;
+        const int q = u / 5, which = u - 5 * q;
+        const int pos = q & (len - 1), base = ((q >> s) << (s + 2)) + pos;
+        const int ea = pos << (6 - s), eb = pos << (5 - s);
+        e = which == 0 ? ea : which == 1 ? eb : which == 2 ? (fwd ? eb + 32 : ea + eb) : which == 3 ? (fwd ? ea + eb : eb + 32) : ea + eb + 32;
+        if (!fwd) {
+            i0 = base + (which == 0 ? 1 : (which == 1 || which == 3) ? 2 : 3) * len;
+            e = (128 - e) & 127;
+        } else {
+            // which 0: (x0 - x1) + (x2 - x3); 1, 3: x0 - x2; 2, 4: x1 - x3
+            const int a = (which == 2 || which == 4) ? 1 : 0;
+            i0 = base + a * len;
+            i1 = base + (which == 0 ? 1 : a + 2) * len;
+            if (which == 0) { i2 = base + 2 * len; i3 = base + 3 * len; }
+            e &= 127;
+        }
+    }
+    G1Jac p = ld_pt(&pts[(size_t)i0 * B + b]);
+    if (i1 >= 0) r4_sub(p, ld_pt(&pts[(size_t)i1 * B + b]));
+    if (i2 >= 0) {
+        G1Jac d = ld_pt(&pts[(size_t)i2 * B + b]);
+        r4_sub(d, ld_pt(&pts[(size_t)i3 * B + b]));
+        jac_add(p, d);
+    }
+    r4_twiddle_mul(p, e, tw);
+    st_pt(&tmp[(size_t)u * B + b], p);
+}
+
+EKZG_NTT_UNIT void r4_combine_unit(G1Jac* __restrict__ pts, const G1Jac* __restrict__ tmp, int B, int b, int sp, int c) {
+    const bool fwd = sp > 3;
+    const int s = fwd ? 2 * (6 - sp) : 2 * sp, len = 1 << s;
+    const int pos = c & (len - 1), base = ((c >> s) << (s + 2)) + pos;
+    G1Jac* o0 = &pts[(size_t)base * B + b];
+    G1Jac* o1 = &pts[(size_t)(base + len) * B + b];
+    G1Jac* o2 = &pts[(size_t)(base + 2 * len) * B + b];
+    G1Jac* o3 = &pts[(size_t)(base + 3 * len) * B + b];
+    const G1Jac* t0 = &tmp[(size_t)(5 * c) * B + b];
+    if (!fwd) {
+        G1Jac a = ld_pt(o0), bm = a;
+        { const G1Jac p1 = ld_pt(t0); jac_add(a, p1); r4_sub(bm, p1); }
+        G1Jac cc = ld_pt(t0 + (size_t)B);
+        jac_add(cc, ld_pt(t0 + (size_t)2 * B));                 // p2 + p3
+        G1Jac y = a;
+        jac_add(y, cc);
+        st_pt(o0, y);
+        r4_sub(a, cc);
+        st_pt(o2, a);
+        G1Jac d = ld_pt(t0 + (size_t)3 * B);
+        r4_sub(d, ld_pt(t0 + (size_t)4 * B));                   // p4 - p5
+        y = bm;
+        jac_add(y, d);
+        st_pt(o1, y);
+        r4_sub(bm, d);
+        st_pt(o3, bm);
+    } else {
+        G1Jac y = ld_pt(o0);
+        jac_add(y, ld_pt(o1));
+        G1Jac z = ld_pt(o2);
+        jac_add(z, ld_pt(o3));
+        jac_add(y, z);
+        st_pt(o0, y);
+        st_pt(o1, ld_pt(t0));
+        y = ld_pt(t0 + (size_t)B);
+        jac_add(y, ld_pt(t0 + (size_t)2 * B));
+        st_pt(o2, y);
+        y = ld_pt(t0 + (size_t)3 * B);
+        r4_sub(y, ld_pt(t0 + (size_t)4 * B));
+        st_pt(o3, y);
+    }
+}
+
+
+}  // namespace ekzg

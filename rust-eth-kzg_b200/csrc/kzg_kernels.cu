@@ -13,6 +13,7 @@
 #include "fr_ntt.cuh"
 #include "fpvm.cuh"
 #include "fp_inv_gcd.cuh"
+#include "g1_ntt_units.cuh"
 #include <algorithm>
 #include <cstdlib>
 
@@ -439,15 +440,13 @@ struct K4aScratch {
     uint4* pre;     // this thread's granule 0 of batch slot 0
     __device__ __forceinline__ Fp ld(const uint4* p) const {
         Fp r;
-        uint4* d = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-        for (int q = 0; q < 3; q++) d[q] = __ldcg(p + q * K4A_THREADS);
+        #pragma unroll
+        for (int q = 0; q < 3; q++) { const uint4 g = __ldcg(p + q * K4A_THREADS); r.v[4 * q] = g.x; r.v[4 * q + 1] = g.y; r.v[4 * q + 2] = g.z; r.v[4 * q + 3] = g.w; }
         return r;
     }
     __device__ __forceinline__ void st(uint4* p, const Fp& v) const {
-        const uint4* s = reinterpret_cast<const uint4*>(&v);
-#pragma unroll
-        for (int q = 0; q < 3; q++) __stcg(p + q * K4A_THREADS, s[q]);
+        #pragma unroll
+        for (int q = 0; q < 3; q++) __stcg(p + q * K4A_THREADS, make_uint4(v.v[4 * q], v.v[4 * q + 1], v.v[4 * q + 2], v.v[4 * q + 3]));
     }
     __device__ __forceinline__ void prefetch(const uint4* p) const {   // one element (three granules) towards L2
 #pragma unroll
@@ -472,15 +471,13 @@ struct K4aXchg {
     uint4* base;   // granule 0 of thread 0
     __device__ __forceinline__ Fp ld(int thread) const {
         Fp r;
-        uint4* d = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-        for (int q = 0; q < 3; q++) d[q] = base[q * K4A_THREADS + thread];
+        #pragma unroll
+        for (int q = 0; q < 3; q++) { const uint4 g = base[q * K4A_THREADS + thread]; r.v[4 * q] = g.x; r.v[4 * q + 1] = g.y; r.v[4 * q + 2] = g.z; r.v[4 * q + 3] = g.w; }
         return r;
     }
     __device__ __forceinline__ void st(int thread, const Fp& v) const {
-        const uint4* s = reinterpret_cast<const uint4*>(&v);
-#pragma unroll
-        for (int q = 0; q < 3; q++) base[q * K4A_THREADS + thread] = s[q];
+        #pragma unroll
+        for (int q = 0; q < 3; q++) base[q * K4A_THREADS + thread] = make_uint4(v.v[4 * q], v.v[4 * q + 1], v.v[4 * q + 2], v.v[4 * q + 3]);
     }
 };
 
@@ -765,20 +762,6 @@ __constant__ uint16_t c_twiddle_ops[128][MULOPS_STRIDE] =
 constexpr int NTT_THREADS = 128;
 constexpr int NTT_PHASES = 14;
 
-__device__ __forceinline__ G1Jac ld_pt(const G1Jac* p) {  // L2-coherent: the producer ran on another SM
-    G1Jac r;
-    const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint4* d = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) d[i] = __ldcg(s + i);
-    return r;
-}
-__device__ __forceinline__ void st_pt(G1Jac* p, const G1Jac& v) {
-    uint4* d = reinterpret_cast<uint4*>(p);
-    const uint4* s = reinterpret_cast<const uint4*>(&v);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) __stcg(d + i, s[i]);
-}
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -786,41 +769,6 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void red_release_inc(unsigned* p) {
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-
-__device__ __noinline__ void g1_ntt_butterfly(G1Jac* __restrict__ pts, int B, int b, int t, int ph) {
-    const int mode = ph >= 7, st = mode ? 13 - ph : ph;
-    const int len = 1 << st;
-    const int pos = t & (len - 1);
-    const int i = ((t >> st) << (st + 1)) + pos, j = i + len;
-    const int e = pos << (6 - st);  // twiddle exponent of omega_128
-    G1Jac* pi = &pts[(size_t)i * B + b];
-    G1Jac* pj = &pts[(size_t)j * B + b];
-    if (mode == 0) {
-        G1Jac u = ld_pt(pi), v = ld_pt(pj);
-        if (e != 0 && !jac_is_inf(v)) jac_mul_ops(v, v, c_twiddle_ops[(128 - e) & 127]);
-        G1Jac s = u;
-        jac_add(s, v);
-        st_pt(pi, s);
-        if (st != 6) {
-            jac_neg(v, v);
-            jac_add(u, v);
-            st_pt(pj, u);
-        }
-    } else if (st == 6) {
-        G1Jac u = ld_pt(pi);
-        if (e != 0 && !jac_is_inf(u)) jac_mul_ops(u, u, c_twiddle_ops[e]);
-        st_pt(pj, u);
-    } else {
-        G1Jac u = ld_pt(pi), v = ld_pt(pj);
-        G1Jac s = u;
-        jac_add(s, v);
-        jac_neg(v, v);
-        jac_add(u, v);
-        if (e != 0 && !jac_is_inf(u)) jac_mul_ops(u, u, c_twiddle_ops[e]);
-        st_pt(pi, s);
-        st_pt(pj, u);
-    }
 }
 
 // queue[0] = ticket counter, queue[1 + g*14 + ph] = finished units of (blob group g, phase ph); zeroed by the launcher
@@ -845,10 +793,69 @@ k_fk20_g1_ntts(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned
             __syncwarp();
         }
         const int b = g * 32 + lane;
-        if (b < B) g1_ntt_butterfly(pts, B, b, t, ph);
+        if (b < B) g1_ntt_butterfly(pts, B, b, t, ph, c_twiddle_ops);
         __threadfence();
         __syncwarp();
         if (lane == 0) red_release_inc(cnt + ph);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5, radix-4 form for SMALL batches (latency mode: a lone blob, a coalesced handful, a 128-blob shard of a strong-scaled job)
+//   A batch of B blobs gives the radix-2 kernel above only 64*ceil(B/32) warps of work per phase, and its 14 phases are a
+//   dependent chain of 12 fixed-scalar multiplications (~1.4 ms each for a warp that has its sub-partition to itself): 20 ms
+//   whatever B is.  Here two consecutive radix-2 stages are flattened into one super-phase:
+//       inverse DIT stages (s, s+1) on x0..x3 = pts[base + {0, 1, 2, 3} * 2^s]:
+//           y0 = x0 + p1 + p2 + p3    y2 = x0 + p1 - p2 - p3    y1 = x0 - p1 + p4 - p5    y3 = x0 - p1 - p4 + p5
+//           p1 = W(ea) x1, p2 = W(eb) x2, p3 = W(ea+eb) x3, p4 = W(eb+32) x2, p5 = W(ea+eb+32) x3        (W(e) = omega^-e)
+//       middle: inverse stage 6 (only the 64 kept outputs) + forward stage 6:  pts[t] = h = x0 + W(t) x1,  pts[t+64] = omega^t h
+//               (two multiplications deep, as two radix-2 butterflies in one unit)
+//       forward DIF stages (s+1, s):
+//           y0 = x0+x1+x2+x3   y1 = w(ea)(x0-x1+x2-x3)   y2 = w(eb)(x0-x2) + w(eb+32)(x1-x3)   y3 = w(ea+eb)(x0-x2) - w(ea+eb+32)(x1-x3)
+//   The five products of a radix-4 butterfly are independent, so a super-phase is ONE multiplication deep: 8 instead of 12 on
+//   the critical path, for 25 % more multiplications (5 per 4 points and two stages instead of 4) -- which is why the wide
+//   launches keep the radix-2 kernel.  Same persistent ticket queue; per blob group and super-phase, 160 (middle: 128)
+//   multiplication units write their products to a scratch array, then 32 (64) combination units add them up in place.
+// ------------------------------------------------------------------------------------------------
+// queue[0] = ticket counter, queue[1 + (g*7 + sp)*2 + kind] = finished multiplication (0) / combination (1) units of blob group g
+// in super-phase sp; zeroed by the launcher.  Tickets: super-phase major, then all multiplication units, then all combinations.
+__global__ void __launch_bounds__(NTT_THREADS, 2)
+k_fk20_g1_ntts_r4(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int G, int sp_end, unsigned* __restrict__ queue) {
+    const int lane = threadIdx.x & 31;
+    const unsigned per_sp = (unsigned)G * R4_UNITS, total = per_sp * (unsigned)sp_end;
+    for (;;) {
+        unsigned id = 0;
+        if (lane == 0) id = atomicAdd(&queue[0], 1u);
+        id = __shfl_sync(0xffffffffu, id, 0);
+        if (id >= total) break;
+        const int sp = (int)(id / per_sp);
+        unsigned rem = id - (unsigned)sp * per_sp;
+        const unsigned nmul = (unsigned)r4_nmul(sp), ncomb = R4_UNITS - nmul;
+        const bool comb = rem >= (unsigned)G * nmul;
+        if (comb) rem -= (unsigned)G * nmul;
+        const unsigned per = comb ? ncomb : nmul;
+        const int g = (int)(rem / per), u = (int)(rem - (unsigned)g * per);
+        unsigned* cnt = queue + 1 + ((size_t)g * R4_SUPER + sp) * 2;
+        // a multiplication unit reads what the combinations of the previous super-phase wrote; a combination unit reads the
+        // products of its own super-phase (and overwrites the inputs of all of them)
+        const unsigned* wait_on = comb ? cnt : (sp > 0 ? cnt - 1 : nullptr);
+        const unsigned need = comb ? nmul : (unsigned)(R4_UNITS - r4_nmul(sp - 1));
+        if (wait_on) {
+            if (lane == 0) {
+                while (ld_acquire_u32(wait_on) < need) __nanosleep(128);
+            }
+            __syncwarp();
+        }
+        const int b = g * 32 + lane;
+        if (b < B) {
+            if (sp == 3) {           // middle: 64 fused butterfly pairs; the other tickets of this super-phase only count
+                if (!comb && u < 64) r4_middle_unit(pts, B, b, u, c_twiddle_ops);
+            } else if (comb) r4_combine_unit(pts, tmp, B, b, sp, u);
+            else r4_mul_unit(pts, tmp, B, b, sp, u, c_twiddle_ops);
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) red_release_inc(cnt + (comb ? 1 : 0));
     }
 }
 
@@ -870,15 +877,13 @@ struct GScratch {                 // this lane's view of its warp's scratch bloc
     uint4* p;
     __device__ __forceinline__ Fp ld(int idx) const {
         Fp r;
-        uint4* d = reinterpret_cast<uint4*>(&r);
-#pragma unroll
-        for (int q = 0; q < 3; q++) d[q] = __ldcg(p + (idx * 3 + q) * 32);
+        #pragma unroll
+        for (int q = 0; q < 3; q++) { const uint4 g = __ldcg(p + (idx * 3 + q) * 32); r.v[4 * q] = g.x; r.v[4 * q + 1] = g.y; r.v[4 * q + 2] = g.z; r.v[4 * q + 3] = g.w; }
         return r;
     }
     __device__ __forceinline__ void st(int idx, const Fp& v) const {
-        const uint4* s = reinterpret_cast<const uint4*>(&v);
-#pragma unroll
-        for (int q = 0; q < 3; q++) __stcg(p + (idx * 3 + q) * 32, s[q]);
+        #pragma unroll
+        for (int q = 0; q < 3; q++) __stcg(p + (idx * 3 + q) * 32, make_uint4(v.v[4 * q], v.v[4 * q + 1], v.v[4 * q + 2], v.v[4 * q + 3]));
     }
 };
 
@@ -1498,9 +1503,17 @@ constexpr int K5_VM_CTAS_PER_SM = 4;
 // ticket counter + one completion flag per (blob group, phase, butterfly)
 size_t g1_ntt_queue_words(int B) { return 1 + (size_t)((B + 31) / 32) * NTT_PHASES * 64; }
 // odd-multiples tables of the resident warps of k_fk20_g1_ntts_vm (one block per warp slot of the persistent grid)
+constexpr int R4_MAX_BLOBS = 256;      // the product scratch of the radix-4 form is sized for this many blobs
+static int k5_r4_max() {
+    // batches up to this many blobs take the radix-4 kernel (EKZG_K5_R4_MAX; 0 switches it off)
+    const char* e = getenv("EKZG_K5_R4_MAX");
+    const int v = e ? atoi(e) : 224;   // measured (tools/k5_sweep.py, profiles/r2_i_k5_sweep.jsonl): faster up to 224 blobs, equal at 256
+    return v < 0 ? 0 : (v > R4_MAX_BLOBS ? R4_MAX_BLOBS : v);
+}
 size_t g1_ntt_scratch_bytes() {
     if (ntt_query_sms() != cudaSuccess) return 0;
-    return (size_t)g_ntt_sms * K5_VM_CTAS_PER_SM * (fpvm::NT / 32) * K5_SCRATCH_WARP_BYTES;
+    return std::max((size_t)g_ntt_sms * K5_VM_CTAS_PER_SM * (fpvm::NT / 32) * K5_SCRATCH_WARP_BYTES,
+                    (size_t)R4_TMP_POINTS * R4_MAX_BLOBS * sizeof(G1Jac));
 }
 
 // phases [ph0, ph1) of the two transforms over pts[128][B]; queue: g1_ntt_queue_words(B) words, scratch: g1_ntt_scratch_bytes()
@@ -1512,6 +1525,13 @@ cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* 
     if (e != cudaSuccess) return e;
     const long units = (long)G * 64;                                   // warps that can run at once
     unsigned* q = reinterpret_cast<unsigned*>(queue);
+    // latency mode (the memset above covers its 1 + 14 G counters); a phase range [0, 2k) is its first k super-phases (test hook)
+    if (ph0 == 0 && (ph1 & 1) == 0 && ph1 >= 2 && ph1 <= NTT_PHASES && scratch && B <= k5_r4_max()) {
+        const int grid = (int)std::min<long>((long)g_ntt_sms * 2, ((long)G * 160 + NTT_THREADS / 32 - 1) / (NTT_THREADS / 32));
+        k_fk20_g1_ntts_r4<<<grid, NTT_THREADS, 0, st>>>(pts, reinterpret_cast<G1Jac*>(scratch), B, G, ph1 / 2, q);
+        EKZG_LAUNCH_CHECK();
+        return cudaSuccess;
+    }
     if (!k5_register_form()) {
         const int grid = (int)std::min<long>((long)g_ntt_sms * K5_VM_CTAS_PER_SM, (units + fpvm::NT / 32 - 1) / (fpvm::NT / 32));
         k_fk20_g1_ntts_vm<<<grid, fpvm::NT, fpvm::SMEM_BYTES, st>>>(pts, B, G, ph0, ph1, q, reinterpret_cast<uint4*>(scratch));

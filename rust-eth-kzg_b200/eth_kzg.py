@@ -25,7 +25,8 @@ class _CResult(C.Structure):
 
 
 def library_path():
-    return os.path.join(_HERE, "lib", "libc_eth_kzg_b200.so")
+    # EKZG_LIB: an A/B build of the same library (tools/*.sh compare kernel variants this way); the product path is the default
+    return os.environ.get("EKZG_LIB") or os.path.join(_HERE, "lib", "libc_eth_kzg_b200.so")
 
 
 def build_library():
@@ -64,7 +65,7 @@ def load_library():
                  "eth_kzg_verify_cell_kzg_proof_batch", "eth_kzg_recover_cells_and_proofs", "eth_kzg_compute_kzg_proof",
                  "eth_kzg_compute_blob_kzg_proof", "eth_kzg_verify_kzg_proof", "eth_kzg_verify_blob_kzg_proof",
                  "eth_kzg_verify_blob_kzg_proof_batch", "eth_kzg_b200_compute_cells_and_kzg_proofs_batch",
-                 "eth_kzg_b200_compute_cells_and_kzg_proofs_device", "eth_kzg_b200_debug_fk20_stages",
+                 "eth_kzg_b200_compute_cells_and_kzg_proofs_device", "eth_kzg_b200_debug_fk20_stages", "eth_kzg_b200_debug_g1_ntt_prefix",
                  "eth_kzg_b200_recover_cells_and_kzg_proofs_batch", "eth_kzg_b200_blob_to_kzg_commitment_batch", "eth_kzg_b200_compute_blob_kzg_proof_batch"):
         getattr(lib, name).restype = _CResult
     _lib = lib
@@ -302,6 +303,11 @@ class DASContext:
         ms = (C.c_double * 5)()
         n = self._lib.eth_kzg_b200_collect_stage_times(C.c_void_p(self._ctx), ms)
         return n, list(ms)
+
+    def debug_g1_ntt_prefix(self, blob, phases):
+        out = C.create_string_buffer(128 * 48)
+        _check(self._lib, self._lib.eth_kzg_b200_debug_g1_ntt_prefix(C.c_void_p(self._ctx), _exact(blob, BYTES_PER_BLOB, "blob"), C.c_int(phases), out))
+        return [out.raw[48 * i:48 * i + 48] for i in range(128)]
 
     def debug_fk20_stages(self, blob):
         sc = (C.c_uint32 * (128 * 64 * 8))()

@@ -149,3 +149,25 @@ def test_precomputed_window_variants(das_ctx, pkg, fk20_w, srs_w, monkeypatch, p
             assert ctx.blob_to_kzg_commitment(inp["blob"]) == expected, name
     finally:
         ctx.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 128, 160])
+def test_k5_radix4_equals_radix2(vec_ctx, pkg, n, monkeypatch):
+    """the latency-mode G1-NTT kernel (radix-4 super-phases, small batches) against the radix-2 kernel the vectors pin, on the
+    same batch: ragged group sizes, identity points everywhere (zero blob), and the oracle on the first two blobs"""
+    syn = _synth(pkg)
+    blobs = [syn.blob(6100 + i) for i in range(n)]
+    if n >= 31:
+        blobs[3:7] = list(syn.edge_blobs())[:4]
+    flat = b"".join(blobs)
+    monkeypatch.setenv("EKZG_K5_R4_MAX", "0")
+    want = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
+    monkeypatch.setenv("EKZG_K5_R4_MAX", "256")
+    got = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
+    assert got[2] == want[2] == [0] * n
+    assert got[0] == want[0]
+    assert got[1] == want[1], "radix-4 proofs differ from the radix-2 kernel's"
+    from oracle import cref
+    for i in range(min(n, 2)):
+        oc, op = cref.compute_cells_and_kzg_proofs(blobs[i])
+        assert got[1][i * 6144:(i + 1) * 6144] == b"".join(op)

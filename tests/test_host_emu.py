@@ -323,3 +323,28 @@ def test_fp_inversion_by_division_steps(emu_field):
         assert val(out) == pow(x, -1, P) * Rm % P, hex(x)
     emu_field.emu_fp_inv_gcd(arr(0, 12), out)
     assert val(out) == 0
+
+
+@pytest.fixture(scope="module")
+def emu_ntt():
+    return _build("emu_ntt")
+
+
+def test_g1_ntt_radix4_units_equal_radix2_units_on_points(emu_ntt):
+    """the device code of both G1-NTT kernels (g1_ntt_units.cuh), unit by unit on the CPU: every prefix of radix-4 super-phases
+    leaves the 128 points exactly where the radix-2 phases leave them -- random points, identities, repeated and opposite points
+    (the doubling / cancellation branches of the additions)"""
+    rng = random.Random(11)
+    gens = [pyref.g1_mul(pyref.G1_GEN, rng.randrange(1, R)) for _ in range(12)]
+    for trial in range(2):
+        if trial == 0:
+            pts = [pyref.g1_mul(gens[i % 12], rng.randrange(1, 1 << 20)) for i in range(128)]
+        else:       # few distinct values: plenty of P + P, P - P and identities on the way
+            pts = [None if i % 5 == 0 else (gens[i % 2] if i % 3 else pyref.g1_neg(gens[i % 2])) for i in range(128)]
+        buf = b"".join(pyref.g1_compress(p) for p in pts)
+        for phases in (2, 6, 8, 10, 14):
+            a, b = ctypes.create_string_buffer(128 * 48), ctypes.create_string_buffer(128 * 48)
+            assert emu_ntt.emu_g1_ntt(0, phases, buf, a) == 0
+            assert emu_ntt.emu_g1_ntt(1, phases, buf, b) == 0
+            bad = [i for i in range(128) if a.raw[48 * i:48 * i + 48] != b.raw[48 * i:48 * i + 48]]
+            assert not bad, "trial %d, %d phases: positions %r differ" % (trial, phases, bad[:16])
