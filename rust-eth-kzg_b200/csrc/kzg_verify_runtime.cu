@@ -238,12 +238,15 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
                                   const uint8_t* y32, const uint8_t* const* proofs, bool* verified) const {
     *verified = false;
     if (n == 0) { *verified = true; return Status::Ok(); }
-    if (n > (1u << 16)) return Status::Error("batch too large");
+    if (n > (1u << 24)) return Status::Error("batch too large");   // (the per-item side buffers are sized by N; the blobs go in chunks)
     EKZG_TRY(bind_device());
     const int N = (int)n;
     std::vector<uint8_t> hc((size_t)N * 48), hp((size_t)N * 48);
     for (int i = 0; i < N; i++) { memcpy(&hc[(size_t)i * 48], commitments[i], 48); memcpy(&hp[(size_t)i * 48], proofs[i], 48); }
-    Workspace* wsp = acquire(mode == 1 ? N : 1, true);
+    // mode 1: the blobs pass through the workspace in chunks (only their challenge z and evaluation y are kept), so that a
+    // large batch neither allocates nor retains a workspace of its own size (the reference accepts any length)
+    const int chunk = mode == 1 ? std::min(N, chunk_capacity()) : 1;
+    Workspace* wsp = acquire(chunk, true);
     if (!wsp) return Status::Error("allocation failed");
     Workspace& ws = *wsp;
     cudaStream_t st = ws.stream;
@@ -275,13 +278,17 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
                 EKZG_CUDA(launch_scalars_from_be(d_zb, d_z, d_stz, N, st));
                 EKZG_CUDA(launch_scalars_from_be(d_yb, d_y, d_sty, N, st));
             } else {
-                for (int i = 0; i < N; i++) memcpy(ws.h_blobs + (size_t)i * BYTES_PER_BLOB, blobs[i], BYTES_PER_BLOB);
-                EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)N * BYTES_PER_BLOB, cudaMemcpyHostToDevice, st));
-                EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * N, st));
-                EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs, ws.d_coeffs, nullptr, ws.d_status, T_, N, false, st));
-                EKZG_CUDA(launch_blob_challenge(ws.d_blobs, d_c, d_z, N, st));
-                EKZG_CUDA(launch_poly_eval(ws.d_coeffs, d_z, d_y, d_yb, N, st));
-                EKZG_CUDA(cudaMemcpyAsync(stb.data(), ws.d_status, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
+                for (int o = 0; o < N; o += chunk) {
+                    const int c = std::min(chunk, N - o);
+                    if (o) EKZG_CUDA(cudaStreamSynchronize(st));   // the staging buffer is reused
+                    for (int i = 0; i < c; i++) memcpy(ws.h_blobs + (size_t)i * BYTES_PER_BLOB, blobs[o + i], BYTES_PER_BLOB);
+                    EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)c * BYTES_PER_BLOB, cudaMemcpyHostToDevice, st));
+                    EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * c, st));
+                    EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs, ws.d_coeffs, nullptr, ws.d_status, T_, c, false, st));
+                    EKZG_CUDA(launch_blob_challenge(ws.d_blobs, d_c + (size_t)o * 48, d_z + o, c, st));
+                    EKZG_CUDA(launch_poly_eval(ws.d_coeffs, d_z + o, d_y + o, d_yb + (size_t)o * 32, c, st));
+                    EKZG_CUDA(cudaMemcpyAsync(stb.data() + o, ws.d_status, sizeof(uint32_t) * c, cudaMemcpyDeviceToHost, st));
+                }
             }
             uint8_t hash[32] = {0};
             if (N > 1) {

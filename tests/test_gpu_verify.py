@@ -125,7 +125,11 @@ def test_verify_config5_full_size(vec_ctx, pkg, nb):
     assert cref.verify_cell_kzg_proof_batch(C[sl], I[sl], bad[sl], PR[sl]) is False
 
 
-def test_verify_blob_proof_batch_synthetic(das_ctx, pkg):
+@pytest.mark.parametrize("chunk", [None, "4"], ids=["one_chunk", "chunks_of_4"])
+def test_verify_blob_proof_batch_synthetic(das_ctx, pkg, chunk, monkeypatch):
+    """(chunks_of_4: the blobs of a batch pass through the workspace in chunks, EKZG_CHUNK -- 9 blobs = 4 + 4 + 1)"""
+    if chunk:
+        monkeypatch.setenv("EKZG_CHUNK", chunk)
     syn = importlib.import_module("eth_kzg_b200.synthetic")
     nb = 9
     blobs = [syn.blob(900 + i) for i in range(nb)]
