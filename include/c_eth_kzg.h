@@ -177,6 +177,8 @@ CResult eth_kzg_b200_debug_g1_ntt_prefix(const DASContext *ctx, const uint8_t *b
 /* Test hook (host only): prod_i e(P_i, Q_i) == 1.  g1_xy: 96 B per point (x then y, plain little-endian 64-bit limbs,
  * all zero = identity); g2_sel[i]: 0 [1]_2, 1 [tau]_2, 2 [tau^64]_2, +3 for the negated point.  Returns 1/0. */
 int eth_kzg_b200_debug_pairing_check(int n, const uint8_t *g1_xy, const int *g2_sel);
+/* Test hook (host only): the pairing's sparse line product and cyclotomic squaring against its general Fp12 routines; 1 = agree. */
+int eth_kzg_b200_debug_pairing_selftest(void);
 
 /* Test hook (host only): SHA-256 of data[0..n) through the library's transcript hasher (x86 SHA extensions when
  * present), fed as two updates split at `split`; force_portable != 0 runs the portable C block function instead. */

@@ -215,6 +215,9 @@ int eth_kzg_b200_debug_pairing_check(int n, const uint8_t* g1_xy, const int* g2_
     return ekzg::host::pairing_check(in.data(), n) ? 1 : 0;
 }
 
+// Test hook (host only): the pairing's shortcut routines against its general ones; 1 = they agree
+int eth_kzg_b200_debug_pairing_selftest(void) { return ekzg::host::pairing_selftest() ? 1 : 0; }
+
 CResult eth_kzg_blob_to_kzg_commitment(const DASContext* ctx, const uint8_t* blob, uint8_t* out) {
     DeviceGuard guard;
     return to_c(next_cx(ctx).blob_to_kzg_commitment_batch(1, blob, out, nullptr));

@@ -7,6 +7,7 @@
 //   the CPU (SURVEY.md §2.2 "(host) 2-pairing check").
 // Tower: Fp2 = Fp[u]/(u^2+1), Fp6 = Fp2[v]/(v^3-(1+u)), Fp12 = Fp6[w]/(w^2-v).  Fp: 6x64-bit Montgomery.
 #include "host_pairing.h"
+#include <immintrin.h>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -29,35 +30,52 @@ static inline void sub_p(uint64_t* t) {
     uint64_t br = 0;
     for (int i = 0; i < 6; i++) { u128 d = (u128)t[i] - FP_P[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
 }
+// branch-free: the tower arithmetic of one pairing check does ~100 k of these against ~24 k multiplications
 static inline void fp_add(Fp& r, const Fp& a, const Fp& b) {
-    uint64_t t[6]; u128 c = 0;
-    for (int i = 0; i < 6; i++) { c += (u128)a.v[i] + b.v[i]; t[i] = (uint64_t)c; c >>= 64; }
-    if (ge_p(t)) sub_p(t);
-    memcpy(r.v, t, 48);
+    unsigned long long t[6], s[6];
+    unsigned char c = 0, br = 0;
+    for (int i = 0; i < 6; i++) c = _addcarry_u64(c, a.v[i], b.v[i], &t[i]);       // a, b < p < 2^381: no carry out
+    for (int i = 0; i < 6; i++) br = _subborrow_u64(br, t[i], FP_P[i], &s[i]);
+    for (int i = 0; i < 6; i++) r.v[i] = br ? t[i] : s[i];                         // borrow <=> t < p
 }
 static inline void fp_sub(Fp& r, const Fp& a, const Fp& b) {
-    uint64_t t[6], br = 0;
-    for (int i = 0; i < 6; i++) { u128 d = (u128)a.v[i] - b.v[i] - br; t[i] = (uint64_t)d; br = (uint64_t)(d >> 64) & 1; }
-    if (br) { u128 c = 0; for (int i = 0; i < 6; i++) { c += (u128)t[i] + FP_P[i]; t[i] = (uint64_t)c; c >>= 64; } }
-    memcpy(r.v, t, 48);
+    unsigned long long t[6];
+    unsigned char br = 0, c = 0;
+    for (int i = 0; i < 6; i++) br = _subborrow_u64(br, a.v[i], b.v[i], &t[i]);
+    const uint64_t mask = 0 - (uint64_t)br;                                        // a < b: add p back
+    for (int i = 0; i < 6; i++) { c = _addcarry_u64(c, t[i], FP_P[i] & mask, &t[i]); r.v[i] = t[i]; }
 }
 static inline void fp_neg(Fp& r, const Fp& a) {
-    if (fp_is_zero(a)) { r = a; return; }
-    Fp z; memset(&z, 0, sizeof z); fp_sub(r, z, a);
+    Fp z; memset(&z, 0, sizeof z);
+    const uint64_t nz = fp_is_zero(a) ? 0 : ~0ull;                                 // -0 = 0, not p
+    unsigned long long t[6];
+    unsigned char br = 0;
+    for (int i = 0; i < 6; i++) { br = _subborrow_u64(br, FP_P[i] & nz, a.v[i], &t[i]); r.v[i] = t[i]; }
 }
-static inline void fp_mul(Fp& r, const Fp& a, const Fp& b) {  // CIOS
-    uint64_t t[8] = {0};
+// CIOS with the two carry chains of a row interleaved; p < 2^381 leaves three spare bits in the top word, so a row never carries
+// out of t5 (the "no-carry" variant) and one conditional subtraction finishes
+#define EKZG_MAC(lo, hi, a, b, c, d) { const u128 x_ = (u128)(a) * (b) + (c) + (d); lo = (uint64_t)x_; hi = (uint64_t)(x_ >> 64); }
+static inline void fp_mul(Fp& r, const Fp& a, const Fp& b) {
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0;
+#pragma GCC unroll 6
     for (int i = 0; i < 6; i++) {
-        u128 c = 0;
-        for (int j = 0; j < 6; j++) { c += (u128)a.v[j] * b.v[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
-        c += t[6]; t[6] = (uint64_t)c; t[7] = (uint64_t)(c >> 64);
-        uint64_t m = t[0] * FP_M0;
-        c = ((u128)m * FP_P[0] + t[0]) >> 64;
-        for (int j = 1; j < 6; j++) { c += (u128)m * FP_P[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
-        c += t[6]; t[5] = (uint64_t)c; t[6] = t[7] + (uint64_t)(c >> 64);
+        const uint64_t bi = b.v[i];
+        uint64_t c, c2, lo;
+        EKZG_MAC(t0, c, a.v[0], bi, t0, 0);
+        const uint64_t m = t0 * FP_M0;
+        EKZG_MAC(lo, c2, m, FP_P[0], t0, 0);
+        EKZG_MAC(t1, c, a.v[1], bi, t1, c); EKZG_MAC(t0, c2, m, FP_P[1], t1, c2);
+        EKZG_MAC(t2, c, a.v[2], bi, t2, c); EKZG_MAC(t1, c2, m, FP_P[2], t2, c2);
+        EKZG_MAC(t3, c, a.v[3], bi, t3, c); EKZG_MAC(t2, c2, m, FP_P[3], t3, c2);
+        EKZG_MAC(t4, c, a.v[4], bi, t4, c); EKZG_MAC(t3, c2, m, FP_P[4], t4, c2);
+        EKZG_MAC(t5, c, a.v[5], bi, t5, c); EKZG_MAC(t4, c2, m, FP_P[5], t5, c2);
+        t5 = c + c2;
+        (void)lo;
     }
-    if (t[6] || ge_p(t)) sub_p(t);
-    memcpy(r.v, t, 48);
+    unsigned long long t[6] = {t0, t1, t2, t3, t4, t5}, s[6];
+    unsigned char br = 0;
+    for (int i = 0; i < 6; i++) br = _subborrow_u64(br, t[i], FP_P[i], &s[i]);
+    for (int i = 0; i < 6; i++) r.v[i] = br ? t[i] : s[i];
 }
 static inline void fp_sqr(Fp& r, const Fp& a) { fp_mul(r, a, a); }
 static Fp fp_from_plain(const uint64_t* x) { Fp a, r2; memcpy(a.v, x, 48); memcpy(r2.v, FP_R2, 48); Fp o; fp_mul(o, a, r2); return o; }
@@ -141,6 +159,53 @@ static void f12_sqr(Fp12& r, const Fp12& a) {  // complex squaring: 2 Fp6 mul
     f6_sub(s, s, ab); f6_mul_v(v, ab); f6_sub(s, s, v);
     r.c0 = s; f6_add(r.c1, ab, ab);
 }
+// a * (b0 + b1 v) in Fp6: five Fp2 multiplications
+static void f6_mul_sparse2(Fp6& r, const Fp6& a, const Fp2& b0, const Fp2& b1) {
+    Fp2 v0, v1, t, s, o0, o1, o2;
+    f2_mul(v0, a.a0, b0); f2_mul(v1, a.a1, b1);
+    f2_mul(t, a.a2, b1); f2_mul_xi(t, t); f2_add(o0, v0, t);
+    f2_add(s, a.a0, a.a1); f2_add(t, b0, b1); f2_mul(t, s, t); f2_sub(t, t, v0); f2_sub(o1, t, v1);
+    f2_mul(t, a.a2, b0); f2_add(o2, t, v1);
+    r.a0 = o0; r.a1 = o1; r.a2 = o2;
+}
+// f * ((A + B v) + (C v) w) with C in Fp: the value of a Miller-loop line at a G1 point.  36 Fp multiplications instead of the 54
+// of a general Fp12 product.
+static void f12_mul_line(Fp12& f, const Fp2& A, const Fp2& B, const Fp& C) {
+    Fp6 t0, t1, s, m, v;
+    f6_mul_sparse2(t0, f.c0, A, B);
+    Fp2 x;
+    f2_mul_fp(x, f.c1.a2, C); f2_mul_xi(t1.a0, x); f2_mul_fp(t1.a1, f.c1.a0, C); f2_mul_fp(t1.a2, f.c1.a1, C);   // c1 * (C v)
+    Fp2 bc = B;
+    fp_add(bc.c0, bc.c0, C);
+    f6_add(s, f.c0, f.c1);
+    f6_mul_sparse2(m, s, A, bc);
+    f6_sub(m, m, t0); f6_sub(m, m, t1);
+    f6_mul_v(v, t1);
+    f6_add(f.c0, t0, v); f.c1 = m;
+}
+// squaring in the cyclotomic subgroup (Granger-Scott: three Fp4 squarings, 18 Fp multiplications instead of 36).  Only valid after
+// the easy part of the final exponentiation.
+static inline void fp4_square(Fp2& c0, Fp2& c1, const Fp2& a, const Fp2& b) {
+    Fp2 t0, t1, t2;
+    f2_sqr(t0, a); f2_sqr(t1, b);
+    f2_mul_xi(t2, t1); f2_add(c0, t2, t0);
+    f2_add(t2, a, b); f2_sqr(t2, t2); f2_sub(t2, t2, t0); f2_sub(c1, t2, t1);
+}
+static void f12_cyc_sqr(Fp12& r, const Fp12& f) {
+    Fp2 z0 = f.c0.a0, z4 = f.c0.a1, z3 = f.c0.a2, z2 = f.c1.a0, z1 = f.c1.a1, z5 = f.c1.a2;
+    Fp2 t0, t1, t2, t3;
+    fp4_square(t0, t1, z0, z1);
+    f2_sub(z0, t0, z0); f2_add(z0, z0, z0); f2_add(z0, z0, t0);     // 3 t0 - 2 z0
+    f2_add(z1, t1, z1); f2_add(z1, z1, z1); f2_add(z1, z1, t1);     // 3 t1 + 2 z1
+    fp4_square(t0, t1, z2, z3);
+    fp4_square(t2, t3, z4, z5);
+    f2_sub(z4, t0, z4); f2_add(z4, z4, z4); f2_add(z4, z4, t0);
+    f2_add(z5, t1, z5); f2_add(z5, z5, z5); f2_add(z5, z5, t1);
+    f2_mul_xi(t0, t3);
+    f2_add(z2, t0, z2); f2_add(z2, z2, z2); f2_add(z2, z2, t0);
+    f2_sub(z3, t2, z3); f2_add(z3, z3, z3); f2_add(z3, z3, t2);
+    r.c0.a0 = z0; r.c0.a1 = z4; r.c0.a2 = z3; r.c1.a0 = z2; r.c1.a1 = z1; r.c1.a2 = z5;
+}
 static void f12_conj(Fp12& r, const Fp12& a) { r.c0 = a.c0; f6_neg(r.c1, a.c1); }
 static void f12_inv(Fp12& r, const Fp12& a) {
     Fp6 t0, t1;
@@ -194,7 +259,7 @@ static void f12_frob1(Fp12& r, const Fp12& a) {
 static void f12_exp_x(Fp12& r, const Fp12& a) {
     Fp12 acc = a;
     for (int bit = 62; bit >= 0; bit--) {
-        f12_sqr(acc, acc);
+        f12_cyc_sqr(acc, acc);
         if ((BLS_X_ABS >> bit) & 1) f12_mul(acc, acc, a);
     }
     f12_conj(r, acc);
@@ -284,10 +349,14 @@ static void init_state() {
     s.ok = ok;
 }
 
+namespace {
+struct Pt { Fp x, y; const std::vector<Line>* ls; };   // affine, Montgomery form
+bool pairing_product_is_one(const std::vector<Pt>& pts);
+}
+
 bool pairing_check(const PairingInput* in, int n) {
     std::call_once(g_once, init_state);
     if (!g_state.ok) return false;
-    struct Pt { Fp x, y; const std::vector<Line>* ls; };
     std::vector<Pt> pts;
     for (int i = 0; i < n; i++) {
         if (in[i].g1_is_identity) continue;  // e(O, Q) = 1 (blstrs skips identity pairs as well)
@@ -296,6 +365,29 @@ bool pairing_check(const PairingInput* in, int n) {
         p.ls = &g_state.lines[(int)in[i].g2];
         pts.push_back(p);
     }
+    return pairing_product_is_one(pts);
+}
+
+bool pairing_check_jac(const PairingInputJac* in, int n) {
+    std::call_once(g_once, init_state);
+    if (!g_state.ok) return false;
+    std::vector<Pt> pts;
+    for (int i = 0; i < n; i++) {
+        if (in[i].g1_is_identity) continue;
+        Fp X, Y, Z, zi, zi2, zi3;
+        memcpy(X.v, in[i].x, 48); memcpy(Y.v, in[i].y, 48); memcpy(Z.v, in[i].z, 48);
+        if (fp_is_zero(Z)) continue;
+        fp_inv(zi, Z); fp_sqr(zi2, zi); fp_mul(zi3, zi2, zi);
+        Pt p;
+        fp_mul(p.x, X, zi2); fp_mul(p.y, Y, zi3);
+        p.ls = &g_state.lines[(int)in[i].g2];
+        pts.push_back(p);
+    }
+    return pairing_product_is_one(pts);
+}
+
+namespace {
+bool pairing_product_is_one(const std::vector<Pt>& pts) {
     Fp12 f = f12_one();
     size_t idx = 0;
     for (int bit = 62; bit >= 0; bit--) {
@@ -304,12 +396,9 @@ bool pairing_check(const PairingInput* in, int n) {
         for (int sidx = 0; sidx < steps; sidx++, idx++) {
             for (const Pt& p : pts) {
                 const Line& l = (*p.ls)[idx];
-                Fp12 lf;
-                memset(&lf, 0, sizeof lf);
-                lf.c0.a0 = l.c;
-                f2_mul_fp(lf.c0.a1, l.lam, p.x); f2_neg(lf.c0.a1, lf.c0.a1);
-                lf.c1.a1.c0 = p.y;
-                f12_mul(f, f, lf);
+                Fp2 b;
+                f2_mul_fp(b, l.lam, p.x); f2_neg(b, b);
+                f12_mul_line(f, l.c, b, p.y);
             }
         }
     }
@@ -328,8 +417,41 @@ bool pairing_check(const PairingInput* in, int n) {
     f12_exp_x(e1, b); f12_exp_x(e1, e1); f12_frob2(e2, b); f12_mul(c, e1, e2);
     f12_conj(e2, b); f12_mul(c, c, e2);                             // ^(x^2+p^2-1)
     Fp12 acc;
-    f12_sqr(acc, t); f12_mul(acc, acc, t); f12_mul(acc, acc, c);    // * t^3
+    f12_cyc_sqr(acc, t); f12_mul(acc, acc, t); f12_mul(acc, acc, c);    // * t^3
     return f12_is_one(acc);
+}
+}  // namespace
+
+// The shortcuts above against the general routines, on values from a real Miller loop: the line product against a full Fp12
+// product with the sparse element written out, the cyclotomic squaring against the general one after the easy part.
+bool pairing_selftest() {
+    std::call_once(g_once, init_state);
+    if (!g_state.ok) return false;
+    Fp12 f = f12_one();
+    Fp px = fp_from_plain(FP_P), py = fp_one();   // any field elements will do (px = p mod p = 0 is avoided below)
+    fp_add(px, py, py); fp_add(py, px, py);       // px = 2, py = 3 (Montgomery form)
+    const std::vector<Line>& ls = g_state.lines[1];
+    for (size_t i = 0; i < 24 && i < ls.size(); i++) {
+        Fp2 b;
+        f2_mul_fp(b, ls[i].lam, px); f2_neg(b, b);
+        Fp12 lf, want;
+        memset(&lf, 0, sizeof lf);
+        lf.c0.a0 = ls[i].c; lf.c0.a1 = b; lf.c1.a1.c0 = py;
+        f12_sqr(f, f);
+        f12_mul(want, f, lf);
+        f12_mul_line(f, ls[i].c, b, py);
+        if (memcmp(&f, &want, sizeof f) != 0) return false;
+    }
+    Fp12 t, u;
+    f12_conj(t, f); f12_inv(u, f); f12_mul(t, t, u);
+    f12_frob2(u, t); f12_mul(t, u, t);            // now in the cyclotomic subgroup
+    for (int i = 0; i < 8; i++) {
+        Fp12 a, b;
+        f12_sqr(a, t); f12_cyc_sqr(b, t);
+        if (memcmp(&a, &b, sizeof a) != 0) return false;
+        f12_mul(t, a, f12_is_one(a) ? a : t);
+    }
+    return true;
 }
 
 }  // namespace host

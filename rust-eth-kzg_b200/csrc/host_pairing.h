@@ -17,5 +17,16 @@ struct PairingInput {
 // prod_i e(P_i, Q_i) == 1
 bool pairing_check(const PairingInput* in, int n);
 
+// the same for G1 points as the device leaves them: Jacobian coordinates in Montgomery form (R = 2^384, 6 x 64-bit limbs);
+// the host normalises (one inversion per point)
+struct PairingInputJac {
+    uint64_t x[6], y[6], z[6];
+    bool g1_is_identity;
+    G2Sel g2;
+};
+bool pairing_check_jac(const PairingInputJac* in, int n);
+// the sparse line product and the cyclotomic squaring against the general Fp12 routines (test hook)
+bool pairing_selftest();
+
 }  // namespace host
 }  // namespace ekzg

@@ -41,6 +41,7 @@ cudaError_t launch_scalars_from_be(const uint8_t* in, Fr* out, uint32_t* status,
 cudaError_t launch_quotient(const Fr* coeffs, const Fr* z, uint32_t* scalars, uint8_t* y_out, int B, cudaStream_t st);
 cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B, cudaStream_t st);
 cudaError_t launch_sum_positions(G1Jac* pts, int B, int count, int stride, cudaStream_t st);
+cudaError_t launch_g1_subgroup(const G1Affine* pts, uint32_t* status, int n, const G1Affine* pts2, uint32_t* status2, int n2, cudaStream_t st);   // status 2 where a decompressed point is outside G1
 cudaError_t launch_g1_validate(const uint8_t* in, G1Affine* out, uint32_t* status, int n, bool check_subgroup, cudaStream_t st);
 
 // kzg_kernels_recover.cu
@@ -59,6 +60,7 @@ cudaError_t launch_sum_points(const G1Jac* in, int n, G1Jac* scratch, G1Jac* out
 cudaError_t launch_cell_interp(const uint8_t* cells, const uint32_t* col, const Fr* rpow, Fr* interp, uint32_t* status, const DevTables& T,
                                int n, cudaStream_t st);
 cudaError_t launch_interp_column_sum(const Fr* interp, uint32_t* out, int n, cudaStream_t st);
+constexpr int PAIRING_INPUT_WORDS = 37;   // per point: Jacobian X, Y, Z (Montgomery limbs) + identity flag
 cudaError_t launch_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* b1, const G1Jac* b2, uint32_t* out, cudaStream_t st);
 cudaError_t launch_kzg_verify_terms(const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* rpow, G1Jac* L,
                                     G1Jac* R, int n, cudaStream_t st);

@@ -215,6 +215,20 @@ k_g1_validate(const uint8_t* __restrict__ in, G1Affine* __restrict__ out, uint32
     st_vec(&out[i], a);
 }
 
+// the prime-order subgroup check on its own (points already decompressed by k_g1_validate with check_subgroup = 0): the verifiers
+// run it on a side stream, beside the scalar multiplications that only need the coordinates.  status: 2 = not in G1.
+// (two arrays in one launch: a small call is latency-bound, and a second launch behind the first would double it)
+__global__ void __launch_bounds__(64)
+k_g1_subgroup(const G1Affine* __restrict__ pts, uint32_t* __restrict__ status, int n, const G1Affine* __restrict__ pts2,
+              uint32_t* __restrict__ status2, int n2) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n + n2) return;
+    if (i >= n) { i -= n; pts = pts2; status = status2; }
+    if (status[i] != 0) return;
+    const G1Affine a = ld_vec(&pts[i]);
+    if (!g1a_is_inf(a) && !g1a_in_subgroup(a)) status[i] = 2;
+}
+
 // ------------------------------------------------------------------------------------------------
 
 cudaError_t launch_blob_challenge(const uint8_t* blobs, const uint8_t* commitments, Fr* z, int B, cudaStream_t st) {
@@ -240,6 +254,11 @@ cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B,
 }
 cudaError_t launch_sum_positions(G1Jac* pts, int B, int count, int stride, cudaStream_t st) {
     k_sum_positions<<<(B + 63) / 64, 64, 0, st>>>(pts, B, count, stride);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
+cudaError_t launch_g1_subgroup(const G1Affine* pts, uint32_t* status, int n, const G1Affine* pts2, uint32_t* status2, int n2, cudaStream_t st) {
+    k_g1_subgroup<<<(n + n2 + 63) / 64, 64, 0, st>>>(pts, status, n, pts2, status2, n2);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }

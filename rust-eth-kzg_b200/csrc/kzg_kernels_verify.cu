@@ -148,6 +148,40 @@ k_scalar_mul(const G1Affine* __restrict__ pts, const uint32_t* __restrict__ scal
     st_vec(&out[i], r);
 }
 
+// the same with the two GLV halves of every multiplication on two lanes (small batches: the call is bound by the latency of ONE
+// ladder, and half the additions of a ladder are the other half's).  Thread 2i + h: half h of item i; the pair meets through
+// shared memory.
+__global__ void __launch_bounds__(64)
+k_scalar_mul_split(const G1Affine* __restrict__ pts, const uint32_t* __restrict__ scalars, G1Jac* __restrict__ out, int n) {
+    __shared__ G1Jac part[32];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t >> 1, h = t & 1;
+    const bool live = i < n;
+    G1Jac r;
+    jac_set_inf(r);
+    if (live) {
+        G1Affine a = ld_vec(&pts[i]);
+        if (!g1a_is_inf(a)) {
+            G1Jac p;
+            jac_from_affine(p, a);
+            uint32_t k[8];
+            const uint4* s4 = reinterpret_cast<const uint4*>(scalars + (size_t)i * 8);
+            uint4 lo = s4[0], hi = s4[1];
+            k[0] = lo.x; k[1] = lo.y; k[2] = lo.z; k[3] = lo.w; k[4] = hi.x; k[5] = hi.y; k[6] = hi.z; k[7] = hi.w;
+            int8_t d[66];
+            glv_split_digits(d, k);
+            if (h) jac_endo(p, p);
+            jac_mul_half16(r, p, d + 33 * h);
+        }
+    }
+    if (h) part[threadIdx.x >> 1] = r;
+    __syncthreads();
+    if (live && !h) {
+        jac_add(r, part[threadIdx.x >> 1]);
+        st_vec(&out[i], r);
+    }
+}
+
 // partial[blockIdx] = sum of in[i] for i = blockIdx*blockDim + tid, strided by the whole grid; block tree in shared memory
 __global__ void __launch_bounds__(128)
 k_reduce_points(const G1Jac* __restrict__ in, G1Jac* __restrict__ partial, int n) {
@@ -232,10 +266,11 @@ k_interp_column_sum(const Fr* __restrict__ interp, uint32_t* __restrict__ out, i
 
 // Final G1 points of a pairing check, as plain affine coordinates for the host:
 //   out[0] = a0 ;  out[1] = b0 - b1 + b2      (each term may be null = identity)
-// layout per point: 12 limbs x, 12 limbs y (plain, little-endian 32-bit) + 1 word identity flag = 25 words
+// layout per point: X, Y, Z of the Jacobian point (12 limbs each, Montgomery form, little-endian 32-bit) + 1 word identity flag
+// = 37 words.  The normalisation (one inversion: ~0.4 ms for a lone device thread, ~25 us on the host) is left to the host, which
+// works on the same Montgomery representation (R = 2^384 on both sides).
 __global__ void k_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* b1, const G1Jac* b2, uint32_t* __restrict__ out) {
-    // two CTAs, one point each (the inversions are the whole cost)
-    if (threadIdx.x != 0 || blockIdx.x > 1) return;
+    if (threadIdx.x != 0 || blockIdx.x > 1) return;   // two CTAs, one point each
     const int i = blockIdx.x;
     G1Jac pt;
     if (i == 0) {
@@ -246,23 +281,9 @@ __global__ void k_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* 
         if (b1) { G1Jac q = ld_vec(b1); jac_neg(q, q); jac_add(pt, q); }
         if (b2) { G1Jac q = ld_vec(b2); jac_add(pt, q); }
     }
-    {
-        uint32_t* o = out + 25 * i;
-        if (jac_is_inf(pt)) {
-            for (int l = 0; l < 24; l++) o[l] = 0;
-            o[24] = 1;
-            return;
-        }
-        Fp zi;
-        fp_inv(zi, pt.z);
-        G1Affine a;
-        jac_to_affine_with_inv(a, pt, zi);
-        Fp x, y;
-        fe_from_mont(x, a.x);
-        fe_from_mont(y, a.y);
-        for (int l = 0; l < 12; l++) { o[l] = x.v[l]; o[12 + l] = y.v[l]; }
-        o[24] = 0;
-    }
+    uint32_t* o = out + PAIRING_INPUT_WORDS * i;
+    for (int l = 0; l < 12; l++) { o[l] = pt.x.v[l]; o[12 + l] = pt.y.v[l]; o[24 + l] = pt.z.v[l]; }
+    o[36] = jac_is_inf(pt) ? 1u : 0u;
 }
 
 // EIP-4844 single / batched proof verification inputs (kzg_single_open/src/verifier.rs:33-108), rewritten so that only G1
@@ -358,7 +379,10 @@ cudaError_t launch_column_sums(const G1Jac* prods, const uint32_t* col, G1Jac* c
     return cudaSuccess;
 }
 cudaError_t launch_scalar_mul(const G1Affine* pts, const uint32_t* scalars, G1Jac* out, int n, cudaStream_t st) {
-    k_scalar_mul<<<(n + 63) / 64, 64, 0, st>>>(pts, scalars, out, n);
+    // up to 8192 items the machine has lanes to spare (2 x 8192 threads per pass, two passes at a time): split every
+    // multiplication over two lanes; above that one lane per item keeps the passes to one wave
+    if (n <= 8192) k_scalar_mul_split<<<(2 * n + 63) / 64, 64, 0, st>>>(pts, scalars, out, n);
+    else k_scalar_mul<<<(n + 63) / 64, 64, 0, st>>>(pts, scalars, out, n);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }

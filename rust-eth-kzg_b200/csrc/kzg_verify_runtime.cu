@@ -36,19 +36,20 @@ struct Scratch {
 
 void be64(uint8_t* o, uint64_t v) { for (int i = 0; i < 8; i++) o[i] = (uint8_t)(v >> (56 - 8 * i)); }
 
-bool run_pairing(const uint32_t* w /*2 x 25 words*/, host::G2Sel q0, host::G2Sel q1) {
-    host::PairingInput in[2];
+bool run_pairing(const uint32_t* w /*2 x PAIRING_INPUT_WORDS*/, host::G2Sel q0, host::G2Sel q1) {
+    host::PairingInputJac in[2];
     for (int i = 0; i < 2; i++) {
-        const uint32_t* o = w + 25 * i;
+        const uint32_t* o = w + PAIRING_INPUT_WORDS * i;
         for (int l = 0; l < 6; l++) {
-            in[i].g1_x[l] = (uint64_t)o[2 * l] | ((uint64_t)o[2 * l + 1] << 32);
-            in[i].g1_y[l] = (uint64_t)o[12 + 2 * l] | ((uint64_t)o[12 + 2 * l + 1] << 32);
+            in[i].x[l] = (uint64_t)o[2 * l] | ((uint64_t)o[2 * l + 1] << 32);
+            in[i].y[l] = (uint64_t)o[12 + 2 * l] | ((uint64_t)o[12 + 2 * l + 1] << 32);
+            in[i].z[l] = (uint64_t)o[24 + 2 * l] | ((uint64_t)o[24 + 2 * l + 1] << 32);
         }
-        in[i].g1_is_identity = o[24] != 0;
+        in[i].g1_is_identity = o[36] != 0;
     }
     in[0].g2 = q0;
     in[1].g2 = q1;
-    return host::pairing_check(in, 2);
+    return host::pairing_check_jac(in, 2);
 }
 
 }  // namespace
@@ -136,7 +137,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
     if (!wsp) { hash_task.wait(); return Status::Error("allocation failed"); }
     cudaStream_t st = wsp->stream;
     Status result = Status::Ok();
-    uint32_t pin[50];
+    uint32_t pin[2 * PAIRING_INPUT_WORDS];
     std::vector<uint32_t> stc(M), stp(N);
     uint32_t cell_status = 0;
     {
@@ -151,7 +152,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_TRY(S.get(&d_c, (size_t)M * 48)); EKZG_TRY(S.get(&d_p, (size_t)N * 48)); EKZG_TRY(S.get(&d_cells, (size_t)N * BYTES_PER_CELL));
             EKZG_TRY(S.get(&d_hash, 32)); EKZG_TRY(S.get(&d_col, N)); EKZG_TRY(S.get(&d_row, N)); EKZG_TRY(S.get(&d_stc, M)); EKZG_TRY(S.get(&d_stp, N));
             EKZG_TRY(S.get(&d_cellst, 1)); EKZG_TRY(S.get(&d_s1, (size_t)N * 8)); EKZG_TRY(S.get(&d_s2, (size_t)N * 8)); EKZG_TRY(S.get(&d_w, (size_t)M * 8));
-            EKZG_TRY(S.get(&d_i, 64 * 8)); EKZG_TRY(S.get(&d_out, 50)); EKZG_TRY(S.get(&a_c, M)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_rpow, N));
+            EKZG_TRY(S.get(&d_i, 64 * 8)); EKZG_TRY(S.get(&d_out, 2 * PAIRING_INPUT_WORDS)); EKZG_TRY(S.get(&a_c, M)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_rpow, N));
             EKZG_TRY(S.get(&d_interp, (size_t)N * 64)); EKZG_TRY(S.get(&d_mul, std::max(N, 128))); EKZG_TRY(S.get(&d_mul_b, std::max(M, 128))); EKZG_TRY(S.get(&d_mul_c, 128)); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_part_b, 148)); EKZG_TRY(S.get(&d_mul_d, std::max(N, 128))); EKZG_TRY(S.get(&d_part_d, 148)); EKZG_TRY(S.get(&d_sums, 4));
             EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
@@ -159,9 +160,15 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_CUDA(cudaMemcpyAsync(d_col, hcol.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_row, rows.data(), sizeof(uint32_t) * N, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemsetAsync(d_cellst, 0, 4, st));
-            // point validation runs while the host hashes the transcript
-            EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, M, true, st));
-            EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, true, st));
+            // point validation runs while the host hashes the transcript: decompression here; the subgroup checks (twice the
+            // work, and nothing downstream needs their result before the final read-back) on a side stream, where for a small
+            // call they run beside the scalar multiplications instead of in front of them
+            cudaStream_t sb = wsp->copy_stream, sc = wsp->in_stream, sd = wsp->aux_stream;
+            EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, false, st));
+            EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, M, false, st));
+            EKZG_CUDA(cudaEventRecord(wsp->sub_ready[1], st));
+            EKZG_CUDA(cudaStreamWaitEvent(sc, wsp->sub_ready[1], 0));
+            EKZG_CUDA(launch_g1_subgroup(a_p, d_stp, N, a_c, d_stc, M, sc));
             tr.mark("alloc + enqueue copies/validation");
             const std::array<uint8_t, 32> hash_arr = hash_task.get();
             const uint8_t* hash = hash_arr.data();
@@ -171,7 +178,6 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_CUDA(launch_cell_verify_scalars(d_rpow, d_col, d_s1, d_s2, T_, N, st));
             // Independent, latency-bound chains follow (a handful of CTAs each: one 255-bit scalar multiplication takes ~3 ms
             // whatever the count): they run side by side on the workspace's four streams.
-            cudaStream_t sb = wsp->copy_stream, sc = wsp->in_stream, sd = wsp->aux_stream;
             EKZG_CUDA(cudaEventRecord(wsp->sub_ready[0], st));
             EKZG_CUDA(cudaStreamWaitEvent(sb, wsp->sub_ready[0], 0));
             EKZG_CUDA(cudaStreamWaitEvent(sc, wsp->sub_ready[0], 0));
@@ -251,7 +257,7 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
     Workspace& ws = *wsp;
     cudaStream_t st = ws.stream;
     Status result = Status::Ok();
-    uint32_t pin[50];
+    uint32_t pin[2 * PAIRING_INPUT_WORDS];
     std::vector<uint32_t> stc(N), stp(N), stb(N, 0), stz(N, 0), sty(N, 0);
     {
         Scratch S(st);
@@ -263,14 +269,19 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
             G1Jac *d_L, *d_R, *d_part, *d_sums;
             EKZG_TRY(S.get(&d_c, (size_t)N * 48)); EKZG_TRY(S.get(&d_p, (size_t)N * 48)); EKZG_TRY(S.get(&d_zb, (size_t)N * 32)); EKZG_TRY(S.get(&d_yb, (size_t)N * 32));
             EKZG_TRY(S.get(&d_hash, 32)); EKZG_TRY(S.get(&d_stc, N)); EKZG_TRY(S.get(&d_stp, N)); EKZG_TRY(S.get(&d_stz, N)); EKZG_TRY(S.get(&d_sty, N));
-            EKZG_TRY(S.get(&d_out, 50)); EKZG_TRY(S.get(&a_c, N)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_z, N)); EKZG_TRY(S.get(&d_y, N));
+            EKZG_TRY(S.get(&d_out, 2 * PAIRING_INPUT_WORDS)); EKZG_TRY(S.get(&a_c, N)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_z, N)); EKZG_TRY(S.get(&d_y, N));
             EKZG_TRY(S.get(&d_rpow, N)); EKZG_TRY(S.get(&d_L, N)); EKZG_TRY(S.get(&d_R, N)); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 2));
             EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemsetAsync(d_stz, 0, sizeof(uint32_t) * N, st));
             EKZG_CUDA(cudaMemsetAsync(d_sty, 0, sizeof(uint32_t) * N, st));
-            EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, N, true, st));
-            EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, true, st));
+            // decompression here, the subgroup checks beside the rest on a side stream (see verify_cell_kzg_proof_batch)
+            EKZG_CUDA(launch_g1_validate(d_c, a_c, d_stc, N, false, st));
+            EKZG_CUDA(launch_g1_validate(d_p, a_p, d_stp, N, false, st));
+            EKZG_CUDA(cudaEventRecord(ws.sub_ready[1], st));
+            EKZG_CUDA(cudaStreamWaitEvent(ws.copy_stream, ws.sub_ready[1], 0));
+            EKZG_CUDA(launch_g1_subgroup(a_c, d_stc, N, a_p, d_stp, N, ws.copy_stream));
+            EKZG_CUDA(cudaEventRecord(ws.sub_out[0], ws.copy_stream));
             std::vector<uint8_t> zb((size_t)N * 32), yb((size_t)N * 32);
             if (mode == 0) {
                 EKZG_CUDA(cudaMemcpyAsync(d_zb, z32, (size_t)N * 32, cudaMemcpyHostToDevice, st));
@@ -322,6 +333,7 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
             EKZG_CUDA(launch_sum_points(d_R, N, d_part, &d_sums[0], st));
             EKZG_CUDA(launch_sum_points(d_L, N, d_part, &d_sums[1], st));
             EKZG_CUDA(launch_pairing_inputs(&d_sums[0], &d_sums[1], nullptr, nullptr, d_out, st));
+            EKZG_CUDA(cudaStreamWaitEvent(st, ws.sub_out[0], 0));   // the subgroup verdicts
             EKZG_CUDA(cudaMemcpyAsync(pin, d_out, sizeof pin, cudaMemcpyDeviceToHost, st));
             EKZG_CUDA(cudaMemcpyAsync(stc.data(), d_stc, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
             EKZG_CUDA(cudaMemcpyAsync(stp.data(), d_stp, sizeof(uint32_t) * N, cudaMemcpyDeviceToHost, st));
@@ -331,7 +343,7 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
             return Status::Ok();
         };
         result = run();
-        if (!result.ok) cudaStreamSynchronize(st);
+        if (!result.ok) { cudaStreamSynchronize(ws.copy_stream); cudaStreamSynchronize(st); }
     }
     give_back(wsp);
     if (!result.ok) return result;

@@ -150,6 +150,14 @@ def test_device_entry_point_finds_the_owning_member(das_ctx, multi_ctx, pkg):
 
 
 def _sharded_worker(rank, world, port, n, backend, q):
+    try:
+        _sharded_worker_body(rank, world, port, n, backend, q)
+    except BaseException as ex:   # the parent must hear about it at once, not after its queue timeout
+        q.put(("error", "rank %d: %r" % (rank, ex)))
+        raise
+
+
+def _sharded_worker_body(rank, world, port, n, backend, q):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root)
@@ -190,7 +198,7 @@ def _sharded_worker(rank, world, port, n, backend, q):
 
 
 @pytest.mark.parametrize("n", [33, 70])
-def test_sharded_processes_gather_real_compute(n):
+def test_sharded_processes_gather_real_compute(n, precomp_holder):
     """sharding.py with the REAL per-shard computation (two processes, one DASContext each): NCCL over NVLink when the box has
     two GPUs, otherwise two processes on device 0 gathering through gloo.  Rank 0 compares the gathered batch with what one
     context computes for the whole batch."""
@@ -199,6 +207,7 @@ def test_sharded_processes_gather_real_compute(n):
     import torch.multiprocessing as mp
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
+    precomp_holder.release()   # the children build contexts of their own: give the 144 GiB of the shared production context back first
     backend = "nccl" if torch.cuda.device_count() >= 2 else "gloo"
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -208,9 +217,23 @@ def test_sharded_processes_gather_real_compute(n):
     procs = [mpc.Process(target=_sharded_worker, args=(r, 2, port, n, backend, q)) for r in range(2)]
     for p in procs:
         p.start()
-    ok_bytes, ok_rows = q.get(timeout=600)
+    import queue as _queue
+    import time
+    res, deadline = None, time.monotonic() + 600
+    while res is None and time.monotonic() < deadline:
+        try:
+            res = q.get(timeout=2)
+        except _queue.Empty:
+            if all(p.exitcode is not None for p in procs):   # both children are gone and said nothing
+                break
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=120 if res is not None and res[0] != "error" else 5)
+        if p.is_alive():
+            p.terminate()
+    assert res is not None, "the sharding processes ended without a result (exit codes %r)" % [p.exitcode for p in procs]
+    assert res[0] != "error", res[1]
+    ok_bytes, ok_rows = res
+    for p in procs:
         assert p.exitcode == 0
     assert ok_bytes, "byte-level gather differs from the single-context batch"
     assert ok_rows, "tensor-level gather differs from the single-context batch"

@@ -59,3 +59,9 @@ def test_pairing_srs_relations(lib):
     assert _check(lib, [(s64, GEN + NEG), (s0, TAU64)]) == 1
     assert _check(lib, [(s64, GEN + NEG), (s0, TAU)]) == 0
     assert _check(lib, [(s1, TAU64), (s64, TAU + NEG), (None, GEN)]) == 1   # tau * tau^64 on both sides
+
+
+def test_pairing_shortcuts_agree_with_general_routines(lib):
+    """the sparse line product (36 instead of 54 Fp multiplications) and the Granger-Scott cyclotomic squaring (18 instead of 36)
+    against the general Fp12 product / squaring, on values from a real Miller loop"""
+    assert lib.eth_kzg_b200_debug_pairing_selftest() == 1
