@@ -62,8 +62,8 @@ cudaError_t launch_cell_interp(const uint8_t* cells, const uint32_t* col, const 
 cudaError_t launch_interp_column_sum(const Fr* interp, uint32_t* out, int n, cudaStream_t st);
 constexpr int PAIRING_INPUT_WORDS = 37;   // per point: Jacobian X, Y, Z (Montgomery limbs) + identity flag
 cudaError_t launch_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* b1, const G1Jac* b2, uint32_t* out, cudaStream_t st);
-cudaError_t launch_kzg_verify_terms(const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* rpow, G1Jac* L,
-                                    G1Jac* R, int n, cudaStream_t st);
+cudaError_t launch_kzg_verify_pairs(const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* rpow, G1Affine* pts,
+                                    uint32_t* scalars, int n, cudaStream_t st);   // 4n (point, scalar) pairs, kind-major
 cudaError_t launch_poly_eval(const Fr* coeffs, const Fr* z, Fr* y, uint8_t* y_be, int B, cudaStream_t st);
 cudaError_t launch_fr_to_be(const Fr* in, uint8_t* out, int n, cudaStream_t st);
 

@@ -91,7 +91,7 @@ __global__ void k_scalars_from_be(const uint8_t* __restrict__ in, Fr* __restrict
         const uint8_t* q = buf + 4 * (7 - l);
         x.v[l] = ((uint32_t)q[0] << 24) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 8) | q[3];
     }
-    if (fe_plain_ge_mod(x)) atomicOr(&status[i], 2u);
+    if (status && fe_plain_ge_mod(x)) atomicOr(&status[i], 2u);   // (status == nullptr: values known to be canonical)
     fe_to_mont(x, x);
     st_vec(&out[i], x);
 }

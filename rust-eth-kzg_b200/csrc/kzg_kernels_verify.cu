@@ -288,60 +288,68 @@ __global__ void k_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* 
 
 // EIP-4844 single / batched proof verification inputs (kzg_single_open/src/verifier.rs:33-108), rewritten so that only G1
 // arithmetic is needed:  e(sum r^i (C_i - y_i G + z_i pi_i), -[1]_2) * e(sum r^i pi_i, [tau]_2) == 1.
-// Per item i (thread i): L_i = r^i * (C_i - y_i*G + z_i*pi_i),  R_i = r^i * pi_i.
+// Per item i the four products  r^i * C_i,  (-r^i y_i) * G,  (r^i z_i) * pi_i  and  r^i * pi_i  are independent: this kernel only writes
+// them down as (point, scalar) pairs, kind-major (pair kind*n + i), and the generic scalar-multiplication kernel runs all 4n at once
+// (first version: one thread per item, four plain 255-bit ladders in a row -- 9 ms for a single proof).  The left sum is then the
+// sum of the first 3n products, the right sum that of the last n.
 __global__ void __launch_bounds__(64)
-k_kzg_verify_terms(const G1Affine* __restrict__ commitments, const G1Affine* __restrict__ proofs, const Fr* __restrict__ z,
-                   const Fr* __restrict__ y, const Fr* __restrict__ rpow, G1Jac* __restrict__ L, G1Jac* __restrict__ R, int n) {
+k_kzg_verify_pairs(const G1Affine* __restrict__ commitments, const G1Affine* __restrict__ proofs, const Fr* __restrict__ z,
+                   const Fr* __restrict__ y, const Fr* __restrict__ rpow, G1Affine* __restrict__ pts, uint32_t* __restrict__ scalars, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    Fr rho = ld_vec(&rpow[i]), zi = ld_vec(&z[i]), yi = ld_vec(&y[i]);
-    Fr rz, ry;
+    const Fr rho = ld_vec(&rpow[i]), zi = ld_vec(&z[i]), yi = ld_vec(&y[i]);
+    Fr rz, ry, p;
     fe_mul(rz, rho, zi);
     fe_mul(ry, rho, yi);
     fe_neg(ry, ry);
-    uint32_t k[8];
-    Fr p;
-    G1Affine c = ld_vec(&commitments[i]), pi = ld_vec(&proofs[i]);
-    G1Jac jc, jp, g, acc, t;
-    jac_from_affine(jc, c);
-    jac_from_affine(jp, pi);
+    const G1Affine c = ld_vec(&commitments[i]), pi = ld_vec(&proofs[i]);
+    G1Affine g;
     for (int l = 0; l < 12; l++) { g.x.v[l] = FpParams::gen_x(l); g.y.v[l] = FpParams::gen_y(l); }
-    fe_set_one(g.z);
+    st_vec(&pts[i], c);
+    st_vec(&pts[(size_t)n + i], g);
+    st_vec(&pts[(size_t)2 * n + i], pi);
+    st_vec(&pts[(size_t)3 * n + i], pi);
     fe_from_mont(p, rho);
-    for (int l = 0; l < 8; l++) k[l] = p.v[l];
-    jac_mul_u256(acc, jc, k);          // rho * C
-    jac_mul_u256(t, jp, k);            // rho * pi
-    st_vec(&R[i], t);
+    for (int l = 0; l < 8; l++) { scalars[(size_t)i * 8 + l] = p.v[l]; scalars[((size_t)3 * n + i) * 8 + l] = p.v[l]; }
     fe_from_mont(p, ry);
-    for (int l = 0; l < 8; l++) k[l] = p.v[l];
-    jac_mul_u256(t, g, k);             // -rho*y * G
-    jac_add(acc, t);
+    for (int l = 0; l < 8; l++) scalars[((size_t)n + i) * 8 + l] = p.v[l];
     fe_from_mont(p, rz);
-    for (int l = 0; l < 8; l++) k[l] = p.v[l];
-    jac_mul_u256(t, jp, k);            // rho*z * pi
-    jac_add(acc, t);
-    st_vec(&L[i], acc);
+    for (int l = 0; l < 8; l++) scalars[((size_t)2 * n + i) * 8 + l] = p.v[l];
 }
 
-// y_i = p_i(z_i) by Horner on the monomial coefficients, one thread per blob (eip4844/src/verifier.rs:83,120 `.eval(&z)`)
+// y_i = p_i(z_i) on the monomial coefficients (eip4844/src/verifier.rs:83,120 `.eval(&z)`): a warp per blob, lane l runs Horner over
+// coefficients [128 l, 128 l + 128), then the 32 partial values are combined with powers of z^128 (one thread per blob took 0.8 ms
+// for its 4096 dependent multiplications, which a single-proof call cannot hide)
 __global__ void __launch_bounds__(32)
 k_poly_eval(const Fr* __restrict__ coeffs, const Fr* __restrict__ z_in, Fr* __restrict__ y_out, uint8_t* __restrict__ y_be, int B) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ Fr part[32];
+    const int b = blockIdx.x, lane = threadIdx.x;
     if (b >= B) return;
-    const Fr* c = coeffs + (size_t)b * N_BLOB;
+    const Fr* c = coeffs + (size_t)b * N_BLOB + (size_t)lane * 128;
     const Fr z = ld_vec(&z_in[b]);
     Fr t;
     fe_set_zero(t);
-    for (int i = N_BLOB - 1; i >= 0; i--) {
+    for (int i = 127; i >= 0; i--) {
         Fr ci = ld_vec(&c[i]);
         fe_mul(t, t, z);
         fe_add(t, t, ci);
     }
-    st_vec(&y_out[b], t);
-    if (y_be) {
-        Fr p;
-        fe_from_mont(p, t);
-        fr_store_be(y_be + (size_t)b * 32, p);
+    part[lane] = t;
+    __syncwarp();
+    if (lane == 0) {
+        Fr z128 = z;
+        for (int i = 0; i < 7; i++) fe_sqr(z128, z128);
+        Fr acc = part[31];
+        for (int l = 30; l >= 0; l--) {
+            fe_mul(acc, acc, z128);
+            fe_add(acc, acc, part[l]);
+        }
+        st_vec(&y_out[b], acc);
+        if (y_be) {
+            Fr p;
+            fe_from_mont(p, acc);
+            fr_store_be(y_be + (size_t)b * 32, p);
+        }
     }
 }
 
@@ -413,14 +421,14 @@ cudaError_t launch_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac*
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }
-cudaError_t launch_kzg_verify_terms(const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* rpow, G1Jac* L,
-                                    G1Jac* R, int n, cudaStream_t st) {
-    k_kzg_verify_terms<<<(n + 63) / 64, 64, 0, st>>>(commitments, proofs, z, y, rpow, L, R, n);
+cudaError_t launch_kzg_verify_pairs(const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* rpow, G1Affine* pts,
+                                    uint32_t* scalars, int n, cudaStream_t st) {
+    k_kzg_verify_pairs<<<(n + 63) / 64, 64, 0, st>>>(commitments, proofs, z, y, rpow, pts, scalars, n);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }
 cudaError_t launch_poly_eval(const Fr* coeffs, const Fr* z, Fr* y, uint8_t* y_be, int B, cudaStream_t st) {
-    k_poly_eval<<<(B + 31) / 32, 32, 0, st>>>(coeffs, z, y, y_be, B);
+    k_poly_eval<<<B, 32, 0, st>>>(coeffs, z, y, y_be, B);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }

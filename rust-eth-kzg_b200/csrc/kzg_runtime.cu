@@ -5,6 +5,7 @@
 #include <ctime>
 #include <cstring>
 #include "fr_consts.cuh"
+#include "host_sha256.h"
 
 // The ceremony output (crates/trusted_setup/data/trusted_setup_4096.json, repacked by
 // tools/convert_trusted_setup.py) is linked into the library, like the reference embeds its JSON
@@ -31,6 +32,41 @@ void TraceClock::mark(const char* phase) {
     double t = now();
     fprintf(stderr, "[ekzg trace] %s: %s %.3f ms\n", what, phase, t - t0);
     t0 = t;
+}
+
+void host_blob_challenge(const uint8_t* blob, const uint8_t* commitment48, uint8_t z_be[32]) {
+    host::Sha256Stream h;
+    uint8_t head[32] = {0};
+    memcpy(head, "FSBLOBVERIFY_V1_", 16);
+    head[30] = 0x10;                      // u128_be(4096)
+    h.update(head, 32);
+    h.update(blob, BYTES_PER_BLOB);
+    h.update(commitment48, 48);
+    uint8_t d[32];
+    h.final(d);
+    // reduce below r (2^256 < 3 r: at most two subtractions)
+    static const uint64_t R[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
+    uint64_t v[4];
+    for (int i = 0; i < 4; i++) {
+        uint64_t x = 0;
+        for (int b = 0; b < 8; b++) x = (x << 8) | d[8 * (3 - i) + b];
+        v[i] = x;
+    }
+    for (int it = 0; it < 2; it++) {
+        bool ge = true;
+        for (int i = 3; i >= 0; i--) {
+            if (v[i] != R[i]) { ge = v[i] > R[i]; break; }
+        }
+        if (!ge) break;
+        unsigned __int128 br = 0;
+        for (int i = 0; i < 4; i++) {
+            const unsigned __int128 t = (unsigned __int128)v[i] - R[i] - (uint64_t)br;
+            v[i] = (uint64_t)t;
+            br = (t >> 64) & 1;
+        }
+    }
+    for (int i = 0; i < 4; i++)
+        for (int b = 0; b < 8; b++) z_be[8 * (3 - i) + b] = (uint8_t)(v[i] >> (8 * (7 - b)));
 }
 
 int chunk_capacity() {
@@ -985,7 +1021,14 @@ Status Context::run_4844(Mode4844 mode, uint64_t n, const uint8_t* blobs, const 
         if (mode == Mode4844::Commit) {
             EKZG_CUDA(launch_coeffs_to_scalars(ws.d_coeffs, ws.d_scalars, cnt, st));
         } else {
-            if (mode == Mode4844::BlobProof) {
+            if (mode == Mode4844::BlobProof && n <= (uint64_t)HOST_CHALLENGE_MAX) {
+                // a handful of blobs: Fiat-Shamir challenges on the host (see host_blob_challenge), uploaded like user-supplied points
+                std::vector<uint8_t> zb((size_t)cnt * 32);
+                for (int i = 0; i < cnt; i++) host_blob_challenge(blobs + (first + i) * BYTES_PER_BLOB, aux_in + (first + i) * 48, &zb[(size_t)i * 32]);
+                EKZG_CUDA(cudaMemcpyAsync(ws.d_z32, zb.data(), zb.size(), cudaMemcpyHostToDevice, st));
+                EKZG_CUDA(cudaStreamSynchronize(st));   // zb is pageable and dies with this scope
+                EKZG_CUDA(launch_scalars_from_be(ws.d_z32, ws.d_z, nullptr, cnt, st));
+            } else if (mode == Mode4844::BlobProof) {
                 EKZG_CUDA(launch_blob_challenge(ws.d_blobs, ws.d_c48, ws.d_z, cnt, st));
             } else {
                 EKZG_CUDA(cudaMemcpyAsync(ws.d_z32, aux_in + first * 32, (size_t)cnt * 32, cudaMemcpyHostToDevice, st));

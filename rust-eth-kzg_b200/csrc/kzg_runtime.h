@@ -215,6 +215,11 @@ private:
 };
 
 int chunk_capacity();
+// z = SHA-256("FSBLOBVERIFY_V1_" || u128_be(4096) || blob || commitment) mod r as 32 canonical big-endian bytes
+// (crates/eip4844/src/verifier.rs:155-196) on the HOST: for a handful of blobs the x86 SHA extensions (0.1 ms per blob) beat the
+// device kernel, where one thread walks the 2049 compressions of a blob (~4 ms whatever the count).
+void host_blob_challenge(const uint8_t* blob, const uint8_t* commitment48, uint8_t z_be[32]);
+constexpr int HOST_CHALLENGE_MAX = 16;   // blobs per call up to which the challenges are hashed on the host
 
 // EKZG_TRACE=1: wall-clock marks of the host-side phases on stderr (the reference's optional `tracing` feature,
 // crates/eip7594/Cargo.toml, plays this role there)

@@ -266,11 +266,14 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
             uint32_t *d_stc, *d_stp, *d_stz, *d_sty, *d_out;
             G1Affine *a_c, *a_p;
             Fr *d_z, *d_y, *d_rpow;
-            G1Jac *d_L, *d_R, *d_part, *d_sums;
+            G1Jac *d_prod, *d_part, *d_part2, *d_sums;
+            G1Affine* d_pairs;
+            uint32_t* d_psc;
             EKZG_TRY(S.get(&d_c, (size_t)N * 48)); EKZG_TRY(S.get(&d_p, (size_t)N * 48)); EKZG_TRY(S.get(&d_zb, (size_t)N * 32)); EKZG_TRY(S.get(&d_yb, (size_t)N * 32));
             EKZG_TRY(S.get(&d_hash, 32)); EKZG_TRY(S.get(&d_stc, N)); EKZG_TRY(S.get(&d_stp, N)); EKZG_TRY(S.get(&d_stz, N)); EKZG_TRY(S.get(&d_sty, N));
             EKZG_TRY(S.get(&d_out, 2 * PAIRING_INPUT_WORDS)); EKZG_TRY(S.get(&a_c, N)); EKZG_TRY(S.get(&a_p, N)); EKZG_TRY(S.get(&d_z, N)); EKZG_TRY(S.get(&d_y, N));
-            EKZG_TRY(S.get(&d_rpow, N)); EKZG_TRY(S.get(&d_L, N)); EKZG_TRY(S.get(&d_R, N)); EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_sums, 2));
+            EKZG_TRY(S.get(&d_rpow, N)); EKZG_TRY(S.get(&d_prod, (size_t)4 * N)); EKZG_TRY(S.get(&d_pairs, (size_t)4 * N)); EKZG_TRY(S.get(&d_psc, (size_t)32 * N));
+            EKZG_TRY(S.get(&d_part, 148)); EKZG_TRY(S.get(&d_part2, 148)); EKZG_TRY(S.get(&d_sums, 2));
             EKZG_CUDA(cudaMemcpyAsync(d_c, hc.data(), hc.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemcpyAsync(d_p, hp.data(), hp.size(), cudaMemcpyHostToDevice, st));
             EKZG_CUDA(cudaMemsetAsync(d_stz, 0, sizeof(uint32_t) * N, st));
@@ -296,7 +299,15 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
                     EKZG_CUDA(cudaMemcpyAsync(ws.d_blobs, ws.h_blobs, (size_t)c * BYTES_PER_BLOB, cudaMemcpyHostToDevice, st));
                     EKZG_CUDA(cudaMemsetAsync(ws.d_status, 0, sizeof(uint32_t) * c, st));
                     EKZG_CUDA(launch_blob_to_coeffs_cells(ws.d_blobs, ws.d_coeffs, nullptr, ws.d_status, T_, c, false, st));
-                    EKZG_CUDA(launch_blob_challenge(ws.d_blobs, d_c + (size_t)o * 48, d_z + o, c, st));
+                    if (N <= HOST_CHALLENGE_MAX) {   // a handful of blobs: challenges on the host (kzg_runtime.h), as canonical bytes
+                        std::vector<uint8_t> zh((size_t)c * 32);
+                        for (int i = 0; i < c; i++) host_blob_challenge(blobs[o + i], &hc[(size_t)(o + i) * 48], &zh[(size_t)i * 32]);
+                        EKZG_CUDA(cudaMemcpyAsync(d_zb + (size_t)o * 32, zh.data(), zh.size(), cudaMemcpyHostToDevice, st));
+                        EKZG_CUDA(cudaStreamSynchronize(st));
+                        EKZG_CUDA(launch_scalars_from_be(d_zb + (size_t)o * 32, d_z + o, nullptr, c, st));
+                    } else {
+                        EKZG_CUDA(launch_blob_challenge(ws.d_blobs, d_c + (size_t)o * 48, d_z + o, c, st));
+                    }
                     EKZG_CUDA(launch_poly_eval(ws.d_coeffs, d_z + o, d_y + o, d_yb + (size_t)o * 32, c, st));
                     EKZG_CUDA(cudaMemcpyAsync(stb.data() + o, ws.d_status, sizeof(uint32_t) * c, cudaMemcpyDeviceToHost, st));
                 }
@@ -329,9 +340,11 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
             // N == 1: the only power used is r^0 = 1, whatever the digest
             EKZG_CUDA(cudaMemcpyAsync(d_hash, hash, 32, cudaMemcpyHostToDevice, st));
             EKZG_CUDA(launch_powers_from_hash(d_hash, d_rpow, N, st));
-            EKZG_CUDA(launch_kzg_verify_terms(a_c, a_p, d_z, d_y, d_rpow, d_L, d_R, N, st));
-            EKZG_CUDA(launch_sum_points(d_R, N, d_part, &d_sums[0], st));
-            EKZG_CUDA(launch_sum_points(d_L, N, d_part, &d_sums[1], st));
+            // the 4 N independent products r^i C_i, (-r^i y_i) G, (r^i z_i) pi_i | r^i pi_i in one pass, then the two sums
+            EKZG_CUDA(launch_kzg_verify_pairs(a_c, a_p, d_z, d_y, d_rpow, d_pairs, d_psc, N, st));
+            EKZG_CUDA(launch_scalar_mul(d_pairs, d_psc, d_prod, 4 * N, st));
+            EKZG_CUDA(launch_sum_points(d_prod + (size_t)3 * N, N, d_part, &d_sums[0], st));
+            EKZG_CUDA(launch_sum_points(d_prod, 3 * N, d_part2, &d_sums[1], st));
             EKZG_CUDA(launch_pairing_inputs(&d_sums[0], &d_sums[1], nullptr, nullptr, d_out, st));
             EKZG_CUDA(cudaStreamWaitEvent(st, ws.sub_out[0], 0));   // the subgroup verdicts
             EKZG_CUDA(cudaMemcpyAsync(pin, d_out, sizeof pin, cudaMemcpyDeviceToHost, st));

@@ -248,10 +248,43 @@ def latency(ctx, pkg, reps=5):
     got_c = [b.raw for b in bufs[0][0]]
     got_p = [b.raw for b in bufs[0][1]]
     assert got_c == list(oc) and got_p == list(op), "single-blob call differs from the oracle"
+
+    # the other per-item symbols of the reference's ABI, one call each from one thread (median of `reps`), GPU | CPU oracle port
+    def med(fn, n=reps):
+        fn()
+        ts = sorted(best(fn, 1)[0] for _ in range(n))
+        return 1e3 * ts[len(ts) // 2]
+
+    def both(gpu_fn, cpu_fn):
+        g = gpu_fn()
+        t0 = time.perf_counter()
+        c = cpu_fn()
+        tcpu = 1e3 * (time.perf_counter() - t0)
+        assert g == c, "GPU and oracle disagree"
+        return {"gpu_ms": med(gpu_fn), "cpu_port_ms_1thread": tcpu}
+    b0 = blobs[0]
+    cm = ctx.blob_to_kzg_commitment(b0)
+    z = (12345).to_bytes(32, "big")
+    pf_blob = ctx.compute_blob_kzg_proof(b0, cm)
+    pf_z, y = ctx.compute_kzg_proof(b0, z)
+    keep = list(range(0, NCELLS, 2))
+    per_item = {
+        "blob_to_kzg_commitment": both(lambda: ctx.blob_to_kzg_commitment(b0), lambda: cref.blob_to_kzg_commitment(b0)),
+        "compute_blob_kzg_proof": both(lambda: ctx.compute_blob_kzg_proof(b0, cm), lambda: cref.compute_blob_kzg_proof(b0, cm)),
+        "compute_kzg_proof": both(lambda: tuple(ctx.compute_kzg_proof(b0, z)), lambda: tuple(cref.compute_kzg_proof(b0, z))),
+        "verify_kzg_proof": both(lambda: ctx.verify_kzg_proof(cm, z, y, pf_z), lambda: cref.verify_kzg_proof(cm, z, y, pf_z)),
+        "verify_blob_kzg_proof": both(lambda: ctx.verify_blob_kzg_proof(b0, cm, pf_blob), lambda: cref.verify_blob_kzg_proof(b0, cm, pf_blob)),
+        "recover_cells_and_kzg_proofs_64_of_128": both(lambda: ctx.recover_cells_and_kzg_proofs(keep, [got_c[i] for i in keep]),
+                                                       lambda: tuple(list(x) for x in cref.recover_cells_and_kzg_proofs(keep, [got_c[i] for i in keep]))),
+        "verify_cell_kzg_proof_batch_128_cells": both(lambda: ctx.verify_cell_kzg_proof_batch([cm] * NCELLS, list(range(NCELLS)), got_c, got_p),
+                                                      lambda: cref.verify_cell_kzg_proof_batch([cm] * NCELLS, list(range(NCELLS)), got_c, got_p)),
+    }
     return {"workload": "compute_cells_and_kzg_proofs for 1 blob through eth_kzg_compute_cells_and_kzg_proofs (BASELINE config #1)",
             "latency_1blob_ms": 1e3 * one[len(one) // 2], "latency_1blob_ms_min": 1e3 * one[0],
             "latency_32blob_ms": 1e3 * many[len(many) // 2], "latency_32blob_note": "32 host threads, one single-blob call each, started together; until the last returns",
-            "cpu_port_1blob_ms": 1e3 * tc, "cpu_port_threads": 1, "parity_checked": 1}
+            "cpu_port_1blob_ms": 1e3 * tc, "cpu_port_threads": 1, "parity_checked": 1,
+            "per_item_symbols_ms": per_item,
+            "per_item_note": "one call from one thread through the Python ctypes stub (list marshalling of 128 cells included), median of %d" % reps}
 
 
 def pageable(ctx, pkg, reps=3):
