@@ -179,11 +179,11 @@ def run_reference(args, rank, world):
     blobs = synth_blobs(n)
     cref.compute_cells_and_kzg_proofs_batch(blobs[:BYTES_PER_BLOB], 1, cores)   # builds the tables
     # keep the whole run inside the driver's limit whatever K and W are: probe the rate on 2 blobs per thread; if K + W
-    # full steps would take more than ~25 minutes, the step shrinks (and the config line says so)
+    # full steps would take more than ~15 minutes, the step shrinks (and the config line says so)
     t0 = time.perf_counter()
     cref.compute_cells_and_kzg_proofs_batch(blobs, min(n, 2 * cores), cores)
     rate = min(n, 2 * cores) / (time.perf_counter() - t0)
-    budget_s = float(os.environ.get("EKZG_REF_BUDGET_S", "1500"))
+    budget_s = float(os.environ.get("EKZG_REF_BUDGET_S", "900"))
     per_step = n
     if (args.steps + args.warmup) * n / rate > budget_s:
         per_step = max(cores, int(budget_s * rate / (args.steps + args.warmup)) // cores * cores)
