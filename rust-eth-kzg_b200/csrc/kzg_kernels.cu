@@ -1379,6 +1379,10 @@ cudaError_t kernels_init() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fk20_msm_vm<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpvm::SMEM_BYTES);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fk20_msm_vm<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fk20_msm_vm<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, fpvm::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fk20_g1_ntts_vm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fk20_g1_ntts_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, fpvm::SMEM_BYTES);
@@ -1469,7 +1473,11 @@ cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable
         if (wide) k_fk20_msm<4><<<dim3((cnt + 31) / 32, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
         else k_fk20_msm<16><<<dim3((cnt + 7) / 8, ngroups), 128, 0, st>>>(scalars, pts, T, B, b0, b0 + cnt);
     } else {
+        // a handful of blobs on a table without a merged top window (the SRS tables at w = 13: a thread may own a single point):
+        // 64 slices, one point per thread -- 20 additions and a 6-level reduction on the critical path instead of 80 and 4
+        const bool tiny = T.mg == 1 && (size_t)cnt * ngroups <= 8 * 64;
         if (wide) k_fk20_msm_vm<4><<<dim3((cnt + 31) / 32, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);
+        else if (tiny) k_fk20_msm_vm<64><<<dim3((cnt + 1) / 2, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);
         else k_fk20_msm_vm<16><<<dim3((cnt + 7) / 8, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);
     }
     EKZG_LAUNCH_CHECK();

@@ -189,6 +189,23 @@ k_sum_positions(G1Jac* __restrict__ pts, int B, int count, int stride) {
     st_vec(&pts[b], acc);
 }
 
+// the same as a tree, one CTA of 64 threads per blob (count <= 64): six levels of additions instead of 63 in a row -- for the
+// single-blob calls (commitment, point proof), which are nothing but dependency chains
+__global__ void __launch_bounds__(64)
+k_sum_positions_tree(G1Jac* __restrict__ pts, int B, int count, int stride) {
+    __shared__ G1Jac sm[64];
+    const int b = blockIdx.x, t = threadIdx.x;
+    G1Jac acc;
+    if (t < count) acc = ld_vec(&pts[(size_t)stride * t * B + b]); else jac_set_inf(acc);
+    for (int step = 32; step >= 1; step >>= 1) {
+        if (t >= step && t < 2 * step) sm[t] = acc;
+        __syncthreads();
+        if (t < step) jac_add(acc, sm[t + step]);
+        __syncthreads();
+    }
+    if (t == 0) st_vec(&pts[b], acc);
+}
+
 // r = BLS12-381 group order as plain limbs
 __device__ __forceinline__ void fr_modulus(uint32_t* k) {
 #pragma unroll
@@ -253,7 +270,8 @@ cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B,
     return cudaSuccess;
 }
 cudaError_t launch_sum_positions(G1Jac* pts, int B, int count, int stride, cudaStream_t st) {
-    k_sum_positions<<<(B + 63) / 64, 64, 0, st>>>(pts, B, count, stride);
+    if (B <= 64 && count <= 64) k_sum_positions_tree<<<B, 64, 0, st>>>(pts, B, count, stride);
+    else k_sum_positions<<<(B + 63) / 64, 64, 0, st>>>(pts, B, count, stride);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }
