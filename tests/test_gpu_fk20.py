@@ -171,3 +171,23 @@ def test_k5_radix4_equals_radix2(vec_ctx, pkg, n, monkeypatch):
     for i in range(min(n, 2)):
         oc, op = cref.compute_cells_and_kzg_proofs(blobs[i])
         assert got[1][i * 6144:(i + 1) * 6144] == b"".join(op)
+
+
+@pytest.mark.parametrize("form", ["r", "a"], ids=["register_xyzz", "batched_affine"])
+def test_k4_alternative_forms_equal_default(vec_ctx, pkg, form, monkeypatch):
+    """the A/B forms of the fixed-base MSM kernel that stay in the tree (EKZG_K4: register XYZZ of round 1; batched affine with a
+    division-step inverter warp) against the default shared-memory-operand form, incl. the edge blobs
+    (identity accumulators, equal-x cases of the affine additions)"""
+    syn = _synth(pkg)
+    n = 40
+    blobs = [syn.blob(8200 + i) for i in range(n - 4)] + list(syn.edge_blobs())[:4]
+    flat = b"".join(blobs)
+    want = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
+    monkeypatch.setenv("EKZG_K4", form)
+    monkeypatch.setenv("EKZG_K4A_MIN", "0")      # the affine kernel is normally reserved for wide launches
+    got = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
+    assert got[2] == want[2] == [0] * n
+    assert got[1] == want[1], "proofs of the '%s' form differ" % form
+    c = vec_ctx.blob_to_kzg_commitment(blobs[0])
+    monkeypatch.delenv("EKZG_K4")
+    assert c == vec_ctx.blob_to_kzg_commitment(blobs[0])
