@@ -692,6 +692,8 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
     static const int linger_us = [] { const char* e = getenv("EKZG_COALESCE_LINGER_US"); return e ? atoi(e) : 300; }();
     constexpr int MAX_IN_FLIGHT = 2, MAX_STAGING = 6;
     std::unique_lock<std::mutex> lk(Q.mu);
+    Q.callers++;
+    struct Leave { CoalesceQueue& q; std::unique_lock<std::mutex>& l; ~Leave() { if (!l.owns_lock()) l.lock(); q.callers--; } } leave{Q, lk};
     // ---- join the batch being formed, or start one ----
     CoalesceBatch* Bt = nullptr;
     bool leader = false;
@@ -762,6 +764,7 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
                 continue;
             }
             if (linger_us <= 0) break;
+            if (Q.callers == 1 && Bt->n == 1) break;     // nobody else is in here: lingering would only add to a lone caller's latency
             const auto gap_end = std::min(t_end, std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us));
             const int before = Bt->n;
             while (Bt->n == before && Q.cv_leader.wait_until(lk, gap_end) != std::cv_status::timeout) {}

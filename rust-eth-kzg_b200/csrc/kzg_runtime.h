@@ -190,6 +190,7 @@ private:
         std::condition_variable cv_leader;  // leader: "somebody joined / finished copying in / a batch left the device"
         CoalesceBatch* forming = nullptr;
         int in_flight = 0;                  // batches handed to the device and not finished
+        int callers = 0;                    // threads inside coalesce() on this queue (a lone caller does not linger)
         int n_staging = 0;
         std::vector<CoalesceStaging*> free_staging;
     };

@@ -25,6 +25,14 @@ def run(pkg, syn, fk20_w, srs_w, nb):
     idx = list(range(0, 128, 2))
     rc, rp = ctx.recover_cells_and_kzg_proofs(idx, [c1[j] for j in idx])
     assert rc == c1 and rp == p1
+    z = (777).to_bytes(32, "big")
+    pz, y = ctx.compute_kzg_proof(blobs[0], z)
+    assert ctx.verify_kzg_proof(com[:48], z, y, pz) is True
+    assert ctx.verify_blob_kzg_proof_batch(blobs[:2], [com[:48], com[48:96]], [prf[:48], prf[48:96]]) is True
+    os.environ["EKZG_K5_R4_MAX"] = "0"          # the wide (radix-2) G1-NTT kernel on the same blob
+    c2, p2 = ctx.compute_cells_and_kzg_proofs(blobs[0])
+    del os.environ["EKZG_K5_R4_MAX"]
+    assert p2 == p1
     sel = [0, 5, 64, 127]
     assert ctx.verify_cell_kzg_proof_batch([com[:48]] * 4, sel, [c1[j] for j in sel], [p1[j] for j in sel]) is True
     assert ctx.verify_cell_kzg_proof_batch([com[:48]] * 4, sel, [c1[j] for j in sel], [p1[j] for j in (5, 0, 64, 127)]) is False
@@ -37,6 +45,7 @@ def main():
     import importlib
     syn = importlib.import_module("eth_kzg_b200.synthetic")
     run(pkg, syn, "10", "9", 3)
+    run(pkg, syn, "10", "8", 2)      # SRS tables without a merged top window: the 64-slice MSM of the single-blob calls
     run(pkg, syn, "12", "12", 40)
     if len(sys.argv) > 1:   # a full-size batch as well (two-piece scheduler path): slow under the tools
         run(pkg, syn, "10", "9", int(sys.argv[1]))
