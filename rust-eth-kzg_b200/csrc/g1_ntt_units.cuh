@@ -77,7 +77,7 @@ EKZG_NTT_UNIT void g1_ntt_butterfly(G1Jac* __restrict__ pts, int B, int b, int t
 constexpr int R4_SUPER = 7;
 constexpr int R4_UNITS = 192;          // units per blob group and super-phase: 160 + 32, middle 128 + 64
 constexpr int R4_TMP_POINTS = 160;     // products per blob and super-phase
-EKZG_NTT_INL int r4_nmul(int sp) { return sp == 3 ? 128 : 160; }   // (middle: only the first 64 do work, see r4_middle_unit)
+EKZG_NTT_INL int r4_nmul(int sp) { return sp == 3 ? 128 : 160; }
 
 // p <- omega_128^tw * p (tw in [0, 128))
 EKZG_NTT_INL void r4_twiddle_mul(G1Jac& p, int e, TwiddleOps tw) {
@@ -91,18 +91,13 @@ EKZG_NTT_INL void r4_sub(G1Jac& a, const G1Jac& b) {   // a -= b
     jac_add(a, n);
 }
 
-// middle super-phase, unit t < 64: the radix-2 butterflies of inverse stage 6 and forward stage 6 on (pts[t], pts[t+64]) back to
-// back -- two multiplications deep.  (The flat form, products omega^-t x1 and omega^t x0 combined afterwards, is one deep and
-// agrees with this one under host emulation, but its combination step gave other points on the device)
-EKZG_NTT_UNIT void r4_middle_unit(G1Jac* __restrict__ pts, int B, int b, int t, TwiddleOps tw) {
-    g1_ntt_butterfly(pts, B, b, t, 6, tw);
-    g1_ntt_butterfly(pts, B, b, t, 7, tw);
-}
-
 EKZG_NTT_UNIT void r4_mul_unit(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int b, int sp, int u, TwiddleOps tw) {
     // which point (or combination of points) times which root of unity
     int i0, i1 = -1, i2 = -1, i3 = -1, e;       // p = pts[i0] - pts[i1] + pts[i2] - pts[i3] (absent terms: -1), then p *= omega^e
-    {
+    if (sp == 3) {           // middle: omega^-t x1 (even u) and omega^t x0 (odd u)
+        const int t = u >> 1;
+        if (u & 1) { i0 = t; e = t; } else { i0 = t + 64; e = (128 - t) & 127; }
+    } else {
         const bool fwd = sp > 3;
         const int s = fwd ? 2 * (6 - sp) : 2 * sp, len = 1 << s;
         const int q = u / 5, which = u - 5 * q;
@@ -133,6 +128,21 @@ EKZG_NTT_UNIT void r4_mul_unit(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp,
 }
 
 EKZG_NTT_UNIT void r4_combine_unit(G1Jac* __restrict__ pts, const G1Jac* __restrict__ tmp, int B, int b, int sp, int c) {
+    if (sp == 3) {           // pts[c] = x0 + omega^-c x1, pts[c + 64] = x1 + omega^c x0
+        // Both operands of the addition sit in ONE array on purpose.  As two separate locals (`G1Jac acc = ld_pt(o); const G1Jac p =
+        // ld_pt(..); jac_add(acc, p);`, and before that as two named points plus two temporaries) nvcc 12.9 gave them the same
+        // stack slot for sm_100a: jac_add then saw acc == p and returned 2 p -- bit-exact under host emulation, clean under
+        // compute-sanitizer, wrong on the device (found with device printf and the prefix hook).
+        G1Jac pair[2];
+        for (int k = 0; k < 2; k++) {
+            G1Jac* o = &pts[(size_t)(c + 64 * k) * B + b];
+            pair[0] = ld_pt(o);
+            pair[1] = ld_pt(&tmp[(size_t)(2 * c + k) * B + b]);
+            jac_add(pair[0], pair[1]);
+            st_pt(o, pair[0]);
+        }
+        return;
+    }
     const bool fwd = sp > 3;
     const int s = fwd ? 2 * (6 - sp) : 2 * sp, len = 1 << s;
     const int pos = c & (len - 1), base = ((c >> s) << (s + 2)) + pos;

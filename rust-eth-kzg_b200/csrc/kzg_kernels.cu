@@ -808,11 +808,10 @@ k_fk20_g1_ntts(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned
 //       inverse DIT stages (s, s+1) on x0..x3 = pts[base + {0, 1, 2, 3} * 2^s]:
 //           y0 = x0 + p1 + p2 + p3    y2 = x0 + p1 - p2 - p3    y1 = x0 - p1 + p4 - p5    y3 = x0 - p1 - p4 + p5
 //           p1 = W(ea) x1, p2 = W(eb) x2, p3 = W(ea+eb) x3, p4 = W(eb+32) x2, p5 = W(ea+eb+32) x3        (W(e) = omega^-e)
-//       middle: inverse stage 6 (only the 64 kept outputs) + forward stage 6:  pts[t] = h = x0 + W(t) x1,  pts[t+64] = omega^t h
-//               (two multiplications deep, as two radix-2 butterflies in one unit)
+//       middle: inverse stage 6 (only the 64 kept outputs) + forward stage 6:  pts[t] = x0 + W(t) x1,  pts[t+64] = omega^t x0 + x1
 //       forward DIF stages (s+1, s):
 //           y0 = x0+x1+x2+x3   y1 = w(ea)(x0-x1+x2-x3)   y2 = w(eb)(x0-x2) + w(eb+32)(x1-x3)   y3 = w(ea+eb)(x0-x2) - w(ea+eb+32)(x1-x3)
-//   The five products of a radix-4 butterfly are independent, so a super-phase is ONE multiplication deep: 8 instead of 12 on
+//   The five products of a radix-4 butterfly are independent, so a super-phase is ONE multiplication deep: 7 instead of 12 on
 //   the critical path, for 25 % more multiplications (5 per 4 points and two stages instead of 4) -- which is why the wide
 //   launches keep the radix-2 kernel.  Same persistent ticket queue; per blob group and super-phase, 160 (middle: 128)
 //   multiplication units write their products to a scratch array, then 32 (64) combination units add them up in place.
@@ -848,9 +847,7 @@ k_fk20_g1_ntts_r4(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int G
         }
         const int b = g * 32 + lane;
         if (b < B) {
-            if (sp == 3) {           // middle: 64 fused butterfly pairs; the other tickets of this super-phase only count
-                if (!comb && u < 64) r4_middle_unit(pts, B, b, u, c_twiddle_ops);
-            } else if (comb) r4_combine_unit(pts, tmp, B, b, sp, u);
+            if (comb) r4_combine_unit(pts, tmp, B, b, sp, u);
             else r4_mul_unit(pts, tmp, B, b, sp, u, c_twiddle_ops);
         }
         __threadfence();
@@ -1515,7 +1512,7 @@ constexpr int R4_MAX_BLOBS = 256;      // the product scratch of the radix-4 for
 static int k5_r4_max() {
     // batches up to this many blobs take the radix-4 kernel (EKZG_K5_R4_MAX; 0 switches it off)
     const char* e = getenv("EKZG_K5_R4_MAX");
-    const int v = e ? atoi(e) : 224;   // measured (tools/k5_sweep.py, profiles/r2_i_k5_sweep.jsonl): faster up to 224 blobs, equal at 256
+    const int v = e ? atoi(e) : 256;   // measured (tools/k5_sweep.py, profiles/r2_i_k5_sweep.jsonl): 10.2 against 17.2 ms up to 64 blobs, 15.3 against 17.2 at 256
     return v < 0 ? 0 : (v > R4_MAX_BLOBS ? R4_MAX_BLOBS : v);
 }
 size_t g1_ntt_scratch_bytes() {

@@ -28,10 +28,6 @@ int emu_g1_ntt(int form, int phases, const uint8_t* in128x48, uint8_t* out128x48
     } else {
         for (int sp = 0; sp < phases / 2; sp++) {
             const int nmul = r4_nmul(sp);
-            if (sp == 3) {
-                for (int t = 0; t < 64; t++) r4_middle_unit(pts.data(), 1, 0, t, TWIDDLE_OPS_HOST);
-                continue;
-            }
             for (int u = 0; u < nmul; u++) r4_mul_unit(pts.data(), tmp.data(), 1, 0, sp, u, TWIDDLE_OPS_HOST);
             for (int c = 0; c < R4_UNITS - nmul; c++) r4_combine_unit(pts.data(), tmp.data(), 1, 0, sp, c);
         }
@@ -40,4 +36,5 @@ int emu_g1_ntt(int form, int phases, const uint8_t* in128x48, uint8_t* out128x48
     return 0;
 }
 }
+
 

@@ -1,6 +1,6 @@
 """The unit list of the radix-4 (latency-mode) G1-NTT kernel, k_fk20_g1_ntts_r4 in csrc/kzg_kernels.cu, replayed on the CPU with
 elements of Fr standing in for the points (both are modules over Fr, the schedule only adds and multiplies by roots of
-unity): the seven super-phases (the middle one is two radix-2 butterflies per point pair) must give exactly what the fourteen radix-2 phases of k_fk20_g1_ntts give -- which the
+unity): the seven super-phases must give exactly what the fourteen radix-2 phases of k_fk20_g1_ntts give -- which the
 consensus vectors pin -- and both must equal the definition: inverse transform of the bit-reversed input, first 64
 coefficients kept, forward transform of (h || 0), output bit-reversed (reference: fk20/prover.rs:199-222 over
 polynomial/src/domain.rs:149-194).  The index arithmetic below is a transcription of r4_mul_unit / r4_combine_unit."""
@@ -45,12 +45,11 @@ def radix4_superphases(p):
     for sp in range(7):
         tmp = [None] * 160
         nmul = 128 if sp == 3 else 160
-        if sp == 3:                                 # r4_middle_unit: the butterflies of phases 6 and 7 back to back
-            for t in range(64):
-                h = (p[t] + p[t + 64] * TW[(128 - t) & 127]) % R
-                p[t], p[t + 64] = h, h * TW[t] % R
-            continue
         for u in range(nmul):                       # r4_mul_unit
+            if sp == 3:
+                t = u >> 1
+                tmp[u] = p[t] * TW[t] % R if u & 1 else p[t + 64] * TW[(128 - t) & 127] % R
+                continue
             fwd = sp > 3
             s = 2 * (6 - sp) if fwd else 2 * sp
             ln = 1 << s
@@ -70,6 +69,9 @@ def radix4_superphases(p):
                     x += p[base + 2 * ln] - p[base + 3 * ln]
                 tmp[u] = x * TW[e & 127] % R
         for c in range(192 - nmul):                 # r4_combine_unit
+            if sp == 3:
+                p[c], p[c + 64] = (p[c] + tmp[2 * c]) % R, (p[c + 64] + tmp[2 * c + 1]) % R
+                continue
             fwd = sp > 3
             s = 2 * (6 - sp) if fwd else 2 * sp
             ln = 1 << s
