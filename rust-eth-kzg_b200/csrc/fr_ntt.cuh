@@ -13,19 +13,24 @@
 
 namespace ekzg {
 
-// 16-byte vector loads / stores of limb structs.  The LOCAL object is only ever touched through uint32_t lvalues (its own limb
-// type): writing it through a uint4* and reading the limbs afterwards is a strict-aliasing violation, and nvcc does act on it
-// (seen in the radix-4 G1-NTT combination unit: two named points and two temporaries ended up in one stack slot).
+// 16-byte vector loads / stores of limb structs.  The LOCAL object is only ever touched through its own members
+// (limb_word(obj, k): word k of a field element or point, resolved at compile time in the unrolled loops): no reinterpret_cast of a
+// local.  Writing it through a uint4* and reading the limbs afterwards was a strict-aliasing violation, and nvcc does merge stack
+// slots it believes unrelated (seen in the radix-4 G1-NTT combination unit, g1_ntt_units.cuh).
+template <class P>
+__host__ __device__ __forceinline__ uint32_t& limb_word(Fe<P>& a, int k) { return a.v[k]; }
+template <class P>
+__host__ __device__ __forceinline__ const uint32_t& limb_word(const Fe<P>& a, int k) { return a.v[k]; }
+
 template <class T>
 __device__ __forceinline__ T ld_vec(const T* p) {
     static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
     T r;
     const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint32_t* w = reinterpret_cast<uint32_t*>(&r);
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(T) / 16); i++) {
         const uint4 q = s[i];
-        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+        limb_word(r, 4 * i) = q.x; limb_word(r, 4 * i + 1) = q.y; limb_word(r, 4 * i + 2) = q.z; limb_word(r, 4 * i + 3) = q.w;
     }
     return r;
 }
@@ -33,9 +38,9 @@ template <class T>
 __device__ __forceinline__ void st_vec(T* p, const T& v) {
     static_assert(sizeof(T) % 16 == 0, "16-byte multiple");
     uint4* d = reinterpret_cast<uint4*>(p);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(T) / 16); i++) d[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+    for (int i = 0; i < (int)(sizeof(T) / 16); i++)
+        d[i] = make_uint4(limb_word(v, 4 * i), limb_word(v, 4 * i + 1), limb_word(v, 4 * i + 2), limb_word(v, 4 * i + 3));
 }
 
 __device__ __forceinline__ Fr smem_ld(const uint32_t* s, int stride, int i) {

@@ -26,6 +26,14 @@ struct G1Jac {  // identity <=> z == 0
     Fp x, y, z;
 };
 
+// word k of a point (x first): what the vector loads / stores of fr_ntt.cuh and g1_ntt_units.cuh address the members through
+EKZG_HD uint32_t& limb_word(G1Affine& p, int k) { return k < 12 ? p.x.v[k] : p.y.v[k - 12]; }
+EKZG_HD const uint32_t& limb_word(const G1Affine& p, int k) { return k < 12 ? p.x.v[k] : p.y.v[k - 12]; }
+EKZG_HD uint32_t& limb_word(G1Jac& p, int k) { return k < 12 ? p.x.v[k] : k < 24 ? p.y.v[k - 12] : p.z.v[k - 24]; }
+EKZG_HD const uint32_t& limb_word(const G1Jac& p, int k) { return k < 12 ? p.x.v[k] : k < 24 ? p.y.v[k - 12] : p.z.v[k - 24]; }
+EKZG_HD uint32_t& limb_word(G1Xyzz& p, int k) { return k < 12 ? p.x.v[k] : k < 24 ? p.y.v[k - 12] : k < 36 ? p.zz.v[k - 24] : p.zzz.v[k - 36]; }
+EKZG_HD const uint32_t& limb_word(const G1Xyzz& p, int k) { return k < 12 ? p.x.v[k] : k < 24 ? p.y.v[k - 12] : k < 36 ? p.zz.v[k - 24] : p.zzz.v[k - 36]; }
+
 EKZG_HD bool g1a_is_inf(const G1Affine& p) { return fe_is_zero(p.x) && fe_is_zero(p.y); }
 EKZG_HD void g1a_set_inf(G1Affine& p) { fe_set_zero(p.x); fe_set_zero(p.y); }
 EKZG_HD bool xyzz_is_inf(const G1Xyzz& p) { return fe_is_zero(p.zz); }

@@ -18,19 +18,18 @@ typedef const uint16_t (*TwiddleOps)[MULOPS_STRIDE];
 EKZG_NTT_INL G1Jac ld_pt(const G1Jac* p) {  // L2-coherent: the producer ran on another SM
     G1Jac r;
     const uint4* s = reinterpret_cast<const uint4*>(p);
-    uint32_t* w = reinterpret_cast<uint32_t*>(&r);   // (uint32_t lvalues only on the local object: see ld_vec, fr_ntt.cuh)
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) {
         const uint4 q = __ldcg(s + i);
-        w[4 * i] = q.x; w[4 * i + 1] = q.y; w[4 * i + 2] = q.z; w[4 * i + 3] = q.w;
+        limb_word(r, 4 * i) = q.x; limb_word(r, 4 * i + 1) = q.y; limb_word(r, 4 * i + 2) = q.z; limb_word(r, 4 * i + 3) = q.w;
     }
     return r;
 }
 EKZG_NTT_INL void st_pt(G1Jac* p, const G1Jac& v) {
     uint4* d = reinterpret_cast<uint4*>(p);
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(&v);
 #pragma unroll
-    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++) __stcg(d + i, make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]));
+    for (int i = 0; i < (int)(sizeof(G1Jac) / 16); i++)
+        __stcg(d + i, make_uint4(limb_word(v, 4 * i), limb_word(v, 4 * i + 1), limb_word(v, 4 * i + 2), limb_word(v, 4 * i + 3)));
 }
 #else
 #define EKZG_NTT_UNIT static inline
