@@ -254,10 +254,13 @@ def strong_scaling(args, ctx, pkg, rank, world, local_rank):
     if rank == 0:
         # the gathered batch equals what one device computes for blobs 0..n-1 (first and last blob of every shard checked)
         probe = sorted({b for r in range(world) for b in (sh.shard_bounds(n, world, r)[0], sum(sh.shard_bounds(n, world, r)) - 1)})
+        bad = []
         for b in probe:
             c, p, st = ctx.compute_cells_and_kzg_proofs_batch(synth_blobs(1, first=b), 1)
-            assert bytes(h_cells[b].numpy()) == c and bytes(h_proofs[b].numpy()) == p, "gathered shard result differs at blob %d" % b
-        check = len(probe)
+            if not (bytes(h_cells[b].numpy()) == c and bytes(h_proofs[b].numpy()) == p):
+                bad.append(b)
+        # a mismatch is reported in the line (shards_checked < 0), not raised: the other ranks are already past their collectives
+        check = len(probe) if not bad else -len(bad)
     return float(t[0]), n, check
 
 
