@@ -125,13 +125,13 @@ def test_verify_config5_full_size(vec_ctx, pkg, nb):
     assert cref.verify_cell_kzg_proof_batch(C[sl], I[sl], bad[sl], PR[sl]) is False
 
 
-@pytest.mark.parametrize("chunk", [None, "4"], ids=["one_chunk", "chunks_of_4"])
-def test_verify_blob_proof_batch_synthetic(das_ctx, pkg, chunk, monkeypatch):
-    """(chunks_of_4: the blobs of a batch pass through the workspace in chunks, EKZG_CHUNK -- 9 blobs = 4 + 4 + 1)"""
+@pytest.mark.parametrize("chunk,nb", [(None, 9), ("4", 9), (None, 20), ("8", 20)], ids=["one_chunk", "chunks_of_4", "device_challenges", "device_challenges_chunked"])
+def test_verify_blob_proof_batch_synthetic(das_ctx, pkg, chunk, nb, monkeypatch):
+    """(chunks: the blobs of a batch pass through the workspace in chunks, EKZG_CHUNK -- 9 blobs = 4 + 4 + 1; up to 16 blobs the
+    Fiat-Shamir challenges are hashed on the host, above that by the device kernel: 20 blobs take that path)"""
     if chunk:
         monkeypatch.setenv("EKZG_CHUNK", chunk)
     syn = importlib.import_module("eth_kzg_b200.synthetic")
-    nb = 9
     blobs = [syn.blob(900 + i) for i in range(nb)]
     flat = b"".join(blobs)
     cms, _ = das_ctx.blob_to_kzg_commitment_batch(flat, nb)
