@@ -339,66 +339,6 @@ EKZG_HD void fe_sqr(Fp& out, const Fp& a) {
 #endif
 }
 
-// TWO independent Fp products in one subroutine.  Inside one product every row waits for the previous one (its m needs the
-// accumulated low limb), so a product offers two carry chains to interleave and a warp issues a wide multiply-add every ~2.5
-// cycles into a pipe that takes one every 4 -- with two warps per sub-partition (K5: 255 registers) that leaves the pipe idle
-// ~17 % of the time, with one (latency mode) more than half.  Two products back to back in one basic block give ptxas four
-// chains.  The point formulas of the fixed-scalar ladder pair their multiplications up (g1.cuh: jac_dbl_pairs, jac_madd_pairs).
-struct FpPair { Fp a, b; };
-#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
-static __device__ __noinline__ FpPair fp_mul_pair_call(Fp a0, Fp b0, Fp a1, Fp b1) {
-    FpPair r;
-    fp_mul_impl(r.a, a0, b0);
-    fp_mul_impl(r.b, a1, b1);
-    return r;
-}
-static __device__ __noinline__ FpPair fp_sqr_pair_call(Fp a0, Fp a1) {
-    FpPair r;
-    fp_sqr_impl(r.a, a0);
-    fp_sqr_impl(r.b, a1);
-    return r;
-}
-static __device__ __noinline__ FpPair fp_sqr_mul_call(Fp a0, Fp a1, Fp b1) {
-    FpPair r;
-    fp_sqr_impl(r.a, a0);
-    fp_mul_impl(r.b, a1, b1);
-    return r;
-}
-#endif
-// (r0, r1) = (a0*b0, a1*b1)
-EKZG_HD void fp_mul_pair(Fp& r0, const Fp& a0, const Fp& b0, Fp& r1, const Fp& a1, const Fp& b1) {
-#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
-    const FpPair r = fp_mul_pair_call(a0, b0, a1, b1);
-    r0 = r.a; r1 = r.b;
-#else
-    Fp t0, t1;
-    fp_mul_impl(t0, a0, b0); fp_mul_impl(t1, a1, b1);
-    r0 = t0; r1 = t1;
-#endif
-}
-// (r0, r1) = (a0^2, a1^2)
-EKZG_HD void fp_sqr_pair(Fp& r0, const Fp& a0, Fp& r1, const Fp& a1) {
-#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
-    const FpPair r = fp_sqr_pair_call(a0, a1);
-    r0 = r.a; r1 = r.b;
-#else
-    Fp t0, t1;
-    fp_sqr_impl(t0, a0); fp_sqr_impl(t1, a1);
-    r0 = t0; r1 = t1;
-#endif
-}
-// (r0, r1) = (a0^2, a1*b1)
-EKZG_HD void fp_sqr_mul(Fp& r0, const Fp& a0, Fp& r1, const Fp& a1, const Fp& b1) {
-#if defined(__CUDA_ARCH__) && !defined(EKZG_FP_MUL_INLINE)
-    const FpPair r = fp_sqr_mul_call(a0, a1, b1);
-    r0 = r.a; r1 = r.b;
-#else
-    Fp t0, t1;
-    fp_sqr_impl(t0, a0); fp_mul_impl(t1, a1, b1);
-    r0 = t0; r1 = t1;
-#endif
-}
-
 template <class P>
 EKZG_HD void fe_add(Fe<P>& out, const Fe<P>& a, const Fe<P>& b) {
     constexpr int N = P::N;

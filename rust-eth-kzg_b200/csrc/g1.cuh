@@ -176,23 +176,6 @@ EKZG_HD void jac_dbl_inl(G1Jac& r, const G1Jac& p) {
     r.x = f;
 }
 EKZG_HD_CALL void jac_dbl(G1Jac& r, const G1Jac& p) { jac_dbl_inl(r, p); }
-// the same doubling with its seven multiplications issued as three independent pairs and one single (field.cuh: fp_sqr_pair ...)
-EKZG_HD void jac_dbl_pairs(G1Jac& r, const G1Jac& p) {
-    Fp a, b, c, d, e, f, z3;
-    fp_sqr_pair(a, p.x, b, p.y);                 // A = X^2, B = Y^2
-    fe_add(d, p.x, b);
-    fp_sqr_pair(c, b, d, d);                     // C = B^2, (X + B)^2
-    fe_sub(d, d, a); fe_sub(d, d, c); fe_dbl(d, d);
-    fe_dbl(e, a); fe_add(e, e, a);               // E = 3A
-    fp_sqr_mul(f, e, z3, p.y, p.z);              // F = E^2, Y*Z
-    fe_dbl(r.z, z3);
-    fe_sub(f, f, d); fe_sub(f, f, d);            // X3
-    fe_sub(d, d, f);
-    fe_mul(d, e, d);
-    fe_dbl(c, c); fe_dbl(c, c); fe_dbl(c, c);
-    fe_sub(r.y, d, c);
-    r.x = f;
-}
 
 // acc += q, both Jacobian  (add-2007-bl: 11M + 5S)
 EKZG_HD_CALL void jac_add(G1Jac& acc, const G1Jac& q) {
@@ -258,35 +241,6 @@ EKZG_HD void jac_madd_inl(G1Jac& acc, const G1Affine& p_in, bool neg) {
     acc.x = u2;
 }
 EKZG_HD_CALL void jac_madd(G1Jac& acc, const G1Affine& p_in, bool neg) { jac_madd_inl(acc, p_in, neg); }
-// the same mixed addition (madd-2007-bl) with its eleven multiplications as four pairs and three singles
-EKZG_HD void jac_madd_pairs(G1Jac& acc, const G1Affine& p_in, bool neg) {
-    if (g1a_is_inf(p_in)) return;
-    G1Affine p;
-    p.x = p_in.x;
-    fe_cneg(p.y, p_in.y, neg);
-    if (jac_is_inf(acc)) { acc.x = p.x; acc.y = p.y; fe_set_one(acc.z); return; }
-    Fp z1z1, u2, s2, h, hh, i, j, rr, v, t;
-    fp_sqr_mul(z1z1, acc.z, s2, p.y, acc.z);     // Z1Z1, Y2*Z1
-    fp_mul_pair(u2, p.x, z1z1, s2, s2, z1z1);    // U2 = X2*Z1Z1, S2 = Y2*Z1*Z1Z1
-    fe_sub(h, u2, acc.x);
-    fe_sub(rr, s2, acc.y);
-    if (fe_is_zero(h)) {
-        if (fe_is_zero(rr)) { G1Jac d; jac_dbl(d, acc); acc = d; } else jac_set_inf(acc);
-        return;
-    }
-    fe_dbl(rr, rr);
-    fe_add(t, acc.z, h);
-    fp_sqr_pair(hh, h, t, t);                    // HH, (Z1 + H)^2
-    fe_sub(t, t, z1z1); fe_sub(acc.z, t, hh);    // Z3
-    fe_dbl(i, hh); fe_dbl(i, i);
-    fp_mul_pair(j, h, i, v, acc.x, i);           // J = H*I, V = X1*I
-    fp_sqr_mul(u2, rr, s2, acc.y, j);            // r^2, Y1*J
-    fe_sub(u2, u2, j); fe_sub(u2, u2, v); fe_sub(u2, u2, v);  // X3
-    fe_sub(v, v, u2); fe_mul(v, rr, v);
-    fe_dbl(s2, s2);
-    fe_sub(acc.y, v, s2);
-    acc.x = u2;
-}
 
 // phi(P) = (beta*x, y, z): multiplication by lambda (GLV endomorphism)
 EKZG_HD void jac_endo(G1Jac& r, const G1Jac& p) {

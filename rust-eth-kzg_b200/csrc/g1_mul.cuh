@@ -269,9 +269,7 @@ EKZG_HD_CALL void jac_mul_ops(G1Jac& out, const G1Jac& p, const uint16_t* ops) {
     const int n = ops[0];
     for (int c = 1; c <= n; c++) {
         const uint32_t op = ops[c];
-#if defined(EKZG_K5_PAIR_MUL)
-        for (int s = op >> 8; s > 0; s--) jac_dbl_pairs(acc, acc);
-#elif defined(__CUDA_ARCH__) && !defined(EKZG_K5_CALL_POINT_OPS)
+#if defined(__CUDA_ARCH__) && !defined(EKZG_K5_CALL_POINT_OPS)
         for (int s = op >> 8; s > 0; s--) jac_dbl_inl(acc, acc);
 #else
         for (int s = op >> 8; s > 0; s--) jac_dbl(acc, acc);
@@ -281,9 +279,7 @@ EKZG_HD_CALL void jac_mul_ops(G1Jac& out, const G1Jac& p, const uint16_t* ops) {
             G1Affine e;
             e.x = (op & 0x10) ? bx[idx] : tbl[idx].x;
             e.y = tbl[idx].y;
-#if defined(EKZG_K5_PAIR_MUL)
-            jac_madd_pairs(acc, e, (op & 8) != 0);
-#elif defined(__CUDA_ARCH__) && !defined(EKZG_K5_CALL_POINT_OPS)
+#if defined(__CUDA_ARCH__) && !defined(EKZG_K5_CALL_POINT_OPS)
             jac_madd_inl(acc, e, (op & 8) != 0);
 #else
             jac_madd(acc, e, (op & 8) != 0);

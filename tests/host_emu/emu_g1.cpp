@@ -19,7 +19,6 @@ int emu_g1_decompress_roundtrip(const uint8_t* in, uint8_t* out) {
     g1a_compress(out, a); return 0;
 }
 // op: 0 xyzz_madd(P,+Q) 1 xyzz_madd(P,-Q) 2 xyzz_add 3 jac_add 4 jac_madd(+) 5 jac_madd(-) 6 jac_dbl(P) 7 xyzz_dbl(P)
-//     8 jac_dbl_pairs(P) 9 jac_madd_pairs(+) 10 jac_madd_pairs(-)
 int emu_g1_binop(int op, const uint8_t* p48, const uint8_t* q48, uint8_t* out) {
     G1Affine p, q;
     if (g1a_decompress(p, p48) || g1a_decompress(q, q48)) return 1;
@@ -36,9 +35,6 @@ int emu_g1_binop(int op, const uint8_t* p48, const uint8_t* q48, uint8_t* out) {
         case 5: jac_madd(jp, q, true); out48(out, jp); break;
         case 6: { G1Jac d; jac_dbl(d, jp); out48(out, d); break; }
         case 7: { G1Xyzz d; xyzz_dbl(d, xp); out48x(out, d); break; }
-        case 8: { G1Jac d; jac_dbl_pairs(d, jp); out48(out, d); break; }          // the paired-multiplication forms of the K5 ladder
-        case 9: jac_madd_pairs(jp, q, false); out48(out, jp); break;
-        case 10: jac_madd_pairs(jp, q, true); out48(out, jp); break;
         default: return 3;
     }
     return 0;
