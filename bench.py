@@ -464,7 +464,7 @@ def main():
             "strong": {"blobs_total": strong_n, "n_gpus": world, "ms_per_step": strong_ms, "value": strong_n / (strong_ms / 1000), "unit": "blobs/s",
                        "shards_checked": strong_checked,
                        "path": "per rank: pinned host shard -> H2D -> kernels; NCCL gather of cells and proofs to rank 0 -> D2H into rank 0's pinned buffer; host wall clock, max over ranks",
-                       "limiter": "K5's 14 dependent G1-NTT phases cost ~20 ms whatever the shard size (DESIGN.md §6)"},
+                       "limiter": "K5's dependency chain of fixed-scalar multiplications (7 deep up to 256 blobs per GPU: 10-15 ms; 12 deep above: 17+ ms) whatever the shard size (DESIGN.md §6)"},
         }
     extras = not args.no_extras
     if extras and world == 1:
