@@ -1,0 +1,13 @@
+set -x
+O=gpurun_out/r2final
+mkdir -p $O
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest.log 2>&1; tail -3 $O/pytest.log
+timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench.json 2> $O/bench.err; tail -c 300 $O/bench.err
+python - <<PY
+import json
+d = json.loads(open("$O/bench.json").read().strip().splitlines()[-1])
+print(round(d["value"]), round(d["e2e"]["value"]), round(d["roofline"]["frac"], 4), d["latency_1blob_ms"], d["latency_32blob_ms"], d["abi_single_blob"].get("blobs_per_s"), d["cpu_baseline"]["value"])
+print({k: round(v["gpu_ms"], 2) for k, v in d["configs"]["1"]["per_item_symbols_ms"].items()})
+for k in ("2", "4", "5"): print(k, round(d["configs"][k]["value"]), round(d["configs"][k]["ms"], 2))
+PY
