@@ -115,7 +115,8 @@ EKZG_HD_CALL void jac_mul_half16(G1Jac& out, const G1Jac& q, const int8_t* d /*3
 // digits jac_mul_glv16 takes: 128 doublings + 66 additions instead of the 252 + 63 of jac_mul_u256.
 // Used by the verifiers' random-linear-combination scalar multiplications (reference: g1_lincomb -> blst Pippenger,
 // crates/cryptography/bls12_381/src/lincomb.rs:7-30; one multiplication per thread here).
-EKZG_HD void glv_split_digits(int8_t* d /*66*/, const uint32_t* k /*8 limbs, < r*/) {
+// the two halves on their own: k = k1 + k2*lambda, k1 and k2 as 5 plain limbs each (both below 2^128: limb 4 is zero on return)
+EKZG_HD void glv_split_halves(uint32_t* k1 /*5*/, uint32_t* q /*5*/, const uint32_t* k /*8 limbs, < r*/) {
     const uint32_t lam[4] = {GLV_LAMBDA[0], GLV_LAMBDA[1], GLV_LAMBDA[2], GLV_LAMBDA[3]};
     const uint32_t rec[5] = {0xf6cfee30u, 0x63f6e522u, 0xe01faaddu, 0x7c6becf1u, 0x1u};   // floor(2^256 / lambda)
     // q = (k * rec) >> 256
@@ -130,7 +131,7 @@ EKZG_HD void glv_split_digits(int8_t* d /*66*/, const uint32_t* k /*8 limbs, < r
         }
         prod[i + 5] = (uint32_t)c;
     }
-    uint32_t q[5] = {prod[8], prod[9], prod[10], prod[11], prod[12]};
+    for (int i = 0; i < 5; i++) q[i] = prod[8 + i];
     // k1 = k - q*lambda, exact below 3*lambda < 2^130: 5 limbs are enough
     uint32_t ql[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 5; i++) {
@@ -142,7 +143,6 @@ EKZG_HD void glv_split_digits(int8_t* d /*66*/, const uint32_t* k /*8 limbs, < r
         }
         ql[i + 4] = (uint32_t)c;
     }
-    uint32_t k1[5];
     {
         uint64_t b = 0;
         for (int i = 0; i < 5; i++) {
@@ -170,6 +170,10 @@ EKZG_HD void glv_split_digits(int8_t* d /*66*/, const uint32_t* k /*8 limbs, < r
         uint64_t c = 1;
         for (int i = 0; i < 5; i++) { uint64_t t = (uint64_t)q[i] + c; q[i] = (uint32_t)t; c = t >> 32; }
     }
+}
+EKZG_HD void glv_split_digits(int8_t* d /*66*/, const uint32_t* k /*8 limbs, < r*/) {
+    uint32_t k1[5], q[5];
+    glv_split_halves(k1, q, k);
     // signed radix-16 digits in [-7, 8], least significant first, 33 per half
     for (int h = 0; h < 2; h++) {
         const uint32_t* v = h ? q : k1;

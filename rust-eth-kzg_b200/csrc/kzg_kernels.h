@@ -60,6 +60,11 @@ cudaError_t launch_sum_points(const G1Jac* in, int n, G1Jac* scratch, G1Jac* out
 cudaError_t launch_cell_interp(const uint8_t* cells, const uint32_t* col, const Fr* rpow, Fr* interp, uint32_t* status, const DevTables& T,
                                int n, cudaStream_t st);
 cudaError_t launch_interp_column_sum(const Fr* interp, uint32_t* out, int n, cudaStream_t st);
+// K7 (kzg_kernels_msm.cu): bucket-method MSM over n variable points for one or two scalar sets
+size_t msm_bucket_scratch_bytes(int n, int sets);
+constexpr int MSM_BUCKET_MIN = 1 << 30;   // batch size from which the verifier takes the bucket method by itself (measured: see DESIGN.md section 4.3)
+cudaError_t launch_msm_bucket(const G1Affine* pts, const uint32_t* scalars0, const uint32_t* scalars1, int n, G1Jac* out0, G1Jac* out1, void* scratch,
+                              cudaStream_t st);
 constexpr int PAIRING_INPUT_WORDS = 37;   // per point: Jacobian X, Y, Z (Montgomery limbs) + identity flag
 cudaError_t launch_pairing_inputs(const G1Jac* a0, const G1Jac* b0, const G1Jac* b1, const G1Jac* b2, uint32_t* out, cudaStream_t st);
 cudaError_t launch_kzg_verify_pairs(const G1Affine* commitments, const G1Affine* proofs, const Fr* z, const Fr* y, const Fr* rpow, G1Affine* pts,

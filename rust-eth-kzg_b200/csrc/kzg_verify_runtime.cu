@@ -183,7 +183,14 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
             EKZG_CUDA(cudaStreamWaitEvent(sc, wsp->sub_ready[0], 0));
             // (A)  P = sum rho_k pi_k ; W = sum rho_k h_k^64 pi_k  (verifier.rs:188-213)
             static const bool force_columns = getenv("EKZG_VERIFY_COLUMN_SUMS") != nullptr;
-            if (N <= 32768 && !force_columns) {
+            // EKZG_VERIFY_MSM=bucket | ladder: the bucket-method MSM (K7, kzg_kernels_msm.cu) for both sums, or never; default: by size
+            const char* msm_env = getenv("EKZG_VERIFY_MSM");
+            const bool bucket = msm_env ? msm_env[0] == 'b' : (N >= MSM_BUCKET_MIN && N <= 32768);
+            if (bucket && !force_columns) {
+                uint8_t* d_msm;
+                EKZG_TRY(S.get(&d_msm, msm_bucket_scratch_bytes(N, 2)));
+                EKZG_CUDA(launch_msm_bucket(a_p, d_s1, d_s2, N, &d_sums[0], &d_sums[1], d_msm, st));
+            } else if (N <= 32768 && !force_columns) {
                 // two passes of N scalar multiplications at the same time (the machine holds both; 16384 points are 512 warps)
                 EKZG_CUDA(cudaStreamWaitEvent(sd, wsp->sub_ready[0], 0));
                 EKZG_CUDA(launch_scalar_mul(a_p, d_s1, d_mul, N, st));

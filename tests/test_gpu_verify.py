@@ -166,3 +166,26 @@ def test_verify_cell_batch_column_sum_path():
     env = dict(os.environ, EKZG_VERIFY_COLUMN_SUMS="1")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_verify_cell_batch_bucket_msm(vec_ctx, pkg, monkeypatch):
+    """EKZG_VERIFY_MSM=bucket sends the two random-linear-combination sums through the bucket-method MSM (K7, kzg_kernels_msm.cu)
+    instead of one ladder per point: every consensus vector, then 40 blobs x 128 cells (5120 openings: every bucket of every
+    window is hit) honest / one corrupted cell / swapped proofs, with the ladder path as the cross-check."""
+    monkeypatch.setenv("EKZG_VERIFY_MSM", "bucket")
+    for name, inp, expected in vectors.load("verify_cell_kzg_proof_batch"):
+        got = _run(pkg, vec_ctx.verify_cell_kzg_proof_batch, inp["commitments"], inp["cell_indices"], inp["cells"], inp["proofs"])
+        assert got == expected, name
+    C, I, CL, PR = _openings(vec_ctx, pkg, 40, 7700)
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, CL, PR) is True
+    sel = list(range(0, len(C), 3))[::-1]       # a ragged, reordered subset
+    assert vec_ctx.verify_cell_kzg_proof_batch([C[i] for i in sel], [I[i] for i in sel], [CL[i] for i in sel], [PR[i] for i in sel]) is True
+    bad = list(CL)
+    bad[3333] = bad[3333][:100] + bytes([bad[3333][100] ^ 4]) + bad[3333][101:]
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, bad, PR) is False
+    badp = list(PR)
+    badp[10], badp[11] = PR[11], PR[10]
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, CL, badp) is False
+    monkeypatch.setenv("EKZG_VERIFY_MSM", "ladder")
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, CL, PR) is True
+    assert vec_ctx.verify_cell_kzg_proof_batch(C, I, bad, PR) is False
