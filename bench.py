@@ -498,7 +498,7 @@ def main():
         if extras and world == 1:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
             import bench_configs as bc
-            line["abi_single_blob"] = bc.abi_load(threads=1024, calls=8)
+            line["abi_single_blob"] = bc.abi_load(threads=1024, calls=16)
         if not args.no_cpu_baseline and world == 1:
             try:
                 # bounded sample: ~20 s of CPU work on a 16-thread host (the oracle port does ~3 blobs/s/thread)

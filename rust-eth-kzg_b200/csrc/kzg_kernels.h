@@ -28,6 +28,7 @@ size_t fixed_msm_scratch_bytes(const MsmTable& T);
 size_t g1_ntt_queue_words(int B);
 size_t g1_ntt_scratch_bytes();   // per concurrently running K5 launch (odd-multiples tables of the resident warps); 0 on error
 cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* queue, void* scratch, cudaStream_t st);
+void set_k5_throughput_hint(bool on);   // this thread's next K5 launches: least work (radix-2) rather than shortest chain, for batches above 64 blobs
 cudaError_t launch_fk20_g1_ntts(G1Jac* pts, int B, uint32_t* queue, void* scratch, cudaStream_t st);
 cudaError_t launch_g1_compress(const G1Jac* pts, uint8_t* out, int npos, int B, cudaStream_t st);
 cudaError_t launch_g1_decompress(const uint8_t* in, G1Affine* out, uint32_t* status, int n, cudaStream_t st);

@@ -780,11 +780,15 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
         Status s = Status::Ok();
         try {
             std::fill(st.status.begin(), st.status.begin() + n, 0);
+            // other batches are on the device already: this one cannot have it to itself, so ask for the G1-NTT kernel with the
+            // least work (kzg_kernels.h) instead of the latency-mode one
+            set_k5_throughput_hint(flying >= 1);
             if (recover) s = recover_cells_and_kzg_proofs_strided(n, st.counts.data(), st.indices.data(), st.in, st.cells, st.proofs, st.status.data());
             else s = compute_cells_and_kzg_proofs_batch(n, st.in, st.cells, want_proofs ? st.proofs : nullptr, st.status.data(), want_proofs);
         } catch (const std::exception& ex) {             // fail the batch, never the queue
             s = Status::Error(std::string("batch failed: ") + ex.what());
         }
+        set_k5_throughput_hint(false);
         if (trace) {
             const auto t_done = std::chrono::steady_clock::now();
             fprintf(stderr, "[ekzg trace] coalesced batch of %d (queue %d, %d already on the device): formed in %.2f ms, ran %.2f ms\n", n, which, flying,

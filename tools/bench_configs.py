@@ -305,7 +305,7 @@ def pageable(ctx, pkg, reps=3):
     return {"workload": "compute_cells_and_kzg_proofs, batch of 1024 blobs, PAGEABLE host buffers through the C ABI", "metric": "blobs/s", "value": n / t, "ms": 1e3 * t}
 
 
-def abi_load(threads=1024, calls=8, mode="compute", timeout=600, env=None):
+def abi_load(threads=1024, calls=16, mode="compute", timeout=600, env=None):
     """tools/abi_load.c (native pthreads, no Python): T callers of the reference's per-item symbol on one shared context.
     Creates its own context, so the caller must have released the device memory of any other."""
     exe = os.path.join(ROOT, "rust-eth-kzg_b200", "lib", "abi_load")

@@ -21,6 +21,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--blobs", type=int, default=16384)
     ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--mixed", type=int, default=1, help="cycle the batch size through 1024 / 256 / 96 / 33 / 512 / 7 (the latency-mode "
+                    "G1-NTT kernel on context A below 257 blobs, the wide kernel forced on context B) instead of --batch every round")
     args = ap.parse_args()
     pkg = __graft_entry__.load_package()
     import importlib
@@ -42,10 +44,14 @@ def main():
         key = np.frombuffer(hashlib.sha256(b"soak" + rnd.to_bytes(4, "little")).digest()[1:], dtype=np.uint8)
         arr = base_arr.copy()
         arr[:, 1:] ^= key
-        flat = arr.tobytes()
-        n = args.batch
+        n = (1024, 256, 96, 33, 512, 7)[rnd % 6] if args.mixed else args.batch
+        n = min(n, args.batch)
+        flat = arr[:n * 4096].tobytes()
+        os.environ.pop("EKZG_K5_R4_MAX", None)
         ca, pa, _ = a.compute_cells_and_kzg_proofs_batch(flat, n)
+        os.environ["EKZG_K5_R4_MAX"] = "0"      # context B: always the radix-2 G1-NTT kernel
         cb, pb, _ = b.compute_cells_and_kzg_proofs_batch(flat, n)
+        os.environ.pop("EKZG_K5_R4_MAX", None)
         ka, _ = a.blob_to_kzg_commitment_batch(flat, n)
         kb, _ = b.blob_to_kzg_commitment_batch(flat, n)
         qa, _ = a.compute_blob_kzg_proof_batch(flat, ka, n)
