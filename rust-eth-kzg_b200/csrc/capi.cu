@@ -94,7 +94,8 @@ CResult eth_kzg_b200_compute_cells_and_kzg_proofs_device(const DASContext* ctx, 
     const ekzg::Context& c = *owner;
     Status s = c.bind_device();
     if (!s.ok) return c_err(s.msg);
-    ekzg::Workspace* ws = c.acquire((int)n, false);
+    // (one or two blobs take the direct proof path, which wants room for 128 virtual blobs per blob: kzg_runtime.h)
+    ekzg::Workspace* ws = c.acquire(d_proofs && n <= (uint64_t)ekzg::direct_proofs_max() ? ekzg::N_CELLS * (int)n : (int)n, false);
     if (!ws) return c_err("device memory allocation failed");
     cudaStream_t st = (cudaStream_t)cuda_stream;
     cudaStreamWaitEvent(st, ws->done, 0);  // the scratch buffers' previous user may have run on another stream

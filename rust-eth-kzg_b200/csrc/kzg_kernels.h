@@ -40,6 +40,7 @@ cudaError_t launch_srs_table_setup(const G1Affine* srs, int npoints, G1Affine* q
 cudaError_t launch_blob_challenge(const uint8_t* blobs, const uint8_t* commitments, Fr* z, int B, cudaStream_t st);
 cudaError_t launch_scalars_from_be(const uint8_t* in, Fr* out, uint32_t* status, int n, cudaStream_t st);
 cudaError_t launch_quotient(const Fr* coeffs, const Fr* z, uint32_t* scalars, uint8_t* y_out, int B, cudaStream_t st);
+cudaError_t launch_coset_quotients(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int nblobs, cudaStream_t st);   // [4096][128 nblobs] plain
 cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B, cudaStream_t st);
 cudaError_t launch_sum_positions(G1Jac* pts, int B, int count, int stride, cudaStream_t st);
 cudaError_t launch_g1_subgroup(const G1Affine* pts, uint32_t* status, int n, const G1Affine* pts2, uint32_t* status2, int n2, cudaStream_t st);   // status 2 where a decompressed point is outside G1

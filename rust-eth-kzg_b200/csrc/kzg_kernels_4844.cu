@@ -164,6 +164,42 @@ k_quotient(const Fr* __restrict__ coeffs, const Fr* __restrict__ z_in, uint32_t*
     }
 }
 
+// DIRECT cell proofs for a blob or two (the latency path of compute_cells_and_kzg_proofs):  proof k of a blob is the commitment to
+//   q_k(X) = f(X) div (X^64 - c_k),   c_k = omega_128^rev7(k) = h_k^64 for the coset h_k <omega_64> of cell k
+// (kzg_multi_open/src/fk20/prover.rs:173-228 computes the same 128 commitments through the Toeplitz / G1-FFT route, whose 14-phase
+// dependency chain costs ~10 ms however few blobs there are; 128 independent 4096-point MSMs over the fixed SRS tables are
+// throughput work -- 10.5 M table additions, ~4 ms -- and win for one or two blobs).  The quotient by X^64 - c is 64 independent
+// Horner recurrences of 63 steps: q[r + 64 m] = f[r + 64 (m+1)] + c q[r + 64 (m+1)].
+// Thread (r, vb): residue r < 64, virtual blob vb = blob * 128 + k; scalars [4096][Bv] plain, the layout k_coeffs_to_scalars writes.
+__global__ void __launch_bounds__(128)
+k_coset_quotients(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars, const Fr* __restrict__ tw128, int Bv) {
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (size_t)64 * Bv) return;
+    const int r = (int)(gid / Bv), vb = (int)(gid % Bv), blob = vb >> 7, k = vb & 127;
+    int e = 0;
+    for (int bit = 0; bit < 7; bit++) e |= ((k >> bit) & 1) << (6 - bit);
+    Fr c = ld_vec(&tw128[e & 63]);
+    if (e >= 64) fe_neg(c, c);
+    const Fr* f = coeffs + (size_t)blob * N_BLOB;
+    Fr q;
+    fe_set_zero(q);
+    {   // block 63 of the quotient is zero
+        uint4* d4 = reinterpret_cast<uint4*>(scalars + ((size_t)(r + 64 * 63) * Bv + vb) * 8);
+        d4[0] = make_uint4(0, 0, 0, 0);
+        d4[1] = make_uint4(0, 0, 0, 0);
+    }
+    for (int m = 62; m >= 0; m--) {
+        const Fr fi = ld_vec(&f[r + 64 * (m + 1)]);
+        fe_mul(q, q, c);
+        fe_add(q, q, fi);
+        Fr v;
+        fe_from_mont(v, q);
+        uint4* d4 = reinterpret_cast<uint4*>(scalars + ((size_t)(r + 64 * m) * Bv + vb) * 8);
+        d4[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]);
+        d4[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+    }
+}
+
 // coefficients [B][4096] (Montgomery) -> plain MSM scalars [4096][B]
 __global__ void k_coeffs_to_scalars(const Fr* __restrict__ coeffs, uint32_t* __restrict__ scalars, int B) {
     size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -263,6 +299,12 @@ cudaError_t launch_quotient(const Fr* coeffs, const Fr* z, uint32_t* scalars, ui
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;
 }
+cudaError_t launch_coset_quotients(const Fr* coeffs, uint32_t* scalars, const DevTables& T, int nblobs, cudaStream_t st) {
+    const int Bv = 128 * nblobs;
+    k_coset_quotients<<<(unsigned)(((size_t)64 * Bv + 127) / 128), 128, 0, st>>>(coeffs, scalars, T.tw128, Bv);
+    EKZG_LAUNCH_CHECK();
+    return cudaSuccess;
+}
 cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B, cudaStream_t st) {
     size_t n = (size_t)N_BLOB * B;
     k_coeffs_to_scalars<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(coeffs, scalars, B);
@@ -270,7 +312,7 @@ cudaError_t launch_coeffs_to_scalars(const Fr* coeffs, uint32_t* scalars, int B,
     return cudaSuccess;
 }
 cudaError_t launch_sum_positions(G1Jac* pts, int B, int count, int stride, cudaStream_t st) {
-    if (B <= 64 && count <= 64) k_sum_positions_tree<<<B, 64, 0, st>>>(pts, B, count, stride);
+    if (B <= 256 && count <= 64) k_sum_positions_tree<<<B, 64, 0, st>>>(pts, B, count, stride);
     else k_sum_positions<<<(B + 63) / 64, 64, 0, st>>>(pts, B, count, stride);
     EKZG_LAUNCH_CHECK();
     return cudaSuccess;

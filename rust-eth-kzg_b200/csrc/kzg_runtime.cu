@@ -69,6 +69,12 @@ void host_blob_challenge(const uint8_t* blob, const uint8_t* commitment48, uint8
         for (int b = 0; b < 8; b++) z_be[8 * (3 - i) + b] = (uint8_t)(v[i] >> (8 * (7 - b)));
 }
 
+int direct_proofs_max() {
+    const char* e = getenv("EKZG_DIRECT_MAX");
+    const int v = e ? atoi(e) : 2;
+    return v < 0 ? 0 : (v > 8 ? 8 : v);
+}
+
 int chunk_capacity() {
     const char* e = getenv("EKZG_CHUNK");
     int c = e ? atoi(e) : 1024;
@@ -428,8 +434,21 @@ int Context::collect_stage_times(double* ms) const {
     return n;
 }
 
+// One or two blobs: every proof as its own 4096-point MSM over the SRS tables (see k_coset_quotients) -- 128 n "virtual blobs"
+// through the commitment pipeline: quotients -> fixed-base MSM (64 partial sums each) -> tree sum -> compression.
+Status Context::proofs_direct_device(Workspace& ws, int n, uint8_t* d_proofs, cudaStream_t stream) const {
+    const int Bv = N_CELLS * n;
+    if (Bv > ws.capacity) return Status::Error("workspace too small for the direct proof path");
+    EKZG_CUDA(launch_coset_quotients(ws.d_coeffs, ws.d_scalars, T_, n, stream));
+    EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.srs, N_BLOB / FK20_POINTS, Bv, stream, 0, -1, ws.d_msm_scratch));
+    EKZG_CUDA(launch_sum_positions(ws.d_pts, Bv, N_BLOB / FK20_POINTS, 2, stream));
+    EKZG_CUDA(launch_g1_compress(ws.d_pts, d_proofs, 1, Bv, stream));
+    return Status::Ok();
+}
+
 Status Context::fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* /*d_cells*/, uint8_t* d_proofs, cudaStream_t stream,
                                         std::vector<cudaEvent_t>* ev) const {
+    if (!ev && n <= direct_proofs_max() && N_CELLS * n <= ws.capacity) return proofs_direct_device(ws, n, d_proofs, stream);
     EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, n, stream));
     if (ev) cudaEventRecord((*ev)[2], stream);
     EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, n, stream, 0, -1, ws.d_msm_scratch));
@@ -498,7 +517,8 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
     EKZG_TRY(bind_device());
     const int cap = (int)std::min<uint64_t>(n, (uint64_t)chunk_capacity());
     const uint64_t nchunks = (n + cap - 1) / cap;
-    Workspace* W[2] = {acquire(cap, true), nchunks > 1 ? acquire(cap, true) : nullptr};
+    const bool direct = want_proofs && n <= (uint64_t)direct_proofs_max();   // latency path: see proofs_direct_device
+    Workspace* W[2] = {acquire(direct ? N_CELLS * (int)n : cap, true), nchunks > 1 ? acquire(cap, true) : nullptr};
     if (!W[0] || (nchunks > 1 && !W[1])) {
         for (Workspace* w : W) if (w) give_back(w);
         return Status::Error("device/pinned memory allocation failed");
@@ -593,16 +613,21 @@ Status Context::compute_cells_and_kzg_proofs_batch(uint64_t n, const uint8_t* bl
                 EKZG_CUDA(cudaMemcpyAsync(dst, ws.d_cells + (size_t)o * CELLS_PER_BLOB, (size_t)c * CELLS_PER_BLOB, cudaMemcpyDeviceToHost, ws.copy_stream));
                 EKZG_CUDA(cudaEventRecord(ws.sub_out[s], ws.copy_stream));
             }
-            if (want_proofs) {
+            if (want_proofs && !direct) {
                 EKZG_CUDA(launch_toeplitz_scalars(ws.d_coeffs, ws.d_scalars, T_, cnt, ws.stream, o, c));
                 EKZG_CUDA(launch_fixed_msm(ws.d_scalars, ws.d_pts, T_.fk20, FK20_MSMS, cnt, ws.stream, o, c, ws.d_msm_scratch));
                 stamp("K4 done, piece", s, ws.stream);
             }
         }
         if (want_proofs) {
-            EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, cnt, ws.d_queue, ws.d_ntt_scratch, ws.stream));
-            stamp("K5 done", -1, ws.stream);
-            EKZG_CUDA(launch_g1_compress(ws.d_pts, ws.d_proofs, N_CELLS, cnt, ws.stream));
+            if (direct) {
+                EKZG_TRY(proofs_direct_device(ws, cnt, ws.d_proofs, ws.stream));
+                stamp("direct proofs done", -1, ws.stream);
+            } else {
+                EKZG_CUDA(launch_fk20_g1_ntts(ws.d_pts, cnt, ws.d_queue, ws.d_ntt_scratch, ws.stream));
+                stamp("K5 done", -1, ws.stream);
+                EKZG_CUDA(launch_g1_compress(ws.d_pts, ws.d_proofs, N_CELLS, cnt, ws.stream));
+            }
             EKZG_CUDA(cudaMemcpyAsync(proofs_pinned ? proofs + first * PROOFS_PER_BLOB : ws.h_proofs, ws.d_proofs, (size_t)cnt * PROOFS_PER_BLOB,
                                       cudaMemcpyDeviceToHost, ws.stream));
             stamp("K6 + proofs D2H done", -1, ws.stream);
@@ -920,7 +945,8 @@ Status Context::recover_impl(uint64_t n, const uint64_t* counts, const uint64_t*
         }
     }
     const int cap = (int)std::min<uint64_t>(n, (uint64_t)chunk_capacity());
-    Workspace* wsp = acquire(cap, true);
+    // (one or two blobs: room for the direct proof path, 128 virtual blobs per blob)
+    Workspace* wsp = acquire(n <= (uint64_t)direct_proofs_max() ? N_CELLS * (int)n : cap, true);
     if (!wsp) return Status::Error("device/pinned memory allocation failed");
     Workspace& ws = *wsp;
     Status result = ws.ensure_recover_buffers();

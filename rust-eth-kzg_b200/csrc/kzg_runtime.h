@@ -89,6 +89,8 @@ public:
     Status fk20_device(Workspace& ws, int n, const uint8_t* d_blobs, uint8_t* d_cells, uint8_t* d_proofs, uint32_t* d_status,
                        cudaStream_t stream) const;
     // same, starting from coefficients already in ws.d_coeffs (recovery path)
+    // proofs of n <= direct_proofs_max() blobs from ws.d_coeffs by the direct route (needs ws.capacity >= 128 n)
+    Status proofs_direct_device(Workspace& ws, int n, uint8_t* d_proofs, cudaStream_t stream) const;
     Status fk20_from_coeffs_device(Workspace& ws, int n, uint8_t* d_cells, uint8_t* d_proofs, cudaStream_t stream,
                                    std::vector<cudaEvent_t>* stage_events = nullptr) const;
 
@@ -216,6 +218,9 @@ private:
 };
 
 int chunk_capacity();
+// up to this many blobs per call take the DIRECT proof path (128 SRS MSMs per blob instead of the FK20 route; EKZG_DIRECT_MAX, 0 = off);
+// a workspace must hold 128 "virtual blobs" per blob for it
+int direct_proofs_max();
 // z = SHA-256("FSBLOBVERIFY_V1_" || u128_be(4096) || blob || commitment) mod r as 32 canonical big-endian bytes
 // (crates/eip4844/src/verifier.rs:155-196) on the HOST: for a handful of blobs the x86 SHA extensions (0.1 ms per blob) beat the
 // device kernel, where one thread walks the 2049 compressions of a blob (~4 ms whatever the count).

@@ -160,6 +160,7 @@ def test_k5_radix4_equals_radix2(vec_ctx, pkg, n, monkeypatch):
     if n >= 31:
         blobs[3:7] = list(syn.edge_blobs())[:4]
     flat = b"".join(blobs)
+    monkeypatch.setenv("EKZG_DIRECT_MAX", "0")      # (one or two blobs would otherwise not reach the G1 transforms at all)
     monkeypatch.setenv("EKZG_K5_R4_MAX", "0")
     want = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
     monkeypatch.setenv("EKZG_K5_R4_MAX", "256")
@@ -191,3 +192,30 @@ def test_k4_alternative_forms_equal_default(vec_ctx, pkg, form, monkeypatch):
     c = vec_ctx.blob_to_kzg_commitment(blobs[0])
     monkeypatch.delenv("EKZG_K4")
     assert c == vec_ctx.blob_to_kzg_commitment(blobs[0])
+
+
+def test_direct_proofs_equal_fk20(vec_ctx, pkg, monkeypatch):
+    """the latency path for one or two blobs -- every proof as its own 4096-point MSM of f div (X^64 - c_k) over the SRS tables
+    (EKZG_DIRECT_MAX, default 2) -- against the FK20 route on the same blobs: synthetic, all-zero, all r-1, constant (128 identity
+    proofs) and the reference bench's blob; through the batch entry point, the single-blob symbol, recovery, and the oracle"""
+    from oracle import cref
+    syn = _synth(pkg)
+    cases = [syn.blob(9100), syn.blob(9101)] + list(syn.edge_blobs())[:4]
+    for i in range(0, len(cases), 2):
+        pair = cases[i:i + 2]
+        flat = b"".join(pair)
+        monkeypatch.setenv("EKZG_DIRECT_MAX", "0")
+        want = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, 2)
+        want1 = vec_ctx.compute_cells_and_kzg_proofs(pair[0])
+        monkeypatch.setenv("EKZG_DIRECT_MAX", "2")
+        got = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, 2)
+        got1 = vec_ctx.compute_cells_and_kzg_proofs(pair[0])
+        assert got == want, "direct proofs of pair %d differ from the FK20 route" % i
+        assert got1 == want1
+        keep = list(range(1, 128, 2))
+        rc, rp = vec_ctx.recover_cells_and_kzg_proofs(keep, [got1[0][j] for j in keep])
+        assert (rc, rp) == (got1[0], got1[1])
+    oc, op = cref.compute_cells_and_kzg_proofs(cases[0])
+    monkeypatch.setenv("EKZG_DIRECT_MAX", "2")
+    c, p = vec_ctx.compute_cells_and_kzg_proofs(cases[0])
+    assert (c, p) == (list(oc), list(op))
