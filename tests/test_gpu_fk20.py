@@ -36,9 +36,13 @@ def test_fk20_stages_match_oracle(das_ctx, pkg):
     assert not badh, "h mismatches at i = %r" % badh[:10]
 
 
+@pytest.mark.parametrize("route", ["direct", "fk20"])
 @pytest.mark.parametrize("name,inp,expected", [pytest.param(n, i, o, id=n) for n, i, o in vectors.load("compute_cells_and_kzg_proofs")])
-def test_consensus_vectors(vec_ctx, pkg, name, inp, expected):
-    """crates/eip7594/tests/compute_cells_and_kzg_proofs.rs: byte-exact cells+proofs, `output: null` <=> Err"""
+def test_consensus_vectors(vec_ctx, pkg, name, inp, expected, route, monkeypatch):
+    """crates/eip7594/tests/compute_cells_and_kzg_proofs.rs: byte-exact cells+proofs, `output: null` <=> Err -- on both routes a
+    single-blob call can take: the direct one (128 SRS MSMs, the default for one blob) and FK20 (EKZG_DIRECT_MAX=0)"""
+    if route == "fk20":
+        monkeypatch.setenv("EKZG_DIRECT_MAX", "0")
     try:
         cells, proofs = vec_ctx.compute_cells_and_kzg_proofs(inp["blob"])
         got = [cells, proofs]

@@ -11,8 +11,12 @@ from tests import vectors
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("route", ["direct", "fk20"])
 @pytest.mark.parametrize("name,inp,expected", [pytest.param(n, i, o, id=n) for n, i, o in vectors.load("recover_cells_and_kzg_proofs")])
-def test_recover_vectors(vec_ctx, pkg, name, inp, expected):
+def test_recover_vectors(vec_ctx, pkg, name, inp, expected, route, monkeypatch):
+    """(both routes the proofs of a single recovered blob can take: direct and, with EKZG_DIRECT_MAX=0, FK20)"""
+    if route == "fk20":
+        monkeypatch.setenv("EKZG_DIRECT_MAX", "0")
     try:
         cells, proofs = vec_ctx.recover_cells_and_kzg_proofs(inp["cell_indices"], inp["cells"])
         got = [cells, proofs]
