@@ -111,6 +111,19 @@ CResult eth_kzg_verify_blob_kzg_proof_batch(const DASContext *ctx, uint64_t blob
  * Additive B200 entry points (not in the reference; SURVEY.md §8b "Gap vs BASELINE.json configs").
  * ---------------------------------------------------------------------------------------------- */
 
+/* A context over a CALLER-SUPPLIED trusted setup: the C-ABI form of what a Rust user of the reference writes as
+ *   DASContext::new(&TrustedSetup::from_json(json), use_precomp)            (subgroup_check = true)
+ *   DASContext::new(&TrustedSetup::from_json_unchecked(json), use_precomp)  (subgroup_check = false)
+ * (crates/trusted_setup/src/lib.rs:112-127, crates/eip7594/src/lib.rs DASContext::new, crates/eip7594/src/trusted_setup.rs:6-23).
+ * `json` is the consensus-specs file layout: {"g1_monomial": 4096 x "0x" + 96 hex digits, "g2_monomial": 65 x "0x" + 192 hex
+ * digits, ...}; other keys (g1_lagrange) are skipped as the reference skips them.  The 4096 G1 points are decompressed and
+ * checked (curve equation; prime-order subgroup unless subgroup_check is false) on the device, the 65 G2 points on the host;
+ * the FK20 and SRS tables are then built from them exactly as for the embedded setup.  Where the reference panics (malformed
+ * JSON, missing "0x", wrong length, invalid point) this returns Err and leaves *out_ctx NULL.  Free with
+ * eth_kzg_das_context_free. */
+CResult eth_kzg_b200_das_context_new_from_json(const char *json, uint64_t json_len, bool subgroup_check, bool use_precomp,
+                                               DASContext **out_ctx);
+
 /* n independent blobs in one call, HOST buffers, contiguous: blobs = n*131072 B, out_cells = n*128*2048 B,
  * out_proofs = n*128*48 B.  blob_status[i] (optional, may be NULL) is 0 for a valid blob and 1 for a
  * non-canonical one, whose outputs are left unspecified; the call returns Err iff any blob is invalid.
@@ -179,6 +192,13 @@ CResult eth_kzg_b200_debug_g1_ntt_prefix(const DASContext *ctx, const uint8_t *b
 int eth_kzg_b200_debug_pairing_check(int n, const uint8_t *g1_xy, const int *g2_sel);
 /* Test hook (host only): the pairing's sparse line product and cyclotomic squaring against its general Fp12 routines; 1 = agree. */
 int eth_kzg_b200_debug_pairing_selftest(void);
+/* Test hooks of the setup loader (host only, no GPU): the JSON parser (point counts, first G1 / last G2 point as bytes), the G2
+ * decompression (out24 = x.c0, x.c1, y.c0, y.c1 as plain little-endian 64-bit limbs; 0 ok, 1 malformed, 2 off the curve,
+ * 3 outside the subgroup, 4 infinity) and the whole G2 side of a setup (65 points). */
+CResult eth_kzg_b200_debug_parse_trusted_setup_json(const char *json, uint64_t json_len, uint64_t *n_g1, uint64_t *n_g2,
+                                                    uint8_t *first_g1_48, uint8_t *last_g2_96);
+int eth_kzg_b200_debug_g2_decompress(const uint8_t *in96, uint64_t *out24);
+CResult eth_kzg_b200_debug_g2_keys(const uint8_t *g2_65x96, int count, bool subgroup_check);
 
 /* Test hook (host only): SHA-256 of data[0..n) through the library's transcript hasher (x86 SHA extensions when
  * present), fed as two updates split at `split`; force_portable != 0 runs the portable C block function instead. */

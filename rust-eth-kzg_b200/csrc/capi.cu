@@ -55,6 +55,44 @@ DASContext* eth_kzg_das_context_new(bool use_precomp) {
     return d;
 }
 
+CResult eth_kzg_b200_das_context_new_from_json(const char* json, uint64_t json_len, bool subgroup_check, bool use_precomp, DASContext** out_ctx) {
+    DeviceGuard guard;
+    if (!out_ctx) return c_err("out_ctx is null");
+    *out_ctx = nullptr;
+    ekzg::SetupBytes setup;
+    Status s = ekzg::parse_trusted_setup_json(json, (size_t)json_len, &setup);
+    if (!s.ok) return to_c(s);
+    setup.subgroup_check = subgroup_check;
+    std::unique_ptr<ekzg::DeviceSet> c;
+    s = ekzg::DeviceSet::create(use_precomp, &c, &setup);
+    if (!s.ok) return to_c(s);
+    DASContext* d = new DASContext();
+    d->set = std::move(c);
+    *out_ctx = d;
+    return c_ok();
+}
+
+// Test hooks (host only, need no GPU): the JSON parser (returns the point counts) and the G2 decompression of the setup loader.
+CResult eth_kzg_b200_debug_parse_trusted_setup_json(const char* json, uint64_t json_len, uint64_t* n_g1, uint64_t* n_g2, uint8_t* first_g1_48,
+                                                    uint8_t* last_g2_96) {
+    ekzg::SetupBytes setup;
+    Status s = ekzg::parse_trusted_setup_json(json, (size_t)json_len, &setup);
+    if (!s.ok) return to_c(s);
+    *n_g1 = setup.g1_monomial.size() / 48;
+    *n_g2 = setup.g2_monomial.size() / 96;
+    if (first_g1_48 && *n_g1) memcpy(first_g1_48, setup.g1_monomial.data(), 48);
+    if (last_g2_96 && *n_g2) memcpy(last_g2_96, setup.g2_monomial.data() + setup.g2_monomial.size() - 96, 96);
+    return c_ok();
+}
+int eth_kzg_b200_debug_g2_decompress(const uint8_t* in96, uint64_t* out24) { return ekzg::host::g2_decompress_plain(in96, out24); }
+CResult eth_kzg_b200_debug_g2_keys(const uint8_t* g2_65x96, int count, bool subgroup_check) {
+    std::string err;
+    ekzg::host::G2Keys* k = ekzg::host::g2_keys_from_compressed(g2_65x96, count, subgroup_check, &err);
+    if (!k) return c_err(err);
+    ekzg::host::g2_keys_free(k);
+    return c_ok();
+}
+
 void eth_kzg_das_context_free(DASContext* ctx) {
     DeviceGuard guard;
     if (ctx) delete ctx;

@@ -10,6 +10,7 @@
 #include <immintrin.h>
 #include <cstring>
 #include <mutex>
+#include <string>
 #include <vector>
 #include "host_consts.h"
 
@@ -354,6 +355,11 @@ struct Pt { Fp x, y; const std::vector<Line>* ls; };   // affine, Montgomery for
 bool pairing_product_is_one(const std::vector<Pt>& pts);
 }
 
+// The line tables of a caller-supplied setup's [1]_2, [tau]_2, [tau^64]_2 and their negations (G2Sel index), built once by
+// g2_keys_from_compressed; the embedded ceremony's tables live in g_state.
+struct G2Keys { std::vector<Line> lines[6]; };
+static inline const std::vector<Line>& lines_of(const G2Keys* keys, G2Sel sel) { return keys ? keys->lines[(int)sel] : g_state.lines[(int)sel]; }
+
 bool pairing_check(const PairingInput* in, int n) {
     std::call_once(g_once, init_state);
     if (!g_state.ok) return false;
@@ -368,7 +374,7 @@ bool pairing_check(const PairingInput* in, int n) {
     return pairing_product_is_one(pts);
 }
 
-bool pairing_check_jac(const PairingInputJac* in, int n) {
+bool pairing_check_jac(const PairingInputJac* in, int n, const G2Keys* keys) {
     std::call_once(g_once, init_state);
     if (!g_state.ok) return false;
     std::vector<Pt> pts;
@@ -380,7 +386,7 @@ bool pairing_check_jac(const PairingInputJac* in, int n) {
         fp_inv(zi, Z); fp_sqr(zi2, zi); fp_mul(zi3, zi2, zi);
         Pt p;
         fp_mul(p.x, X, zi2); fp_mul(p.y, Y, zi3);
-        p.ls = &g_state.lines[(int)in[i].g2];
+        p.ls = &lines_of(keys, in[i].g2);
         pts.push_back(p);
     }
     return pairing_product_is_one(pts);
@@ -452,6 +458,179 @@ bool pairing_selftest() {
         f12_mul(t, a, f12_is_one(a) ? a : t);
     }
     return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Caller-supplied trusted setup: the 65 G2 points of `g2_monomial` in the ZCash compressed form (96 bytes: x.c1 || x.c0 big-endian,
+// flag bits compressed / infinity / y-is-the-larger-root in the top three bits), as deserialize_g2_points hands them to blstrs'
+// G2Affine::from_compressed[_unchecked] (crates/serialization/src/trusted_setup.rs, crates/trusted_setup/src/lib.rs:40-61):
+// field elements canonical, point on the twist, and -- with the subgroup check on -- [r]Q = O for every one of them.
+static bool fp_from_be48(Fp& out, const uint8_t* b, bool mask_flags) {
+    uint64_t t[6];
+    for (int i = 0; i < 6; i++) {
+        uint64_t w = 0;
+        for (int k = 0; k < 8; k++) w = (w << 8) | b[(5 - i) * 8 + k];
+        t[i] = w;
+    }
+    if (mask_flags) t[5] &= 0x1fffffffffffffffULL;
+    if (ge_p(t)) return false;
+    out = fp_from_plain(t);
+    return true;
+}
+static void fp_to_plain(uint64_t* out, const Fp& a) {
+    Fp one_plain; memset(&one_plain, 0, sizeof one_plain); one_plain.v[0] = 1;
+    Fp o; fp_mul(o, a, one_plain);
+    memcpy(out, o.v, 48);
+}
+// a > (p-1)/2 as a plain integer  <=>  2a > p - 1  <=>  2a >= p + 1 (p odd)  <=>  2a > p
+static bool fp_is_larger_half(const Fp& a) {
+    uint64_t t[7], c = 0;
+    uint64_t pl[6]; fp_to_plain(pl, a);
+    for (int i = 0; i < 6; i++) { t[i] = (pl[i] << 1) | c; c = pl[i] >> 63; }
+    t[6] = c;
+    if (t[6]) return true;
+    for (int i = 5; i >= 0; i--) { if (t[i] > FP_P[i]) return true; if (t[i] < FP_P[i]) return false; }
+    return false;
+}
+// square root in Fp (p = 3 mod 4): a^((p+1)/4), checked
+static bool fp_sqrt(Fp& r, const Fp& a) {
+    uint64_t e[6], c = 1;
+    for (int i = 0; i < 6; i++) { const uint64_t s = FP_P[i] + c; c = (s < c) ? 1 : 0; e[i] = s; }   // p + 1 (no overflow: p < 2^381)
+    for (int i = 0; i < 6; i++) e[i] = (e[i] >> 2) | (i < 5 ? e[i + 1] << 62 : 0);
+    Fp acc = fp_one();
+    for (int i = 383; i >= 0; i--) {
+        fp_sqr(acc, acc);
+        if ((e[i / 64] >> (i % 64)) & 1) fp_mul(acc, acc, a);
+    }
+    Fp chk; fp_sqr(chk, acc);
+    r = acc;
+    return fp_eq(chk, a);
+}
+// square root in Fp2 = Fp[u]/(u^2+1): x0^2 = (a0 +- sqrt(a0^2 + a1^2))/2, x1 = a1 / (2 x0); checked by squaring
+static bool f2_sqrt(Fp2& r, const Fp2& a) {
+    Fp2 x = f2_zero();
+    if (fp_is_zero(a.c1)) {
+        Fp s;
+        if (fp_sqrt(s, a.c0)) { x.c0 = s; }
+        else { Fp na; fp_neg(na, a.c0); if (!fp_sqrt(s, na)) return false; x.c1 = s; }
+    } else {
+        Fp n, t, s, d, two_inv, x0;
+        fp_sqr(n, a.c0); fp_sqr(t, a.c1); fp_add(n, n, t);
+        if (!fp_sqrt(s, n)) return false;                       // the norm of a square is a square
+        Fp two = fp_one(); fp_add(two, two, two); fp_inv(two_inv, two);
+        fp_add(d, a.c0, s); fp_mul(d, d, two_inv);
+        if (!fp_sqrt(x0, d)) { fp_sub(d, a.c0, s); fp_mul(d, d, two_inv); if (!fp_sqrt(x0, d)) return false; }
+        Fp den; fp_add(den, x0, x0); fp_inv(den, den);
+        x.c0 = x0; fp_mul(x.c1, a.c1, den);
+    }
+    Fp2 chk; f2_sqr(chk, x);
+    if (!fp_eq(chk.c0, a.c0) || !fp_eq(chk.c1, a.c1)) return false;
+    r = x;
+    return true;
+}
+
+// 0 ok, 1 malformed encoding, 2 not on the curve; *inf set for the point at infinity
+static int g2_decompress(G2Aff& q, bool* inf, const uint8_t* b) {
+    *inf = false;
+    if (!(b[0] & 0x80)) return 1;                               // the setup file holds compressed points only
+    if (b[0] & 0x40) {
+        if (b[0] & 0x3f) return 1;
+        for (int i = 1; i < 96; i++) if (b[i]) return 1;
+        *inf = true;
+        return 0;
+    }
+    if (!fp_from_be48(q.x.c1, b, true) || !fp_from_be48(q.x.c0, b + 48, false)) return 1;
+    Fp2 rhs, bb;
+    f2_sqr(rhs, q.x); f2_mul(rhs, rhs, q.x);
+    uint64_t four[6] = {4, 0, 0, 0, 0, 0};
+    bb.c0 = fp_from_plain(four); bb.c1 = bb.c0;
+    f2_add(rhs, rhs, bb);
+    if (!f2_sqrt(q.y, rhs)) return 2;
+    const bool larger = fp_is_zero(q.y.c1) ? fp_is_larger_half(q.y.c0) : fp_is_larger_half(q.y.c1);
+    if (larger != ((b[0] & 0x20) != 0)) f2_neg(q.y, q.y);
+    return 0;
+}
+
+// [r]Q == O, by a plain double-and-add in Jacobian coordinates over Fp2 (a = 0)
+struct G2Jac { Fp2 x, y, z; };
+static void g2_dbl(G2Jac& r, const G2Jac& p) {
+    Fp2 a, b, c, d, e, f, t;
+    f2_sqr(a, p.x); f2_sqr(b, p.y); f2_sqr(c, b);
+    f2_add(d, p.x, b); f2_sqr(d, d); f2_sub(d, d, a); f2_sub(d, d, c); f2_add(d, d, d);
+    f2_add(e, a, a); f2_add(e, e, a);
+    f2_sqr(f, e);
+    G2Jac o;
+    f2_mul(o.z, p.y, p.z); f2_add(o.z, o.z, o.z);
+    f2_sub(o.x, f, d); f2_sub(o.x, o.x, d);
+    f2_sub(t, d, o.x); f2_mul(o.y, e, t);
+    f2_add(c, c, c); f2_add(c, c, c); f2_add(c, c, c);
+    f2_sub(o.y, o.y, c);
+    r = o;
+}
+static void g2_add_affine(G2Jac& r, const G2Jac& p, const G2Aff& q) {
+    if (f2_is_zero(p.z)) { r.x = q.x; r.y = q.y; r.z = f2_zero(); r.z.c0 = fp_one(); return; }
+    Fp2 z2, u2, s2, h, rr, h2, h3, v, t;
+    f2_sqr(z2, p.z); f2_mul(u2, q.x, z2); f2_mul(s2, q.y, z2); f2_mul(s2, s2, p.z);
+    f2_sub(h, u2, p.x); f2_sub(rr, s2, p.y);
+    if (f2_is_zero(h)) {
+        if (f2_is_zero(rr)) { g2_dbl(r, p); return; }
+        r.x = f2_zero(); r.y = f2_zero(); r.y.c0 = fp_one(); r.z = f2_zero();   // P + (-P)
+        return;
+    }
+    f2_sqr(h2, h); f2_mul(h3, h2, h); f2_mul(v, p.x, h2);
+    G2Jac o;
+    f2_sqr(o.x, rr); f2_sub(o.x, o.x, h3); f2_sub(o.x, o.x, v); f2_sub(o.x, o.x, v);
+    f2_sub(t, v, o.x); f2_mul(o.y, rr, t); f2_mul(t, p.y, h3); f2_sub(o.y, o.y, t);
+    f2_mul(o.z, p.z, h);
+    r = o;
+}
+static bool g2_in_subgroup(const G2Aff& q) {
+    static const uint64_t R[4] = {0xffffffff00000001ULL, 0x53bda402fffe5bfeULL, 0x3339d80809a1d805ULL, 0x73eda753299d7d48ULL};
+    G2Jac acc; acc.x = f2_zero(); acc.y = f2_zero(); acc.y.c0 = fp_one(); acc.z = f2_zero();
+    for (int i = 254; i >= 0; i--) {
+        if (!f2_is_zero(acc.z)) g2_dbl(acc, acc);
+        if ((R[i / 64] >> (i % 64)) & 1) g2_add_affine(acc, acc, q);
+    }
+    return f2_is_zero(acc.z);
+}
+
+G2Keys* g2_keys_from_compressed(const uint8_t* g2, int count, bool subgroup_check, std::string* err) {
+    std::call_once(g_once, init_state);
+    if (!g_state.ok) { *err = "host pairing self-check failed"; return nullptr; }
+    if (count != 65) { *err = "trusted setup: g2_monomial must hold 65 points, got " + std::to_string(count); return nullptr; }
+    G2Aff used[3];
+    for (int i = 0; i < count; i++) {
+        G2Aff q; bool inf = false;
+        const int rc = g2_decompress(q, &inf, g2 + (size_t)96 * i);
+        if (rc) { *err = "trusted setup: g2_monomial[" + std::to_string(i) + (rc == 1 ? "] is not a valid compressed G2 encoding" : "] is not on the curve"); return nullptr; }
+        if (!inf && subgroup_check && !g2_in_subgroup(q)) { *err = "trusted setup: g2_monomial[" + std::to_string(i) + "] is outside the prime-order subgroup"; return nullptr; }
+        const int slot = i == 0 ? 0 : i == 1 ? 1 : i == 64 ? 2 : -1;
+        if (slot >= 0) {
+            if (inf) { *err = "trusted setup: g2_monomial[" + std::to_string(i) + "] is the point at infinity"; return nullptr; }
+            used[slot] = q;
+        }
+    }
+    G2Keys* k = new G2Keys();
+    for (int neg = 0; neg < 2; neg++)
+        for (int sidx = 0; sidx < 3; sidx++) {
+            G2Aff q = used[sidx];
+            if (neg) f2_neg(q.y, q.y);
+            prepare(k->lines[sidx + 3 * neg], q);
+        }
+    return k;
+}
+void g2_keys_free(G2Keys* k) { delete k; }
+
+// test hook: decompress one G2 point; out = x.c0, x.c1, y.c0, y.c1 as plain little-endian 64-bit limbs.  0 ok, 1 malformed,
+// 2 off the curve, 3 outside the subgroup, 4 infinity
+int g2_decompress_plain(const uint8_t* in96, uint64_t* out24) {
+    std::call_once(g_once, init_state);
+    G2Aff q; bool inf = false;
+    const int rc = g2_decompress(q, &inf, in96);
+    if (rc) return rc;
+    if (inf) return 4;
+    fp_to_plain(out24, q.x.c0); fp_to_plain(out24 + 6, q.x.c1); fp_to_plain(out24 + 12, q.y.c0); fp_to_plain(out24 + 18, q.y.c1);
+    return g2_in_subgroup(q) ? 0 : 3;
 }
 
 }  // namespace host

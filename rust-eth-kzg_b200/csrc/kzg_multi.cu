@@ -38,7 +38,7 @@ static Status parse_devices(std::vector<int>* out) {
     return Status::Ok();
 }
 
-Status DeviceSet::create(bool use_precomp, std::unique_ptr<DeviceSet>* out) {
+Status DeviceSet::create(bool use_precomp, std::unique_ptr<DeviceSet>* out, const SetupBytes* custom) {
     std::vector<int> devs;
     Status s = parse_devices(&devs);
     if (!s.ok) return s;
@@ -48,8 +48,8 @@ Status DeviceSet::create(bool use_precomp, std::unique_ptr<DeviceSet>* out) {
     std::vector<Status> st(devs.size());
     std::vector<std::thread> th;
     for (size_t i = 1; i < devs.size(); i++)
-        th.emplace_back([&, i] { st[i] = Context::create(use_precomp, &set->ctx_[i], devs[i]); });
-    st[0] = Context::create(use_precomp, &set->ctx_[0], devs[0]);
+        th.emplace_back([&, i] { st[i] = Context::create(use_precomp, &set->ctx_[i], devs[i], custom); });
+    st[0] = Context::create(use_precomp, &set->ctx_[0], devs[0], custom);
     for (auto& t : th) t.join();
     for (size_t i = 0; i < devs.size(); i++)
         if (!st[i].ok) return Status::Error("device " + std::to_string(devs[i]) + ": " + st[i].msg);

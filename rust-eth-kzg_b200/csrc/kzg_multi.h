@@ -17,7 +17,7 @@ namespace ekzg {
 
 class DeviceSet {
 public:
-    static Status create(bool use_precomp, std::unique_ptr<DeviceSet>* out);
+    static Status create(bool use_precomp, std::unique_ptr<DeviceSet>* out, const SetupBytes* custom = nullptr);
 
     size_t size() const { return ctx_.size(); }
     const Context& primary() const { return *ctx_[0]; }

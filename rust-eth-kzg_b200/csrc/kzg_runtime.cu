@@ -166,9 +166,9 @@ Status Context::bind_device() const {
     return Status::Ok();
 }
 
-Status Context::create(bool use_precomp, std::unique_ptr<Context>* out, int device) {
+Status Context::create(bool use_precomp, std::unique_ptr<Context>* out, int device, const SetupBytes* custom) {
     std::unique_ptr<Context> c(new Context());
-    Status s = c->init(use_precomp, device);
+    Status s = c->init(use_precomp, device, custom);
     if (!s.ok) return s;
     *out = std::move(c);
     return Status::Ok();
@@ -179,6 +179,7 @@ Context::~Context() {
     for (Workspace* w : pool_) { w->release(); delete w; }
     for (auto& q : co_) for (CoalesceStaging* st : q.free_staging) { st->release(); delete st; }
     for (void* p : allocs_) cudaFree(p);
+    if (g2keys_) host::g2_keys_free(g2keys_);
 }
 
 template <class T>
@@ -198,7 +199,7 @@ static size_t hbm_reserve_bytes() {
     return (size_t)((gib < 1.0 ? 1.0 : gib) * 1073741824.0);
 }
 
-Status Context::init(bool use_precomp, int device) {
+Status Context::init(bool use_precomp, int device, const SetupBytes* custom) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return Status::Error("no CUDA device: this backend has no CPU fallback");
@@ -277,35 +278,56 @@ Status Context::init(bool use_precomp, int device) {
     coset_shift_fwd_ = sh_fwd;
     coset_shift_inv_ = sh_inv;
 
-    // trusted setup
-    const unsigned char* ts = ekzg_trusted_setup_start;
-    size_t ts_len = (size_t)(ekzg_trusted_setup_end - ekzg_trusted_setup_start);
-    if (ts_len < 16 || memcmp(ts, "EKZGTS01", 8) != 0) return Status::Error("embedded trusted setup: bad magic");
-    uint32_t n_g1, n_g2;
-    memcpy(&n_g1, ts + 8, 4);
-    memcpy(&n_g2, ts + 12, 4);
-    if (n_g1 != 4096 || n_g2 != 65 || ts_len != 16 + (size_t)48 * 2 * n_g1 + (size_t)96 * n_g2)
-        return Status::Error("embedded trusted setup: unexpected size");
+    // trusted setup: the embedded ceremony output, or the caller's (TrustedSetup::from_json[_unchecked])
+    const unsigned char* g1_bytes = nullptr;
+    uint32_t n_g1 = 4096, n_pts = 0;
+    bool check_subgroup = true;
+    const char* what = "embedded trusted setup";
+    if (custom) {
+        what = "trusted setup";
+        if (custom->g1_monomial.size() != (size_t)48 * 4096)
+            return Status::Error("trusted setup: g1_monomial must hold 4096 points, got " + std::to_string(custom->g1_monomial.size() / 48));
+        for (uint32_t i = 0; i < 4096; i++)   // the table fill divides by differences of these points: the identity has no place in a setup
+            if (custom->g1_monomial[(size_t)48 * i] & 0x40) return Status::Error("trusted setup: g1_monomial[" + std::to_string(i) + "] is the point at infinity");
+        std::string err;
+        g2keys_ = host::g2_keys_from_compressed(custom->g2_monomial.data(), (int)(custom->g2_monomial.size() / 96), custom->subgroup_check, &err);
+        if (!g2keys_) return Status::Error(err);
+        g1_bytes = custom->g1_monomial.data();
+        n_pts = 4096;                       // the Lagrange-basis points of the file are not used (the reference skips them as well)
+        check_subgroup = custom->subgroup_check;
+    } else {
+        const unsigned char* ts = ekzg_trusted_setup_start;
+        size_t ts_len = (size_t)(ekzg_trusted_setup_end - ekzg_trusted_setup_start);
+        if (ts_len < 16 || memcmp(ts, "EKZGTS01", 8) != 0) return Status::Error("embedded trusted setup: bad magic");
+        uint32_t n_g2;
+        memcpy(&n_g1, ts + 8, 4);
+        memcpy(&n_g2, ts + 12, 4);
+        if (n_g1 != 4096 || n_g2 != 65 || ts_len != 16 + (size_t)48 * 2 * n_g1 + (size_t)96 * n_g2)
+            return Status::Error("embedded trusted setup: unexpected size");
+        g1_bytes = ts + 16;
+        n_pts = 2 * n_g1;
+    }
     uint8_t* d_bytes = nullptr;
     uint32_t* d_st = nullptr;
-    EKZG_CUDA(cudaMalloc(&d_bytes, (size_t)48 * 2 * n_g1));
-    EKZG_CUDA(cudaMalloc(&d_st, sizeof(uint32_t) * 2 * n_g1));
-    EKZG_CUDA(cudaMemset(d_st, 0, sizeof(uint32_t) * 2 * n_g1));
-    EKZG_CUDA(cudaMemcpy(d_bytes, ts + 16, (size_t)48 * 2 * n_g1, cudaMemcpyHostToDevice));
+    EKZG_CUDA(cudaMalloc(&d_bytes, (size_t)48 * n_pts));
+    EKZG_CUDA(cudaMalloc(&d_st, sizeof(uint32_t) * n_pts));
+    EKZG_CUDA(cudaMemset(d_st, 0, sizeof(uint32_t) * n_pts));
+    EKZG_CUDA(cudaMemcpy(d_bytes, g1_bytes, (size_t)48 * n_pts, cudaMemcpyHostToDevice));
     G1Affine* srs;
-    EKZG_TRY(dev_alloc(allocs_, &srs, 2 * (size_t)n_g1));
-    // decompress + on-curve + prime-order-subgroup check of all 8192 G1 points on the device: the same validation
+    EKZG_TRY(dev_alloc(allocs_, &srs, (size_t)n_pts));
+    // decompress + on-curve + prime-order-subgroup check of every G1 point on the device: the same validation
     // blstrs' from_compressed gives the reference when it parses the ceremony JSON (crates/trusted_setup/src/lib.rs:112-115,
-    // crates/serialization/src/lib.rs:69-81), so a corrupted or substituted setup blob cannot yield a context
-    EKZG_CUDA(launch_g1_validate(d_bytes, srs, d_st, 2 * n_g1, true, st));
-    std::vector<uint32_t> hst(2 * n_g1);
-    EKZG_CUDA(cudaMemcpy(hst.data(), d_st, sizeof(uint32_t) * 2 * n_g1, cudaMemcpyDeviceToHost));
+    // crates/serialization/src/lib.rs:69-81), so a corrupted or substituted setup cannot yield a context
+    // (from_json_unchecked: decompression and the curve equation only)
+    EKZG_CUDA(launch_g1_validate(d_bytes, srs, d_st, n_pts, check_subgroup, st));
+    std::vector<uint32_t> hst(n_pts);
+    EKZG_CUDA(cudaMemcpy(hst.data(), d_st, sizeof(uint32_t) * n_pts, cudaMemcpyDeviceToHost));
     cudaFree(d_bytes);
     cudaFree(d_st);
-    for (uint32_t v : hst)
-        if (v) return Status::Error("embedded trusted setup: a G1 point is malformed, off the curve or outside the prime-order subgroup");
+    for (uint32_t i = 0; i < n_pts; i++)
+        if (hst[i]) return Status::Error(std::string(what) + ": G1 point " + std::to_string(i) + " is malformed, off the curve or outside the prime-order subgroup");
     T_.srs_g1 = srs;
-    T_.srs_g1_lagrange = srs + n_g1;
+    T_.srs_g1_lagrange = custom ? nullptr : srs + n_g1;
 
     // FK20 tables
     size_t nbases = (size_t)FK20_MSMS * FK20_POINTS * T_.fk20.nw;

@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include "kzg_kernels.h"
+#include "host_pairing.h"
 
 namespace ekzg {
 
@@ -26,6 +27,17 @@ struct Status {
         cudaError_t e_ = (expr);                                                                                \
         if (e_ != cudaSuccess) return ::ekzg::Status::Error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #expr); \
     } while (0)
+
+// A caller-supplied trusted setup with its points still in compressed form: what TrustedSetup::from_json /
+// from_json_unchecked (crates/trusted_setup/src/lib.rs:112-127) hand to DASContext::new (crates/eip7594/src/lib.rs).
+struct SetupBytes {
+    std::vector<uint8_t> g1_monomial;   // 4096 x 48 bytes
+    std::vector<uint8_t> g2_monomial;   // 65 x 96 bytes
+    bool subgroup_check = true;         // from_json: true; from_json_unchecked: false (curve equation only)
+};
+// The consensus-specs JSON layout ({"g1_monomial": ["0x..", ..], "g1_lagrange": [..], "g2_monomial": [..]}); keys other than
+// g1_monomial and g2_monomial are skipped, as serde does for the reference's TrustedSetupJSON (trusted_setup_json.cpp).
+Status parse_trusted_setup_json(const char* json, size_t len, SetupBytes* out);
 
 // Device + pinned buffers for one in-flight chunk of up to `capacity` blobs.
 struct Workspace {
@@ -78,12 +90,14 @@ struct Workspace {
 class Context {
 public:
     // device < 0: the calling thread's current device (or EKZG_DEVICE)
-    static Status create(bool use_precomp, std::unique_ptr<Context>* out, int device = -1);
+    // custom == nullptr: the embedded mainnet ceremony output
+    static Status create(bool use_precomp, std::unique_ptr<Context>* out, int device = -1, const SetupBytes* custom = nullptr);
     ~Context();
 
     int device() const { return device_; }
     const DevTables& tables() const { return T_; }
     uint64_t table_bytes() const { return table_bytes_; }
+    const host::G2Keys* g2_keys() const { return g2keys_; }
 
     // Everything on device, asynchronous on `stream`; scratch comes from `ws` (capacity >= n).
     Status fk20_device(Workspace& ws, int n, const uint8_t* d_blobs, uint8_t* d_cells, uint8_t* d_proofs, uint32_t* d_status,
@@ -203,7 +217,8 @@ private:
                         uint8_t* item_status, bool strided) const;
     Status recover_cells_and_kzg_proofs_strided(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
                                                 uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const;
-    Status init(bool use_precomp, int device);
+    Status init(bool use_precomp, int device, const SetupBytes* custom);
+    host::G2Keys* g2keys_ = nullptr;   // G2 side of a caller-supplied setup (nullptr: the embedded ceremony's constants)
     int device_ = 0;
     DevTables T_{};
     std::vector<void*> allocs_;

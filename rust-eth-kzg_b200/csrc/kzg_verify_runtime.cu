@@ -36,7 +36,7 @@ struct Scratch {
 
 void be64(uint8_t* o, uint64_t v) { for (int i = 0; i < 8; i++) o[i] = (uint8_t)(v >> (56 - 8 * i)); }
 
-bool run_pairing(const uint32_t* w /*2 x PAIRING_INPUT_WORDS*/, host::G2Sel q0, host::G2Sel q1) {
+bool run_pairing(const uint32_t* w /*2 x PAIRING_INPUT_WORDS*/, host::G2Sel q0, host::G2Sel q1, const host::G2Keys* keys) {
     host::PairingInputJac in[2];
     for (int i = 0; i < 2; i++) {
         const uint32_t* o = w + PAIRING_INPUT_WORDS * i;
@@ -49,7 +49,7 @@ bool run_pairing(const uint32_t* w /*2 x PAIRING_INPUT_WORDS*/, host::G2Sel q0, 
     }
     in[0].g2 = q0;
     in[1].g2 = q1;
-    return host::pairing_check_jac(in, 2);
+    return host::pairing_check_jac(in, 2, keys);
 }
 
 }  // namespace
@@ -240,7 +240,7 @@ Status Context::verify_cell_kzg_proof_batch(uint64_t n_commitments, const uint8_
     for (uint32_t v : stc) if (v) return Status::Error("Serialization(G1PointInvalid): commitment");
     for (uint32_t v : stp) if (v) return Status::Error("Serialization(G1PointInvalid): proof");
     if (cell_status) return Status::Error("Serialization(ScalarNotCanonical): cell");
-    *verified = run_pairing(pin, host::G2Sel::Tau64, host::G2Sel::NegGen);
+    *verified = run_pairing(pin, host::G2Sel::Tau64, host::G2Sel::NegGen, g2keys_);
     tr.mark("pairing");
     return Status::Ok();
 }
@@ -372,7 +372,7 @@ Status Context::verify_kzg_proofs(int mode, uint64_t n, const uint8_t* const* bl
     for (uint32_t v : stp) if (v) return Status::Error("Serialization(G1PointInvalid): proof");
     for (uint32_t v : stz) if (v) return Status::Error("Serialization(ScalarNotCanonical): z");
     for (uint32_t v : sty) if (v) return Status::Error("Serialization(ScalarNotCanonical): y");
-    *verified = run_pairing(pin, host::G2Sel::Tau, host::G2Sel::NegGen);
+    *verified = run_pairing(pin, host::G2Sel::Tau, host::G2Sel::NegGen, g2keys_);
     return Status::Ok();
 }
 

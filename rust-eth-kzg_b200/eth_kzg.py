@@ -66,7 +66,8 @@ def load_library():
                  "eth_kzg_compute_blob_kzg_proof", "eth_kzg_verify_kzg_proof", "eth_kzg_verify_blob_kzg_proof",
                  "eth_kzg_verify_blob_kzg_proof_batch", "eth_kzg_b200_compute_cells_and_kzg_proofs_batch",
                  "eth_kzg_b200_compute_cells_and_kzg_proofs_device", "eth_kzg_b200_debug_fk20_stages", "eth_kzg_b200_debug_g1_ntt_prefix",
-                 "eth_kzg_b200_recover_cells_and_kzg_proofs_batch", "eth_kzg_b200_blob_to_kzg_commitment_batch", "eth_kzg_b200_compute_blob_kzg_proof_batch"):
+                 "eth_kzg_b200_recover_cells_and_kzg_proofs_batch", "eth_kzg_b200_blob_to_kzg_commitment_batch", "eth_kzg_b200_compute_blob_kzg_proof_batch",
+                 "eth_kzg_b200_das_context_new_from_json", "eth_kzg_b200_debug_parse_trusted_setup_json", "eth_kzg_b200_debug_g2_keys"):
         getattr(lib, name).restype = _CResult
     _lib = lib
     return lib
@@ -103,11 +104,25 @@ class DASContext:
     """Mirror of rust_eth_kzg::DASContext (crates/eip7594/src/lib.rs:41).  `use_precomp` is the only
     runtime knob of the C ABI (bindings/c/src/lib.rs:79)."""
 
-    def __init__(self, use_precomp=False):
+    def __init__(self, use_precomp=False, _handle=None):
         self._lib = load_library()
+        if _handle is not None:
+            self._ctx = _handle
+            return
         self._ctx = self._lib.eth_kzg_das_context_new(bool(use_precomp))
         if not self._ctx:
             raise KzgError("eth_kzg_das_context_new failed (no usable CUDA device? there is no CPU fallback)")
+
+    @classmethod
+    def from_json(cls, json_text, use_precomp=False, subgroup_check=True):
+        """DASContext::new(&TrustedSetup::from_json(json), use_precomp) -- or from_json_unchecked with subgroup_check=False
+        (crates/trusted_setup/src/lib.rs:112-127).  Raises KzgError where the reference panics."""
+        lib = load_library()
+        data = json_text.encode() if isinstance(json_text, str) else bytes(json_text)
+        out = C.c_void_p()
+        _check(lib, lib.eth_kzg_b200_das_context_new_from_json(data, C.c_uint64(len(data)), C.c_bool(subgroup_check), C.c_bool(use_precomp),
+                                                               C.byref(out)))
+        return cls(_handle=out.value)
 
     def close(self):
         if getattr(self, "_ctx", None):
