@@ -90,9 +90,10 @@ EKZG_NTT_INL void r4_sub(G1Jac& a, const G1Jac& b) {   // a -= b
     jac_add(a, n);
 }
 
-EKZG_NTT_UNIT void r4_mul_unit(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int b, int sp, int u, TwiddleOps tw) {
-    // which point (or combination of points) times which root of unity
-    int i0, i1 = -1, i2 = -1, i3 = -1, e;       // p = pts[i0] - pts[i1] + pts[i2] - pts[i3] (absent terms: -1), then p *= omega^e
+// which point (or combination of points) a multiplication unit multiplies by which root of unity:
+// p = pts[i0] - pts[i1] + pts[i2] - pts[i3] (absent terms: -1), then p *= omega^e
+EKZG_NTT_INL void r4_mul_operands(int sp, int u, int& i0, int& i1, int& i2, int& i3, int& e) {
+    i1 = i2 = i3 = -1;
     if (sp == 3) {           // middle: omega^-t x1 (even u) and omega^t x0 (odd u)
         const int t = u >> 1;
         if (u & 1) { i0 = t; e = t; } else { i0 = t + 64; e = (128 - t) & 127; }
@@ -115,6 +116,8 @@ EKZG_NTT_UNIT void r4_mul_unit(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp,
             e &= 127;
         }
     }
+}
+EKZG_NTT_INL G1Jac r4_mul_operand_point(const G1Jac* __restrict__ pts, int B, int b, int i0, int i1, int i2, int i3) {
     G1Jac p = ld_pt(&pts[(size_t)i0 * B + b]);
     if (i1 >= 0) r4_sub(p, ld_pt(&pts[(size_t)i1 * B + b]));
     if (i2 >= 0) {
@@ -122,9 +125,48 @@ EKZG_NTT_UNIT void r4_mul_unit(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp,
         r4_sub(d, ld_pt(&pts[(size_t)i3 * B + b]));
         jac_add(p, d);
     }
+    return p;
+}
+
+EKZG_NTT_UNIT void r4_mul_unit(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int b, int sp, int u, TwiddleOps tw) {
+    int i0, i1, i2, i3, e;
+    r4_mul_operands(sp, u, i0, i1, i2, i3, e);
+    G1Jac p = r4_mul_operand_point(pts, B, b, i0, i1, i2, i3);
     r4_twiddle_mul(p, e, tw);
     st_pt(&tmp[(size_t)u * B + b], p);
 }
+
+#ifdef __CUDACC__
+}  // namespace ekzg
+#include "g1_coop.cuh"
+namespace ekzg {
+// The same unit for EIGHT blobs per warp, four lanes per blob (batches that leave most of the machine idle): the four lanes of a
+// group form the operand point redundantly in one-thread arithmetic (a handful of additions), then run the fixed-scalar ladder --
+// 98 % of the unit -- cooperatively, each on its three limbs of every coordinate (g1_coop.cuh: half the latency per dependent
+// product).  Every lane of the warp must come here (the ladder shuffles and votes across the whole warp); groups without work
+// (b >= B, identity operand) run the ladder on whatever they hold and drop the result.  Bit-identical to r4_mul_unit.
+EKZG_NTT_UNIT void r4_mul_unit_coop(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int b, int sp, int u, TwiddleOps tw) {
+    int i0, i1, i2, i3, e;
+    r4_mul_operands(sp, u, i0, i1, i2, i3, e);
+    const bool valid = b < B;
+    G1Jac p;
+    if (valid) p = r4_mul_operand_point(pts, B, b, i0, i1, i2, i3);
+    else jac_set_inf(p);
+    if (e == 64) {
+        jac_neg(p, p);
+    } else if (e != 0) {     // e is the same for the whole warp
+        const bool active = valid && !jac_is_inf(p);
+        if (__any_sync(0xffffffffu, active)) {
+            const coop::Ctx c = coop::make_ctx();
+            coop::CJac r;
+            coop::cjac_mul_ops(c, r, coop::from_jac(c, p), tw[e]);
+            const G1Jac full = coop::to_jac(c, r);
+            if (active) p = full;
+        }
+    }
+    if (valid && (threadIdx.x & 3) == 0) st_pt(&tmp[(size_t)u * B + b], p);
+}
+#endif
 
 EKZG_NTT_UNIT void r4_combine_unit(G1Jac* __restrict__ pts, const G1Jac* __restrict__ tmp, int B, int b, int sp, int c) {
     if (sp == 3) {           // pts[c] = x0 + omega^-c x1, pts[c + 64] = x1 + omega^c x0

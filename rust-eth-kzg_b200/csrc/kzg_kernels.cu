@@ -818,6 +818,10 @@ k_fk20_g1_ntts(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned
 // ------------------------------------------------------------------------------------------------
 // queue[0] = ticket counter, queue[1 + (g*7 + sp)*2 + kind] = finished multiplication (0) / combination (1) units of blob group g
 // in super-phase sp; zeroed by the launcher.  Tickets: super-phase major, then all multiplication units, then all combinations.
+// GW = blobs per blob group (= per warp): 32, one lane per blob; or 8 (COOP), where a multiplication unit spreads every field element
+// of a blob over four lanes (r4_mul_unit_coop) and a combination unit simply uses 8 of its 32 lanes -- for batches so small that the
+// machine is mostly idle and only the latency of the dependent products counts (launch_g1_ntt_phases picks).
+template <int GW>
 __global__ void __launch_bounds__(NTT_THREADS, 2)
 k_fk20_g1_ntts_r4(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int G, int sp_end, unsigned* __restrict__ queue) {
     const int lane = threadIdx.x & 31;
@@ -845,10 +849,17 @@ k_fk20_g1_ntts_r4(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int G
             }
             __syncwarp();
         }
-        const int b = g * 32 + lane;
-        if (b < B) {
-            if (comb) r4_combine_unit(pts, tmp, B, b, sp, u);
-            else r4_mul_unit(pts, tmp, B, b, sp, u, c_twiddle_ops);
+        if (GW == 32) {
+            const int b = g * 32 + lane;
+            if (b < B) {
+                if (comb) r4_combine_unit(pts, tmp, B, b, sp, u);
+                else r4_mul_unit(pts, tmp, B, b, sp, u, c_twiddle_ops);
+            }
+        } else if (comb) {
+            const int b = g * GW + lane;
+            if (lane < GW && b < B) r4_combine_unit(pts, tmp, B, b, sp, u);
+        } else {
+            r4_mul_unit_coop(pts, tmp, B, g * GW + (lane >> 2), sp, u, c_twiddle_ops);   // all 32 lanes: 8 blobs x 4 lanes
         }
         __threadfence();
         __syncwarp();
@@ -1519,6 +1530,12 @@ static int k5_r4_max() {
     const int v = e ? atoi(e) : 256;   // measured (tools/k5_sweep.py, profiles/r2_i_k5_sweep.jsonl): 10.2 against 17.2 ms up to 64 blobs, 15.3 against 17.2 at 256
     return v < 0 ? 0 : (v > R4_MAX_BLOBS ? R4_MAX_BLOBS : v);
 }
+static int k5_coop_max() {
+    // batches up to this many blobs run their multiplication units cooperatively, four lanes per field element (EKZG_K5_COOP_MAX; 0 = never)
+    const char* e = getenv("EKZG_K5_COOP_MAX");
+    const int v = e ? atoi(e) : 48;   // measured (tools/k5_sweep.py, profiles/r2_coop_k5_sweep.jsonl): K5 7.1 against 10.2 ms up to 16 blobs, 9.0 against 10.2 at 48, equal at 64
+    return v < 0 ? 0 : (v > R4_MAX_BLOBS ? R4_MAX_BLOBS : v);
+}
 size_t g1_ntt_scratch_bytes() {
     if (ntt_query_sms() != cudaSuccess) return 0;
     return std::max((size_t)g_ntt_sms * K5_VM_CTAS_PER_SM * (fpvm::NT / 32) * K5_SCRATCH_WARP_BYTES,
@@ -1536,8 +1553,15 @@ cudaError_t launch_g1_ntt_phases(G1Jac* pts, int B, int ph0, int ph1, uint32_t* 
     unsigned* q = reinterpret_cast<unsigned*>(queue);
     // latency mode (the memset above covers its 1 + 14 G counters); a phase range [0, 2k) is its first k super-phases (test hook)
     if (ph0 == 0 && (ph1 & 1) == 0 && ph1 >= 2 && ph1 <= NTT_PHASES && scratch && B <= k5_r4_max() && !(t_k5_prefer_throughput && B > 64)) {
+        if (B <= k5_coop_max() && !t_k5_prefer_throughput) {   // cooperative multiplication units (40 % less throughput: not beside other batches): 8 blobs per warp (the queue holds 1 + 14 ceil(B/8) counters)
+            const int G8 = (B + 7) / 8;
+            const int grid = (int)std::min<long>((long)g_ntt_sms * 2, ((long)G8 * 160 + NTT_THREADS / 32 - 1) / (NTT_THREADS / 32));
+            k_fk20_g1_ntts_r4<8><<<grid, NTT_THREADS, 0, st>>>(pts, reinterpret_cast<G1Jac*>(scratch), B, G8, ph1 / 2, q);
+            EKZG_LAUNCH_CHECK();
+            return cudaSuccess;
+        }
         const int grid = (int)std::min<long>((long)g_ntt_sms * 2, ((long)G * 160 + NTT_THREADS / 32 - 1) / (NTT_THREADS / 32));
-        k_fk20_g1_ntts_r4<<<grid, NTT_THREADS, 0, st>>>(pts, reinterpret_cast<G1Jac*>(scratch), B, G, ph1 / 2, q);
+        k_fk20_g1_ntts_r4<32><<<grid, NTT_THREADS, 0, st>>>(pts, reinterpret_cast<G1Jac*>(scratch), B, G, ph1 / 2, q);
         EKZG_LAUNCH_CHECK();
         return cudaSuccess;
     }

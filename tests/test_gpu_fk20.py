@@ -155,13 +155,17 @@ def test_precomputed_window_variants(das_ctx, pkg, fk20_w, srs_w, monkeypatch, p
         ctx.close()
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 33, 128, 160])
-def test_k5_radix4_equals_radix2(vec_ctx, pkg, n, monkeypatch):
+@pytest.mark.parametrize("coop", ["0", "256"], ids=["lane_per_blob", "four_lanes_per_element"])
+@pytest.mark.parametrize("n", [1, 2, 7, 9, 31, 33, 128, 160])
+def test_k5_radix4_equals_radix2(vec_ctx, pkg, n, coop, monkeypatch):
     """the latency-mode G1-NTT kernel (radix-4 super-phases, small batches) against the radix-2 kernel the vectors pin, on the
-    same batch: ragged group sizes, identity points everywhere (zero blob), and the oracle on the first two blobs"""
+    same batch: ragged group sizes, identity points everywhere (zero blob), and the oracle on the first two blobs -- with its
+    multiplication units one lane per blob and in the cooperative form (four lanes per field element, eight blobs per warp:
+    csrc/g1_coop.cuh; the default up to 64 blobs)"""
+    monkeypatch.setenv("EKZG_K5_COOP_MAX", coop)
     syn = _synth(pkg)
     blobs = [syn.blob(6100 + i) for i in range(n)]
-    if n >= 31:
+    if n >= 7:
         blobs[3:7] = list(syn.edge_blobs())[:4]
     flat = b"".join(blobs)
     monkeypatch.setenv("EKZG_DIRECT_MAX", "0")      # (one or two blobs would otherwise not reach the G1 transforms at all)

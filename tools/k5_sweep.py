@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
-"""K5 (the two G1 NTTs) stage time against batch size, radix-2 kernel vs the radix-4 latency-mode kernel (EKZG_K5_R4_MAX):
-where the switch-over belongs.  One JSON line per (batch size, form)."""
+"""K5 (the two G1 NTTs) stage time against batch size: radix-2 kernel, the radix-4 latency-mode kernel (EKZG_K5_R4_MAX) and the
+latter with cooperative multiplication units, four lanes per field element (EKZG_K5_COOP_MAX): where the switch-overs belong.  One JSON line per (batch size, form)."""
 import json
 import os
 import sys
@@ -17,16 +17,18 @@ ctx = pkg.DASContext(use_precomp=True)
 names = ["K1", "K2", "K4", "K5", "K6"]
 stream = torch.cuda.current_stream()
 blobs_all = syn.blobs(512)
-for n in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "1,32,64,96,128,160,192,224,256,512".split(","))]:
+for n in [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else "1,8,16,32,48,64,96,128,160,192,224,256,512".split(","))]:
     d_in = torch.frombuffer(bytearray(blobs_all[:n * 131072]), dtype=torch.uint8).cuda()
     d_cells = torch.empty(n * 262144, dtype=torch.uint8, device="cuda")
     d_proofs = torch.empty(n * 6144, dtype=torch.uint8, device="cuda")
     d_status = torch.zeros(n, dtype=torch.int32, device="cuda")
     ref = None
-    for form, r4max in (("radix2", "0"), ("radix4", "256")):
-        if form == "radix4" and n > 256:
+    os.environ["EKZG_DIRECT_MAX"] = "0"     # (one or two blobs would otherwise bypass the G1 transforms)
+    for form, r4max, coopmax in (("radix2", "0", "0"), ("radix4", "256", "0"), ("radix4_coop", "256", "256")):
+        if form != "radix2" and n > 256:
             continue
         os.environ["EKZG_K5_R4_MAX"] = r4max
+        os.environ["EKZG_K5_COOP_MAX"] = coopmax
         step = lambda: ctx.compute_cells_and_kzg_proofs_device(n, d_in.data_ptr(), d_cells.data_ptr(), d_proofs.data_ptr(), d_status.data_ptr(), stream.cuda_stream)
         for _ in range(3):
             step()
