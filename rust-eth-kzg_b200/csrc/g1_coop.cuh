@@ -174,6 +174,52 @@ static __device__ __noinline__ CFp cmul(CFp a, CFp b, CFp p, unsigned gl) {
 __device__ __forceinline__ void cmul(const Ctx& c, CFp& r, const CFp& a, const CFp& b) { r = cmul(a, b, c.p, c.gl); }
 __device__ __forceinline__ void csqr(const Ctx& c, CFp& r, const CFp& a) { r = cmul(a, a, c.p, c.gl); }
 
+// TWO independent products, row by row in lock step: a lone product is a chain of 12 x (shuffle, multiply-adds, shuffle, multiply-adds,
+// shuffle) in which the warp mostly waits; the second product's chain fills those gaps (the sync shuffles keep ptxas from interleaving
+// two separate calls by itself).  The point formulas below issue their multiplications in independent pairs wherever they have them.
+struct CFp2 { CFp a, b; };
+static __device__ __noinline__ CFp2 cmul2(CFp a1, CFp b1, CFp a2, CFp b2, CFp p, unsigned gl) {
+    uint32_t t0 = 0, t1 = 0, t2 = 0, h0 = 0, h1 = 0;
+    uint32_t u0 = 0, u1 = 0, u2 = 0, k0 = 0, k1 = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        const uint32_t bi = __shfl_sync(FULL, b1.v[i % 3], i / 3, 4);
+        const uint32_t ci = __shfl_sync(FULL, b2.v[i % 3], i / 3, 4);
+        mad3(t0, t1, t2, h0, h1, a1, bi);
+        mad3(u0, u1, u2, k0, k1, a2, ci);
+        const uint32_t m = __shfl_sync(FULL, t0, 0, 4) * FpParams::M0;
+        const uint32_t n = __shfl_sync(FULL, u0, 0, 4) * FpParams::M0;
+        mad3(t0, t1, t2, h0, h1, p, m);
+        mad3(u0, u1, u2, k0, k1, p, n);
+        uint32_t y = __shfl_down_sync(FULL, t0, 1, 4);
+        uint32_t w = __shfl_down_sync(FULL, u0, 1, 4);
+        if (gl == 3) { y = 0; w = 0; }
+        t0 = t1; t1 = t2;
+        asm("add.cc.u32 %0, %2, %3;\n\t addc.u32 %1, %4, 0;" : "=r"(t2), "=r"(h0) : "r"(h0), "r"(y), "r"(h1));
+        h1 = 0;
+        u0 = u1; u1 = u2;
+        asm("add.cc.u32 %0, %2, %3;\n\t addc.u32 %1, %4, 0;" : "=r"(u2), "=r"(k0) : "r"(k0), "r"(w), "r"(k1));
+        k1 = 0;
+    }
+    for (int pass = 0; pass < 3; pass++) {
+        uint32_t cin = __shfl_up_sync(FULL, h0, 1, 4), din = __shfl_up_sync(FULL, k0, 1, 4);
+        if (gl == 0) { cin = 0; din = 0; }
+        asm("add.cc.u32 %0, %0, %4;\n\t addc.cc.u32 %1, %1, 0;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.u32 %3, 0, 0;" : "+r"(t0), "+r"(t1), "+r"(t2), "=r"(h0) : "r"(cin));
+        asm("add.cc.u32 %0, %0, %4;\n\t addc.cc.u32 %1, %1, 0;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.u32 %3, 0, 0;" : "+r"(u0), "+r"(u1), "+r"(u2), "=r"(k0) : "r"(din));
+        if (!__any_sync(FULL, (h0 | k0) != 0)) break;
+    }
+    CFp2 r;
+    r.a.v[0] = t0; r.a.v[1] = t1; r.a.v[2] = t2;
+    r.b.v[0] = u0; r.b.v[1] = u1; r.b.v[2] = u2;
+    return r;
+}
+// r1 = a1 b1, r2 = a2 b2 (the results may alias the operands)
+__device__ __forceinline__ void cmul2(const Ctx& c, CFp& r1, const CFp& a1, const CFp& b1, CFp& r2, const CFp& a2, const CFp& b2) {
+    const CFp2 r = cmul2(a1, b1, a2, b2, c.p, c.gl);
+    r1 = r.a;
+    r2 = r.b;
+}
+
 // ---- points (the formulas of g1.cuh / g1_mul.cuh without their exceptional-case branches) ------------------------------------
 __device__ __forceinline__ CJac from_jac(const Ctx& c, const G1Jac& p) {
     CJac r;
@@ -186,16 +232,16 @@ __device__ __forceinline__ G1Jac to_jac(const Ctx& c, const CJac& p) {
     return r;
 }
 
-// dbl-2009-l (jac_dbl_inl)
+// dbl-2009-l (jac_dbl_inl): 7 products in 4 steps
 static __device__ __noinline__ void cjac_dbl(const Ctx& c, CJac& r, const CJac& p) {
     CFp a, b, cc, d, e, f, z;
-    csqr(c, a, p.x);
-    csqr(c, b, p.y);
-    csqr(c, cc, b);
-    cadd(c, d, p.x, b); csqr(c, d, d); csub(c, d, d, a); csub(c, d, d, cc); cdbl(c, d, d);
+    cmul2(c, a, p.x, p.x, b, p.y, p.y);
+    cmul2(c, cc, b, b, z, p.y, p.z);
+    cadd(c, d, p.x, b);
     cdbl(c, e, a); cadd(c, e, e, a);
-    csqr(c, f, e);
-    cmul(c, z, p.y, p.z); cdbl(c, z, z);
+    cmul2(c, d, d, d, f, e, e);
+    csub(c, d, d, a); csub(c, d, d, cc); cdbl(c, d, d);
+    cdbl(c, z, z);
     csub(c, f, f, d); csub(c, f, f, d);
     csub(c, d, d, f);
     cmul(c, d, e, d);
@@ -205,48 +251,43 @@ static __device__ __noinline__ void cjac_dbl(const Ctx& c, CJac& r, const CJac& 
     r.z = z;
 }
 
-// acc += (px, py) affine, acc neither the identity nor +-(px, py)  (madd-2007-bl, jac_madd_inl)
+// acc += (px, py) affine, acc neither the identity nor +-(px, py)  (madd-2007-bl, jac_madd_inl): 11 products in 6 steps
 static __device__ __noinline__ void cjac_madd(const Ctx& c, CJac& acc, const CFp& px, const CFp& py) {
-    CFp z1z1, u2, s2, h, hh, i, j, rr, v;
-    csqr(c, z1z1, acc.z);
-    cmul(c, u2, px, z1z1);
-    cmul(c, s2, py, acc.z); cmul(c, s2, s2, z1z1);
+    CFp z1z1, u2, s2, h, hh, i, j, rr, v, w;
+    cmul2(c, z1z1, acc.z, acc.z, s2, py, acc.z);
+    cmul2(c, u2, px, z1z1, s2, s2, z1z1);
     csub(c, h, u2, acc.x);
     csub(c, rr, s2, acc.y);
     cdbl(c, rr, rr);
-    csqr(c, hh, h);
+    cadd(c, w, acc.z, h);
+    cmul2(c, hh, h, h, w, w, w);
     cdbl(c, i, hh); cdbl(c, i, i);
-    cmul(c, j, h, i);
-    cmul(c, v, acc.x, i);
-    cadd(c, u2, acc.z, h); csqr(c, u2, u2); csub(c, u2, u2, z1z1); csub(c, acc.z, u2, hh);
-    csqr(c, u2, rr); csub(c, u2, u2, j); csub(c, u2, u2, v); csub(c, u2, u2, v);
+    csub(c, w, w, z1z1); csub(c, acc.z, w, hh);
+    cmul2(c, j, h, i, v, acc.x, i);
+    cmul2(c, u2, rr, rr, s2, acc.y, j);
+    csub(c, u2, u2, j); csub(c, u2, u2, v); csub(c, u2, u2, v);
     csub(c, v, v, u2); cmul(c, v, rr, v);
-    cmul(c, s2, acc.y, j); cdbl(c, s2, s2);
+    cdbl(c, s2, s2);
     csub(c, acc.y, v, s2);
     acc.x = u2;
 }
 
-// r = a + (bx, by) affine with zr = Z3 / Z1 (madd-2004-hmv, jac_madd_zr)
+// r = a + (bx, by) affine with zr = Z3 / Z1 (madd-2004-hmv, jac_madd_zr): 11 products in 6 steps; r must not alias a
 static __device__ __noinline__ void cjac_madd_zr(const Ctx& c, CJac& r, const CJac& a, const CFp& bx, const CFp& by, CFp& zr) {
     CFp t1, t2, t3, t4, x3;
     csqr(c, t1, a.z);
-    cmul(c, t2, t1, a.z);
-    cmul(c, t1, t1, bx);
-    cmul(c, t2, t2, by);
-    csub(c, t1, t1, a.x);
-    csub(c, t2, t2, a.y);
+    cmul2(c, t2, t1, a.z, t1, t1, bx);
+    csub(c, t1, t1, a.x);                      // H
     zr = t1;
-    cmul(c, r.z, a.z, t1);
-    csqr(c, t3, t1);
-    cmul(c, t4, t3, t1);
-    cmul(c, t3, t3, a.x);
+    cmul2(c, t2, t2, by, r.z, a.z, t1);
+    csub(c, t2, t2, a.y);                      // R
+    cmul2(c, t3, t1, t1, x3, t2, t2);          // HH, R^2
+    cmul2(c, t4, t3, t1, t3, t3, a.x);         // HHH, V
     cdbl(c, t1, t3);
-    csqr(c, x3, t2);
     csub(c, x3, x3, t1);
     csub(c, x3, x3, t4);
     csub(c, t3, t3, x3);
-    cmul(c, t3, t3, t2);
-    cmul(c, t4, t4, a.y);
+    cmul2(c, t3, t3, t2, t4, t4, a.y);
     csub(c, r.y, t3, t4);
     r.x = x3;
 }
@@ -261,8 +302,7 @@ static __device__ __noinline__ void cjac_mul_ops(const Ctx& c, CJac& out, const 
         CJac cur;
         CFp dz2, dz3;
         csqr(c, dz2, d.z);
-        cmul(c, dz3, dz2, d.z);
-        cmul(c, cur.x, p.x, dz2);
+        cmul2(c, dz3, dz2, d.z, cur.x, p.x, dz2);
         cmul(c, cur.y, p.y, dz3);
         cur.z = p.z;
         tx[0] = cur.x; ty[0] = cur.y;
@@ -277,13 +317,12 @@ static __device__ __noinline__ void cjac_mul_ops(const Ctx& c, CJac& out, const 
         for (int i = 6; i >= 0; i--) {
             CFp z2, z3;
             csqr(c, z2, zs);
-            cmul(c, z3, z2, zs);
-            cmul(c, tx[i], tx[i], z2);
-            cmul(c, ty[i], ty[i], z3);
-            if (i) cmul(c, zs, zs, zr[i]);
+            cmul2(c, z3, z2, zs, tx[i], tx[i], z2);
+            if (i) cmul2(c, ty[i], ty[i], z3, zs, zs, zr[i]);
+            else cmul(c, ty[i], ty[i], z3);
         }
         const CFp beta = const_fp(c, beta_limb);
-        for (int i = 0; i < 8; i++) cmul(c, bx[i], tx[i], beta);
+        for (int i = 0; i < 8; i += 2) cmul2(c, bx[i], tx[i], beta, bx[i + 1], tx[i + 1], beta);
     }
     CJac acc;
     const int n = ops[0];
