@@ -54,6 +54,10 @@ __device__ __forceinline__ CFp const_fp(const Ctx& c, uint32_t (*f)(int)) {
 }
 __device__ __forceinline__ uint32_t one_limb(int i) { return FpParams::one(i); }
 __device__ __forceinline__ uint32_t beta_limb(int i) { return FpParams::beta(i); }
+// 3/2 mod p in Montgomery form (3 * 2^-1 * 2^384 mod p): the doubling below multiplies by it instead of tripling and halving
+__device__ __forceinline__ uint32_t three_halves_limb(int i) {
+    switch (i) { case 0: return 0x0004aaa6u; case 1: return 0xd40e0000u; case 2: return 0x4d680003u; case 3: return 0x52980012u; case 4: return 0x82528a06u; case 5: return 0x5b547b32u; case 6: return 0xaeb8f988u; case 7: return 0x8179debau; case 8: return 0x51dc8c38u; case 9: return 0xe47cd408u; case 10: return 0xdb01638fu; case 11: return 0x13f10530u; default: return 0u; }
+}
 
 // this lane's three limbs of a one-thread element (every lane of the group holds the same `a`)
 __device__ __forceinline__ CFp from_fp(const Ctx& c, const Fp& a) {
@@ -232,44 +236,43 @@ __device__ __forceinline__ G1Jac to_jac(const Ctx& c, const CJac& p) {
     return r;
 }
 
-// dbl-2009-l (jac_dbl_inl): 7 products in 4 steps
-static __device__ __noinline__ void cjac_dbl(const Ctx& c, CJac& r, const CJac& p) {
-    CFp a, b, cc, d, e, f, z;
+// An addition or subtraction costs two ballot rounds here (~180 clocks, a fifth of a product), so the ladder does NOT use the
+// add-heavy formulas of g1.cuh (dbl-2009-l: 14 additions, madd-2007-bl: 15) but forms of the same maps with the small constants moved
+// into products and into the choice of the projective representative.  The points are the same; their Jacobian coordinates differ
+// from the one-thread kernels' by a factor (lambda^2, lambda^3, lambda), which the final normalisation removes.
+//
+// Doubling, scaled by lambda = 1/2:  m = (3/2) X^2,  X3 = m^2 - 2 X Y^2,  Y3 = m (X Y^2 - X3) - Y^4,  Z3 = Y Z
+// (from S = 4 X Y^2, M = 3 X^2, X3 = M^2 - 2 S, Y3 = M (S - X3) - 8 Y^4, Z3 = 2 Y Z): 8 products in 4 paired steps, 4 additions.
+static __device__ __noinline__ void cjac_dbl(const Ctx& c, CJac& r, const CJac& p, const CFp& three_halves) {
+    CFp a, b, m, xb, m2, bb, t, y, z;
     cmul2(c, a, p.x, p.x, b, p.y, p.y);
-    cmul2(c, cc, b, b, z, p.y, p.z);
-    cadd(c, d, p.x, b);
-    cdbl(c, e, a); cadd(c, e, e, a);
-    cmul2(c, d, d, d, f, e, e);
-    csub(c, d, d, a); csub(c, d, d, cc); cdbl(c, d, d);
-    cdbl(c, z, z);
-    csub(c, f, f, d); csub(c, f, f, d);
-    csub(c, d, d, f);
-    cmul(c, d, e, d);
-    cdbl(c, cc, cc); cdbl(c, cc, cc); cdbl(c, cc, cc);
-    csub(c, r.y, d, cc);
-    r.x = f;
+    cmul2(c, m, a, three_halves, xb, p.x, b);
+    cmul2(c, m2, m, m, bb, b, b);
+    csub(c, m2, m2, xb); csub(c, m2, m2, xb);   // X3
+    csub(c, t, xb, m2);
+    cmul2(c, y, m, t, z, p.y, p.z);
+    csub(c, r.y, y, bb);
+    r.x = m2;
     r.z = z;
 }
 
-// acc += (px, py) affine, acc neither the identity nor +-(px, py)  (madd-2007-bl, jac_madd_inl): 11 products in 6 steps
+// acc += (px, py) affine, acc neither the identity nor +-(px, py)  (madd-2004-hmv: H = px Z^2 - X, R = py Z^3 - Y,
+// X3 = R^2 - H^3 - 2 X H^2, Y3 = R (X H^2 - X3) - Y H^3, Z3 = Z H): 11 products in 6 steps, 7 additions
 static __device__ __noinline__ void cjac_madd(const Ctx& c, CJac& acc, const CFp& px, const CFp& py) {
-    CFp z1z1, u2, s2, h, hh, i, j, rr, v, w;
-    cmul2(c, z1z1, acc.z, acc.z, s2, py, acc.z);
-    cmul2(c, u2, px, z1z1, s2, s2, z1z1);
+    CFp zz, t, u2, s2, h, rr, hh, r2, hhh, v, x3, z3;
+    cmul2(c, zz, acc.z, acc.z, t, py, acc.z);
+    cmul2(c, u2, px, zz, s2, t, zz);
     csub(c, h, u2, acc.x);
     csub(c, rr, s2, acc.y);
-    cdbl(c, rr, rr);
-    cadd(c, w, acc.z, h);
-    cmul2(c, hh, h, h, w, w, w);
-    cdbl(c, i, hh); cdbl(c, i, i);
-    csub(c, w, w, z1z1); csub(c, acc.z, w, hh);
-    cmul2(c, j, h, i, v, acc.x, i);
-    cmul2(c, u2, rr, rr, s2, acc.y, j);
-    csub(c, u2, u2, j); csub(c, u2, u2, v); csub(c, u2, u2, v);
-    csub(c, v, v, u2); cmul(c, v, rr, v);
-    cdbl(c, s2, s2);
-    csub(c, acc.y, v, s2);
-    acc.x = u2;
+    cmul2(c, hh, h, h, r2, rr, rr);
+    cmul2(c, hhh, hh, h, v, acc.x, hh);
+    cmul(c, z3, acc.z, h);
+    csub(c, x3, r2, hhh); csub(c, x3, x3, v); csub(c, x3, x3, v);
+    csub(c, v, v, x3);
+    cmul2(c, v, v, rr, hhh, hhh, acc.y);
+    csub(c, acc.y, v, hhh);
+    acc.x = x3;
+    acc.z = z3;
 }
 
 // r = a + (bx, by) affine with zr = Z3 / Z1 (madd-2004-hmv, jac_madd_zr): 11 products in 6 steps; r must not alias a
@@ -296,8 +299,9 @@ static __device__ __noinline__ void cjac_madd_zr(const Ctx& c, CJac& r, const CJ
 static __device__ __noinline__ void cjac_mul_ops(const Ctx& c, CJac& out, const CJac& p, const uint16_t* ops) {
     CFp tx[8], ty[8], bx[8], zr[8];
     CFp zg;
+    const CFp three_halves = const_fp(c, three_halves_limb);
     CJac d;
-    cjac_dbl(c, d, p);
+    cjac_dbl(c, d, p, three_halves);
     {
         CJac cur;
         CFp dz2, dz3;
@@ -328,7 +332,7 @@ static __device__ __noinline__ void cjac_mul_ops(const Ctx& c, CJac& out, const 
     const int n = ops[0];
     for (int k = 1; k <= n; k++) {
         const uint32_t op = ops[k];
-        for (int s = op >> 8; s > 0; s--) cjac_dbl(c, acc, acc);
+        for (int s = op >> 8; s > 0; s--) cjac_dbl(c, acc, acc, three_halves);
         if (op & 0x20) {
             const int idx = op & 7;
             const CFp ex = (op & 0x10) ? bx[idx] : tx[idx];

@@ -168,6 +168,76 @@ EKZG_NTT_UNIT void r4_mul_unit_coop(G1Jac* __restrict__ pts, G1Jac* __restrict__
 }
 #endif
 
+#ifdef __CUDACC__
+// The combination unit of the cooperative kernel (8 blobs per warp): the four lanes of a blob share the unit's additions.  Its 5 - 8
+// additions are only two deep (a = x0 + p1, bm = x0 - p1, cc = p2 + p3, d = p4 - p5, then four independent sums), and in a batch this
+// small the other lanes are idle anyway: every lane does ONE addition per level, its operands and sign picked by its role k = lane & 3
+// -- one instruction stream for the whole warp --, the intermediate sums change hands through `xch` (this warp's 32 slots of shared
+// memory).  All loads from pts happen before the first store to it.  Same sums as r4_combine_unit.
+EKZG_NTT_UNIT void r4_combine_unit_par(G1Jac* __restrict__ pts, const G1Jac* __restrict__ tmp, int B, int b, int k, bool valid, int sp, int c,
+                                       G1Jac* __restrict__ xch /* indexed by lane */) {
+    const int lane = threadIdx.x & 31, base_lane = lane & 28;
+    G1Jac pair[2];   // both operands of an addition in ONE array: see r4_combine_unit below
+    if (sp == 3) {   // pts[c] += tmp[2c], pts[c + 64] += tmp[2c + 1]: two independent additions
+        if (valid && k < 2) {
+            G1Jac* o = &pts[(size_t)(c + 64 * k) * B + b];
+            pair[0] = ld_pt(o);
+            pair[1] = ld_pt(&tmp[(size_t)(2 * c + k) * B + b]);
+            jac_add(pair[0], pair[1]);
+            st_pt(o, pair[0]);
+        }
+        return;
+    }
+    const bool fwd = sp > 3;
+    const int s = fwd ? 2 * (6 - sp) : 2 * sp, len = 1 << s;
+    const int pos = c & (len - 1), base = ((c >> s) << (s + 2)) + pos;
+    G1Jac* o[4];
+    for (int q = 0; q < 4; q++) o[q] = &pts[(size_t)(base + q * len) * B + b];
+    const G1Jac* t0 = &tmp[(size_t)(5 * c) * B + b];
+    // level 1
+    if (valid) {
+        const G1Jac* pa;
+        const G1Jac* pb;
+        bool neg;
+        if (!fwd) {
+            pa = k < 2 ? o[0] : (k == 2 ? t0 + (size_t)B : t0 + (size_t)3 * B);
+            pb = k < 2 ? t0 : (k == 2 ? t0 + (size_t)2 * B : t0 + (size_t)4 * B);
+            neg = (k & 1) != 0;
+        } else {
+            pa = k == 0 ? o[0] : k == 1 ? o[2] : (k == 2 ? t0 + (size_t)B : t0 + (size_t)3 * B);
+            pb = k == 0 ? o[1] : k == 1 ? o[3] : (k == 2 ? t0 + (size_t)2 * B : t0 + (size_t)4 * B);
+            neg = k == 3;
+        }
+        pair[0] = ld_pt(pa);
+        pair[1] = ld_pt(pb);
+        jac_cneg(pair[1], pair[1], neg);
+        jac_add(pair[0], pair[1]);
+        xch[lane] = pair[0];
+    }
+    __syncwarp();
+    // level 2
+    if (valid) {
+        if (!fwd) {          // k = 0: a + cc -> o0, 1: a - cc -> o2, 2: bm + d -> o1, 3: bm - d -> o3
+            pair[0] = xch[base_lane + (k < 2 ? 0 : 1)];
+            pair[1] = xch[base_lane + (k < 2 ? 2 : 3)];
+            jac_cneg(pair[1], pair[1], (k & 1) != 0);
+            jac_add(pair[0], pair[1]);
+            st_pt(o[k == 0 ? 0 : k == 1 ? 2 : k == 2 ? 1 : 3], pair[0]);
+        } else if (k == 0) { // (x0 + x1) + (x2 + x3) -> o0
+            pair[0] = xch[base_lane];
+            pair[1] = xch[base_lane + 1];
+            jac_add(pair[0], pair[1]);
+            st_pt(o[0], pair[0]);
+        } else if (k == 1) {
+            st_pt(o[1], ld_pt(t0));
+        } else {             // the sums of level 1 are final: p2 + p3 -> o2, p4 - p5 -> o3
+            st_pt(o[k], xch[lane]);
+        }
+    }
+    __syncwarp();            // the next unit of this warp reuses xch
+}
+#endif
+
 EKZG_NTT_UNIT void r4_combine_unit(G1Jac* __restrict__ pts, const G1Jac* __restrict__ tmp, int B, int b, int sp, int c) {
     if (sp == 3) {           // pts[c] = x0 + omega^-c x1, pts[c + 64] = x1 + omega^c x0
         // Both operands of the addition sit in ONE array on purpose.  As two separate locals (`G1Jac acc = ld_pt(o); const G1Jac p =

@@ -824,6 +824,7 @@ k_fk20_g1_ntts(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned
 template <int GW>
 __global__ void __launch_bounds__(NTT_THREADS, 2)
 k_fk20_g1_ntts_r4(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int G, int sp_end, unsigned* __restrict__ queue) {
+    __shared__ G1Jac xch[GW == 32 ? 1 : NTT_THREADS];   // cooperative form: intermediate sums of the combination units, one slot per lane
     const int lane = threadIdx.x & 31;
     const unsigned per_sp = (unsigned)G * R4_UNITS, total = per_sp * (unsigned)sp_end;
     for (;;) {
@@ -856,8 +857,8 @@ k_fk20_g1_ntts_r4(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int G
                 else r4_mul_unit(pts, tmp, B, b, sp, u, c_twiddle_ops);
             }
         } else if (comb) {
-            const int b = g * GW + lane;
-            if (lane < GW && b < B) r4_combine_unit(pts, tmp, B, b, sp, u);
+            const int b = g * GW + (lane >> 2);              // all 32 lanes: the four lanes of a blob share the unit's additions
+            r4_combine_unit_par(pts, tmp, B, b, lane & 3, b < B, sp, u, &xch[(threadIdx.x >> 5) * 32]);
         } else {
             r4_mul_unit_coop(pts, tmp, B, g * GW + (lane >> 2), sp, u, c_twiddle_ops);   // all 32 lanes: 8 blobs x 4 lanes
         }
@@ -1533,7 +1534,7 @@ static int k5_r4_max() {
 static int k5_coop_max() {
     // batches up to this many blobs run their multiplication units cooperatively, four lanes per field element (EKZG_K5_COOP_MAX; 0 = never)
     const char* e = getenv("EKZG_K5_COOP_MAX");
-    const int v = e ? atoi(e) : 48;   // measured (tools/k5_sweep.py, profiles/r2_coop_k5_sweep.jsonl): K5 7.1 against 10.2 ms up to 16 blobs, 9.0 against 10.2 at 48, equal at 64
+    const int v = e ? atoi(e) : 80;   // measured (tools/k5_sweep.py, profiles/r2_coop_k5_sweep.jsonl): K5 5.4 against 10.2 ms up to 16 blobs, 7.2 at 32, 8.5 at 64, 10.8 against 10.2 at 96
     return v < 0 ? 0 : (v > R4_MAX_BLOBS ? R4_MAX_BLOBS : v);
 }
 size_t g1_ntt_scratch_bytes() {

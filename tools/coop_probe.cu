@@ -16,6 +16,11 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "field.cuh"
+#ifdef EKZG_PROBE_96
+#define COOP_MUL coop_mul96
+#else
+#define COOP_MUL coop_mul
+#endif
 using namespace ekzg;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
@@ -76,6 +81,64 @@ __device__ __forceinline__ Fp3 coop_mul(const Fp3& a, const Fp3& b, const Fp3& p
     return r;
 }
 
+// ---- radix-2^96 variant: a lane's three limbs are ONE Montgomery digit, four rounds instead of twelve --------------------------------
+// per round: broadcast the three limbs of b's digit j, T += a_lane * b_j (3x3 limbs), m = T_0 * (-p^-1 mod 2^96) from lane 0,
+// T += p_lane * m, shift one DIGIT down (the next lane's low digit comes in).  Same work, a third of the dependent shuffle rounds.
+__device__ __forceinline__ void mul3x3(uint32_t (&P)[6], const Fp3& a, uint32_t b0, uint32_t b1, uint32_t b2) {
+    uint64_t c;
+    c = (uint64_t)a.x0 * b0; P[0] = (uint32_t)c;
+    c = (uint64_t)a.x1 * b0 + (c >> 32); P[1] = (uint32_t)c;
+    c = (uint64_t)a.x2 * b0 + (c >> 32); P[2] = (uint32_t)c; P[3] = (uint32_t)(c >> 32);
+    c = (uint64_t)a.x0 * b1 + P[1]; P[1] = (uint32_t)c;
+    c = (uint64_t)a.x1 * b1 + P[2] + (c >> 32); P[2] = (uint32_t)c;
+    c = (uint64_t)a.x2 * b1 + P[3] + (c >> 32); P[3] = (uint32_t)c; P[4] = (uint32_t)(c >> 32);
+    c = (uint64_t)a.x0 * b2 + P[2]; P[2] = (uint32_t)c;
+    c = (uint64_t)a.x1 * b2 + P[3] + (c >> 32); P[3] = (uint32_t)c;
+    c = (uint64_t)a.x2 * b2 + P[4] + (c >> 32); P[4] = (uint32_t)c; P[5] = (uint32_t)(c >> 32);
+}
+__device__ __forceinline__ void add6(uint32_t (&T)[7], const uint32_t (&P)[6]) {
+    asm("add.cc.u32 %0, %0, %7;\n\t addc.cc.u32 %1, %1, %8;\n\t addc.cc.u32 %2, %2, %9;\n\t addc.cc.u32 %3, %3, %10;\n\t"
+        "addc.cc.u32 %4, %4, %11;\n\t addc.cc.u32 %5, %5, %12;\n\t addc.u32 %6, %6, 0;"
+        : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "+r"(T[3]), "+r"(T[4]), "+r"(T[5]), "+r"(T[6])
+        : "r"(P[0]), "r"(P[1]), "r"(P[2]), "r"(P[3]), "r"(P[4]), "r"(P[5]));
+}
+__device__ __forceinline__ Fp3 coop_mul96(const Fp3& a, const Fp3& b, const Fp3& p, unsigned gl) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t N0 = 0xfffcfffdu, N1 = 0x89f3fffcu, N2 = 0xd9d113e8u;   // -p^-1 mod 2^96
+    uint32_t T[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t b0 = __shfl_sync(full, b.x0, j, 4), b1 = __shfl_sync(full, b.x1, j, 4), b2 = __shfl_sync(full, b.x2, j, 4);
+        uint32_t P[6];
+        mul3x3(P, a, b0, b1, b2);
+        add6(T, P);
+        // m = T[0..2] * N mod 2^96 (every lane on its own digit; lane 0's is the one that counts)
+        uint32_t m0, m1, m2;
+        {
+            uint64_t c = (uint64_t)T[0] * N0; m0 = (uint32_t)c;
+            c = (uint64_t)T[0] * N1 + (c >> 32) + (uint64_t)((uint32_t)(T[1] * N0)); m1 = (uint32_t)c;
+            m2 = (uint32_t)(c >> 32) + __umulhi(T[1], N0) + T[0] * N2 + T[1] * N1 + T[2] * N0;
+        }
+        m0 = __shfl_sync(full, m0, 0, 4); m1 = __shfl_sync(full, m1, 0, 4); m2 = __shfl_sync(full, m2, 0, 4);
+        mul3x3(P, p, m0, m1, m2);
+        add6(T, P);
+        uint32_t y0 = __shfl_down_sync(full, T[0], 1, 4), y1 = __shfl_down_sync(full, T[1], 1, 4), y2 = __shfl_down_sync(full, T[2], 1, 4);
+        if (gl == 3) { y0 = 0; y1 = 0; y2 = 0; }
+        asm("add.cc.u32 %0, %4, %7;\n\t addc.cc.u32 %1, %5, %8;\n\t addc.cc.u32 %2, %6, %9;\n\t addc.u32 %3, %10, 0;"
+            : "=r"(T[0]), "=r"(T[1]), "=r"(T[2]), "=r"(T[3]) : "r"(T[3]), "r"(T[4]), "r"(T[5]), "r"(y0), "r"(y1), "r"(y2), "r"(T[6]));
+        T[4] = 0; T[5] = 0; T[6] = 0;
+    }
+    for (int pass = 0; pass < 3; pass++) {
+        uint32_t c = __shfl_up_sync(full, T[3], 1, 4);
+        if (gl == 0) c = 0;
+        asm("add.cc.u32 %0, %0, %4;\n\t addc.cc.u32 %1, %1, 0;\n\t addc.cc.u32 %2, %2, 0;\n\t addc.u32 %3, 0, 0;" : "+r"(T[0]), "+r"(T[1]), "+r"(T[2]), "=r"(T[3]) : "r"(c));
+        if (!__any_sync(full, T[3] != 0)) break;
+    }
+    Fp3 r;
+    r.x0 = T[0]; r.x1 = T[1]; r.x2 = T[2];
+    return r;
+}
+
 // ---- correctness: every group multiplies its own pair both ways ---------------------------------------------------------------
 __global__ void k_check(const Fp* a, const Fp* b, uint32_t* bad, int n, int chain) {
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
@@ -88,7 +151,7 @@ __global__ void k_check(const Fp* a, const Fp* b, uint32_t* bad, int n, int chai
         Fp r;
         fe_mul_inline<FpParams>(r, x, y);
         x = r;
-        cx = coop_mul(cx, cy, p, gl);
+        cx = COOP_MUL(cx, cy, p, gl);
     }
     // reassemble the cooperative result in every lane and bring it below p
     uint32_t w[12];
@@ -131,7 +194,7 @@ __global__ void __launch_bounds__(128) k_coop(const Fp* a, const Fp* b, Fp* out,
     const Fp& ya = b[(t >> 2) & 1023];
     Fp3 x = {xa.v[3 * gl], xa.v[3 * gl + 1], xa.v[3 * gl + 2]}, y = {ya.v[3 * gl], ya.v[3 * gl + 1], ya.v[3 * gl + 2]};
     const Fp3 p = p_of_lane(gl);
-    for (int it = 0; it < iters; it++) x = coop_mul(x, y, p, gl);
+    for (int it = 0; it < iters; it++) x = COOP_MUL(x, y, p, gl);
     if (x.x0 == 0x12345678u && x.x2 == 77u) out[(t >> 2) & 1023].v[gl] = x.x1;
 }
 // two independent products per group in flight (what a point formula offers: its multiplications come in independent pairs)
@@ -144,8 +207,8 @@ __global__ void __launch_bounds__(128) k_coop2(const Fp* a, const Fp* b, Fp* out
     Fp3 u = y, v = x;
     const Fp3 p = p_of_lane(gl);
     for (int it = 0; it < iters; it++) {
-        x = coop_mul(x, y, p, gl);
-        u = coop_mul(u, v, p, gl);
+        x = COOP_MUL(x, y, p, gl);
+        u = COOP_MUL(u, v, p, gl);
     }
     if ((x.x0 ^ u.x0) == 0x12345678u && x.x2 == 77u) out[(t >> 2) & 1023].v[gl] = x.x1 + u.x1;
 }
