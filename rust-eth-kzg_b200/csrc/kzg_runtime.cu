@@ -71,7 +71,7 @@ void host_blob_challenge(const uint8_t* blob, const uint8_t* commitment48, uint8
 
 int direct_proofs_max() {
     const char* e = getenv("EKZG_DIRECT_MAX");
-    const int v = e ? atoi(e) : 2;
+    const int v = e ? atoi(e) : 1;   // two blobs: 8.2 ms direct against 7.0 ms through FK20 with the cooperative G1 NTTs (profiles/r2_latency_sweep.jsonl)
     return v < 0 ? 0 : (v > 8 ? 8 : v);
 }
 
@@ -822,14 +822,15 @@ Status Context::coalesce(int which, CoalesceReq& me) const {
         while (Bt->copied < Bt->n) Q.cv_leader.wait(lk);
         const int n = Bt->n;
         const int flying = Q.in_flight++;
+        const bool crowded = flying >= 1 || Q.callers > n;   // other batches on the device, or callers that did not make it into this one
         lk.unlock();
         const auto t_run = std::chrono::steady_clock::now();
         Status s = Status::Ok();
         try {
             std::fill(st.status.begin(), st.status.begin() + n, 0);
-            // other batches are on the device already: this one cannot have it to itself, so ask for the G1-NTT kernel with the
-            // least work (kzg_kernels.h) instead of the latency-mode one
-            set_k5_throughput_hint(flying >= 1);
+            // other batches are on the device already (or the next one is forming behind this one): this batch cannot have the
+            // device to itself, so ask for the G1-NTT kernel with the least work (kzg_kernels.h) instead of the latency-mode ones
+            set_k5_throughput_hint(crowded);
             if (recover) s = recover_cells_and_kzg_proofs_strided(n, st.counts.data(), st.indices.data(), st.in, st.cells, st.proofs, st.status.data());
             else s = compute_cells_and_kzg_proofs_batch(n, st.in, st.cells, want_proofs ? st.proofs : nullptr, st.status.data(), want_proofs);
         } catch (const std::exception& ex) {             // fail the batch, never the queue

@@ -204,7 +204,7 @@ def test_k4_alternative_forms_equal_default(vec_ctx, pkg, form, monkeypatch):
 
 def test_direct_proofs_equal_fk20(vec_ctx, pkg, monkeypatch):
     """the latency path for one or two blobs -- every proof as its own 4096-point MSM of f div (X^64 - c_k) over the SRS tables
-    (EKZG_DIRECT_MAX, default 2) -- against the FK20 route on the same blobs: synthetic, all-zero, all r-1, constant (128 identity
+    (EKZG_DIRECT_MAX, default 1) -- against the FK20 route on the same blobs: synthetic, all-zero, all r-1, constant (128 identity
     proofs) and the reference bench's blob; through the batch entry point, the single-blob symbol, recovery, and the oracle"""
     from oracle import cref
     syn = _synth(pkg)
