@@ -151,20 +151,25 @@ __device__ __forceinline__ void mad3(uint32_t& t0, uint32_t& t1, uint32_t& t2, u
 // low word, t += p_lane m, shift one limb down pulling the next lane's low word in; the carries that leave a lane's three limbs wait
 // in (h0, h1) and are folded into the next lane once at the end.  One copy per kernel image.
 static __device__ __noinline__ CFp cmul(CFp a, CFp b, CFp p, unsigned gl) {
-    uint32_t t0 = 0, t1 = 0, t2 = 0, h0 = 0, h1 = 0;
+    uint32_t t0 = 0, t1 = 0, t2 = 0, h0 = 0, h1 = 0, ypend = 0;
+    uint32_t bb[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) bb[i] = __shfl_sync(FULL, b.v[i % 3], i / 3, 4);   // all broadcasts of b up front: off the critical path
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        const uint32_t bi = __shfl_sync(FULL, b.v[i % 3], i / 3, 4);
-        mad3(t0, t1, t2, h0, h1, a, bi);
-        const uint32_t m = __shfl_sync(FULL, t0, 0, 4) * FpParams::M0;
+        mad3(t0, t1, t2, h0, h1, a, bb[i]);
+        uint32_t m = __shfl_sync(FULL, t0, 0, 4);
+        // the word shifted in from the next lane at the END of the previous row is added only now: a warp issues in order, so consuming
+        // that shuffle right away would stall the whole row on its latency; one row later it has long arrived (the limb it belongs to is
+        // still t2, and lane 0's t0 -- the only word m depends on -- is two rows away from it)
+        asm("add.cc.u32 %0, %0, %3;\n\t addc.cc.u32 %1, %1, 0;\n\t addc.u32 %2, %2, 0;" : "+r"(t2), "+r"(h0), "+r"(h1) : "r"(ypend));
+        m *= FpParams::M0;
         mad3(t0, t1, t2, h0, h1, p, m);
-        uint32_t y = __shfl_down_sync(FULL, t0, 1, 4);
-        if (gl == 3) y = 0;
-        t0 = t1;
-        t1 = t2;
-        asm("add.cc.u32 %0, %2, %3;\n\t addc.u32 %1, %4, 0;" : "=r"(t2), "=r"(h0) : "r"(h0), "r"(y), "r"(h1));
-        h1 = 0;
+        ypend = __shfl_down_sync(FULL, t0, 1, 4);
+        if (gl == 3) ypend = 0;
+        t0 = t1; t1 = t2; t2 = h0; h0 = h1; h1 = 0;
     }
+    asm("add.cc.u32 %0, %0, %2;\n\t addc.u32 %1, %1, 0;" : "+r"(t2), "+r"(h0) : "r"(ypend));
     for (int pass = 0; pass < 3; pass++) {     // a second / third pass only if a carry ripples through a whole lane
         uint32_t cin = __shfl_up_sync(FULL, h0, 1, 4);
         if (gl == 0) cin = 0;
@@ -183,28 +188,34 @@ __device__ __forceinline__ void csqr(const Ctx& c, CFp& r, const CFp& a) { r = c
 // two separate calls by itself).  The point formulas below issue their multiplications in independent pairs wherever they have them.
 struct CFp2 { CFp a, b; };
 static __device__ __noinline__ CFp2 cmul2(CFp a1, CFp b1, CFp a2, CFp b2, CFp p, unsigned gl) {
-    uint32_t t0 = 0, t1 = 0, t2 = 0, h0 = 0, h1 = 0;
-    uint32_t u0 = 0, u1 = 0, u2 = 0, k0 = 0, k1 = 0;
+    uint32_t t0 = 0, t1 = 0, t2 = 0, h0 = 0, h1 = 0, ypend = 0;
+    uint32_t u0 = 0, u1 = 0, u2 = 0, k0 = 0, k1 = 0, wpend = 0;
+    uint32_t bb[12], cb[12];
 #pragma unroll
     for (int i = 0; i < 12; i++) {
-        const uint32_t bi = __shfl_sync(FULL, b1.v[i % 3], i / 3, 4);
-        const uint32_t ci = __shfl_sync(FULL, b2.v[i % 3], i / 3, 4);
-        mad3(t0, t1, t2, h0, h1, a1, bi);
-        mad3(u0, u1, u2, k0, k1, a2, ci);
-        const uint32_t m = __shfl_sync(FULL, t0, 0, 4) * FpParams::M0;
-        const uint32_t n = __shfl_sync(FULL, u0, 0, 4) * FpParams::M0;
-        mad3(t0, t1, t2, h0, h1, p, m);
-        mad3(u0, u1, u2, k0, k1, p, n);
-        uint32_t y = __shfl_down_sync(FULL, t0, 1, 4);
-        uint32_t w = __shfl_down_sync(FULL, u0, 1, 4);
-        if (gl == 3) { y = 0; w = 0; }
-        t0 = t1; t1 = t2;
-        asm("add.cc.u32 %0, %2, %3;\n\t addc.u32 %1, %4, 0;" : "=r"(t2), "=r"(h0) : "r"(h0), "r"(y), "r"(h1));
-        h1 = 0;
-        u0 = u1; u1 = u2;
-        asm("add.cc.u32 %0, %2, %3;\n\t addc.u32 %1, %4, 0;" : "=r"(u2), "=r"(k0) : "r"(k0), "r"(w), "r"(k1));
-        k1 = 0;
+        bb[i] = __shfl_sync(FULL, b1.v[i % 3], i / 3, 4);
+        cb[i] = __shfl_sync(FULL, b2.v[i % 3], i / 3, 4);
     }
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        mad3(t0, t1, t2, h0, h1, a1, bb[i]);
+        uint32_t m = __shfl_sync(FULL, t0, 0, 4);
+        mad3(u0, u1, u2, k0, k1, a2, cb[i]);
+        uint32_t n = __shfl_sync(FULL, u0, 0, 4);
+        asm("add.cc.u32 %0, %0, %3;\n\t addc.cc.u32 %1, %1, 0;\n\t addc.u32 %2, %2, 0;" : "+r"(t2), "+r"(h0), "+r"(h1) : "r"(ypend));   // (see cmul)
+        asm("add.cc.u32 %0, %0, %3;\n\t addc.cc.u32 %1, %1, 0;\n\t addc.u32 %2, %2, 0;" : "+r"(u2), "+r"(k0), "+r"(k1) : "r"(wpend));
+        m *= FpParams::M0;
+        mad3(t0, t1, t2, h0, h1, p, m);
+        ypend = __shfl_down_sync(FULL, t0, 1, 4);
+        n *= FpParams::M0;
+        mad3(u0, u1, u2, k0, k1, p, n);
+        wpend = __shfl_down_sync(FULL, u0, 1, 4);
+        if (gl == 3) { ypend = 0; wpend = 0; }
+        t0 = t1; t1 = t2; t2 = h0; h0 = h1; h1 = 0;
+        u0 = u1; u1 = u2; u2 = k0; k0 = k1; k1 = 0;
+    }
+    asm("add.cc.u32 %0, %0, %2;\n\t addc.u32 %1, %1, 0;" : "+r"(t2), "+r"(h0) : "r"(ypend));
+    asm("add.cc.u32 %0, %0, %2;\n\t addc.u32 %1, %1, 0;" : "+r"(u2), "+r"(k0) : "r"(wpend));
     for (int pass = 0; pass < 3; pass++) {
         uint32_t cin = __shfl_up_sync(FULL, h0, 1, 4), din = __shfl_up_sync(FULL, k0, 1, 4);
         if (gl == 0) { cin = 0; din = 0; }

@@ -51,10 +51,14 @@ __device__ __forceinline__ void mad3(uint32_t& t0, uint32_t& t1, uint32_t& t2, u
         : "r"(a.x0), "r"(a.x1), "r"(a.x2), "r"(s));
 }
 
-// a, b in [0, 2p), lane gl of a 4-lane group holds limbs 3 gl .. 3 gl + 2; returns a b / 2^384 mod p in [0, 2p)
+// a, b in [0, 2p), lane gl of a 4-lane group holds limbs 3 gl .. 3 gl + 2; returns a b / 2^384 mod p in [0, 2p).
+// EKZG_PROBE_V1: the first schedule (the word shifted in from the next lane is consumed at once: the in-order warp then waits for two
+// shuffles per row, 967 clocks per product); default: the schedule of csrc/g1_coop.cuh (b broadcast up front, the shifted-in word added
+// one row later).
 __device__ __forceinline__ Fp3 coop_mul(const Fp3& a, const Fp3& b, const Fp3& p, unsigned gl) {
     const unsigned full = 0xffffffffu;
     uint32_t t0 = 0, t1 = 0, t2 = 0, h0 = 0, h1 = 0;
+#ifdef EKZG_PROBE_V1
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         const uint32_t bsel = (i % 3 == 0) ? b.x0 : (i % 3 == 1) ? b.x1 : b.x2;
@@ -69,6 +73,23 @@ __device__ __forceinline__ Fp3 coop_mul(const Fp3& a, const Fp3& b, const Fp3& p
         asm("add.cc.u32 %0, %2, %3;\n\t addc.u32 %1, %4, 0;" : "=r"(t2), "=r"(h0) : "r"(h0), "r"(y), "r"(h1));
         h1 = 0;
     }
+#else
+    uint32_t ypend = 0, bb[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) bb[i] = __shfl_sync(full, (i % 3 == 0) ? b.x0 : (i % 3 == 1) ? b.x1 : b.x2, i / 3, 4);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        mad3(t0, t1, t2, h0, h1, a, bb[i]);
+        uint32_t m = __shfl_sync(full, t0, 0, 4);
+        asm("add.cc.u32 %0, %0, %3;\n\t addc.cc.u32 %1, %1, 0;\n\t addc.u32 %2, %2, 0;" : "+r"(t2), "+r"(h0), "+r"(h1) : "r"(ypend));
+        m *= FpParams::M0;
+        mad3(t0, t1, t2, h0, h1, p, m);
+        ypend = __shfl_down_sync(full, t0, 1, 4);
+        if (gl == 3) ypend = 0;
+        t0 = t1; t1 = t2; t2 = h0; h0 = h1; h1 = 0;
+    }
+    asm("add.cc.u32 %0, %0, %2;\n\t addc.u32 %1, %1, 0;" : "+r"(t2), "+r"(h0) : "r"(ypend));
+#endif
     // fold the deferred carries into the next lane; a second and third pass only if a carry ripples through a whole lane
     for (int pass = 0; pass < 3; pass++) {
         uint32_t c = __shfl_up_sync(full, h0, 1, 4);

@@ -33,6 +33,15 @@ def run(pkg, syn, fk20_w, srs_w, nb):
     c2, p2 = ctx.compute_cells_and_kzg_proofs(blobs[0])
     del os.environ["EKZG_K5_R4_MAX"]
     assert p2 == p1
+    # latency mode of the G1 NTTs with identity points in some lanes: cooperative form (four lanes per field element) against the
+    # lane-per-blob form, 9 blobs = one full group of eight + a ragged one
+    edge = [syn.blob(70 + i) for i in range(5)] + list(syn.edge_blobs())[:4]
+    os.environ["EKZG_DIRECT_MAX"] = "0"
+    got = ctx.compute_cells_and_kzg_proofs_batch(b"".join(edge), 9)
+    os.environ["EKZG_K5_COOP_MAX"] = "0"
+    want = ctx.compute_cells_and_kzg_proofs_batch(b"".join(edge), 9)
+    del os.environ["EKZG_K5_COOP_MAX"], os.environ["EKZG_DIRECT_MAX"]
+    assert got[1] == want[1] and got[0] == want[0]
     sel = [0, 5, 64, 127]
     assert ctx.verify_cell_kzg_proof_batch([com[:48]] * 4, sel, [c1[j] for j in sel], [p1[j] for j in sel]) is True
     assert ctx.verify_cell_kzg_proof_batch([com[:48]] * 4, sel, [c1[j] for j in sel], [p1[j] for j in (5, 0, 64, 127)]) is False
