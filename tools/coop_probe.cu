@@ -16,7 +16,10 @@
 #include <vector>
 #include <cuda_runtime.h>
 #include "field.cuh"
-#ifdef EKZG_PROBE_96
+#ifdef EKZG_PROBE_LIB
+#include "g1_coop.cuh"   // the multiplier the library ships (shadow chain of lane 0: no shuffle on the critical path)
+#define COOP_MUL coop_mul_lib
+#elif defined(EKZG_PROBE_96)
 #define COOP_MUL coop_mul96
 #else
 #define COOP_MUL coop_mul
@@ -25,6 +28,11 @@ using namespace ekzg;
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(2); } } while (0)
 
 struct Fp3 { uint32_t x0, x1, x2; };
+#ifdef EKZG_PROBE_LIB
+__device__ __forceinline__ coop::CFp to_c(const Fp3& a) { coop::CFp r; r.v[0] = a.x0; r.v[1] = a.x1; r.v[2] = a.x2; return r; }
+__device__ __forceinline__ Fp3 from_c(const coop::CFp& a) { Fp3 r; r.x0 = a.v[0]; r.x1 = a.v[1]; r.x2 = a.v[2]; return r; }
+__device__ __forceinline__ Fp3 coop_mul_lib(const Fp3& a, const Fp3& b, const Fp3& p, unsigned gl) { return from_c(coop::cmul(to_c(a), to_c(b), to_c(p), gl)); }
+#endif
 
 __device__ __forceinline__ uint32_t p_limb(int i) { return FpParams::mod(i); }
 __device__ __forceinline__ Fp3 p_of_lane(unsigned gl) {
@@ -228,8 +236,14 @@ __global__ void __launch_bounds__(128) k_coop2(const Fp* a, const Fp* b, Fp* out
     Fp3 u = y, v = x;
     const Fp3 p = p_of_lane(gl);
     for (int it = 0; it < iters; it++) {
+#ifdef EKZG_PROBE_LIB
+        const coop::CFp2 r2 = coop::cmul2(to_c(x), to_c(y), to_c(u), to_c(v), to_c(p), gl);   // the dual multiplier
+        x = from_c(r2.a);
+        u = from_c(r2.b);
+#else
         x = COOP_MUL(x, y, p, gl);
         u = COOP_MUL(u, v, p, gl);
+#endif
     }
     if ((x.x0 ^ u.x0) == 0x12345678u && x.x2 == 77u) out[(t >> 2) & 1023].v[gl] = x.x1 + u.x1;
 }
