@@ -482,6 +482,8 @@ def main():
         if "latency_1blob_ms" in cfgs.get("1", {}):
             line["latency_1blob_ms"] = cfgs["1"]["latency_1blob_ms"]
             line["latency_32blob_ms"] = cfgs["1"]["latency_32blob_ms"]
+            if "latency_8blob_batch_ms" in cfgs["1"]:
+                line["latency_8blob_batch_ms"] = cfgs["1"]["latency_8blob_batch_ms"]
     ctx.close()
     del d_in
     torch.cuda.empty_cache()

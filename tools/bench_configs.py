@@ -279,7 +279,21 @@ def latency(ctx, pkg, reps=5):
         "verify_cell_kzg_proof_batch_128_cells": both(lambda: ctx.verify_cell_kzg_proof_batch([cm] * NCELLS, list(range(NCELLS)), got_c, got_p),
                                                       lambda: cref.verify_cell_kzg_proof_batch([cm] * NCELLS, list(range(NCELLS)), got_c, got_p)),
     }
+    # a block's worth of blobs in ONE batch call (preallocated host buffers): FK20 in latency mode (cooperative G1 NTTs)
+    nb = 8
+    src = bytearray(b"".join(blobs[:nb]))
+    bc, bp, bs = bytearray(nb * NCELLS * CELL), bytearray(nb * NCELLS * 48), bytearray(nb)
+    cb, cc_, cp_, cs_ = [(C.c_char * len(x)).from_buffer(x) for x in (src, bc, bp, bs)]
+    batch8 = lambda: _ok(lib.eth_kzg_b200_compute_cells_and_kzg_proofs_batch(H, C.c_uint64(nb), cb, cc_, cp_, cs_))
+    batch8()
+    eight = sorted(best(batch8, 1)[0] for _ in range(reps))
+    assert bytes(bc[:NCELLS * CELL]) == b"".join(oc) and bytes(bp[:NCELLS * 48]) == b"".join(op), "8-blob batch differs from the oracle"
+    t0 = time.perf_counter()
+    cref.compute_cells_and_kzg_proofs_batch(bytes(src), nb)
+    tc8 = time.perf_counter() - t0
     return {"workload": "compute_cells_and_kzg_proofs for 1 blob through eth_kzg_compute_cells_and_kzg_proofs (BASELINE config #1)",
+            "latency_8blob_batch_ms": 1e3 * eight[len(eight) // 2], "cpu_port_8blob_batch_ms": 1e3 * tc8, "cpu_port_8blob_threads": cref.num_threads(),
+            "latency_8blob_note": "8 blobs (a block's worth) in one eth_kzg_b200_compute_cells_and_kzg_proofs_batch call, host buffers",
             "latency_1blob_ms": 1e3 * one[len(one) // 2], "latency_1blob_ms_min": 1e3 * one[0],
             "latency_32blob_ms": 1e3 * many[len(many) // 2], "latency_32blob_note": "32 host threads, one single-blob call each, started together; until the last returns",
             "cpu_port_1blob_ms": 1e3 * tc, "cpu_port_threads": 1, "parity_checked": 1,
