@@ -331,6 +331,7 @@ k_fk20_msm_vm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, Msm
     const int b = b0 + blockIdx.x * BLOBS_PER_CTA + lane_b;
     const bool active = b < b1;
     bool inf = true;                       // accumulator is the identity (nothing in slots 0..3 yet)
+    int comb = 0, radix = 1;               // digits of the merged top window collected so far
     if (active) {
         const int w = T.w, nw = T.nw, mg = T.mg;
         const int nreg = mg > 1 ? nw - 1 : nw;
@@ -346,7 +347,6 @@ k_fk20_msm_vm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, Msm
         pend = np_;                                               \
         pend_neg = (negflag);                                     \
     } while (0)
-        int comb = 0, radix = 1;
         for (int kk = 0; kk < KPER; kk++) {
             const int k = slice * KPER + kk;
             const uint4* sp = reinterpret_cast<const uint4*>(scalars + ((size_t)(j * FK20_POINTS + k) * B + b) * 8);
@@ -378,6 +378,22 @@ k_fk20_msm_vm(const uint32_t* __restrict__ scalars, G1Jac* __restrict__ pts, Msm
         }
         if (pend) inf = k4_accumulate(base, pend, pend_neg, inf);
 #undef K4_EMIT
+    }
+    if (KPER < 4 && T.mg > 1) {
+        // fewer points per thread than the merged top window ties together (64 slices: ONE point per thread): the top digits of a group
+        // of mg consecutive points sit in mg neighbouring slices -- threads BLOBS_PER_CTA apart, in one warp -- and the thread of the
+        // group's first point adds the merged entry.  (Every thread of the CTA is here: inactive ones contribute zero digits.)
+        static_assert(KPER >= 4 || KPER == 1, "one point per thread, or whole merge groups");
+        const int mg = T.mg;
+        int total = comb, rad = T.rtop;
+        for (int i = 1; i < mg; i++) {
+            total += rad * __shfl_down_sync(0xffffffffu, comb, i * BLOBS_PER_CTA);
+            rad *= T.rtop;
+        }
+        if (active && (slice & (mg - 1)) == 0 && total != 0) {
+            const G1Affine* tg = T.table + (size_t)(j * FK20_POINTS + slice) * T.nw * T.half;   // top slice of the group's first point
+            inf = k4_accumulate(base, &tg[(size_t)(T.nw - 1) * T.half + total - 1], false, inf);
+        }
     }
     if (NSLICE > 1) {
         __shared__ uint8_t s_inf[128];
@@ -1461,6 +1477,8 @@ static size_t k4a_min_work() {   // launches with fewer (blob, MSM) pairs use th
     return e ? (size_t)atoll(e) : (size_t)512 * 128;
 }
 
+static bool k4_no_tiny() { const char* e = getenv("EKZG_K4_NO_TINY"); return e && *e == '1'; }   // A/B and test knob: never the 64-slice form
+
 cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable& T, int ngroups, int B, cudaStream_t st, int b0, int cnt,
                              void* scratch) {
     // ngroups MSMs of 64 points each per blob (FK20: 128; SRS commitment: 64 partial sums), blobs [b0, b0 + cnt) of the
@@ -1484,7 +1502,8 @@ cudaError_t launch_fixed_msm(const uint32_t* scalars, G1Jac* pts, const MsmTable
     } else {
         // a handful of blobs on a table without a merged top window (the SRS tables at w = 13: a thread may own a single point):
         // 64 slices, one point per thread -- 20 additions and a 6-level reduction on the critical path instead of 80 and 4
-        const bool tiny = T.mg == 1 && (size_t)cnt * ngroups <= 8 * 64;
+        // (FK20 tables with a merged top window as well: the digits of a merge group are gathered across its threads; up to 16 blobs)
+        const bool tiny = T.mg <= 4 && (size_t)cnt * ngroups <= (T.mg == 1 ? 8 * 64 : 16 * 128) && !k4_no_tiny();
         if (wide) k_fk20_msm_vm<4><<<dim3((cnt + 31) / 32, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);
         else if (tiny) k_fk20_msm_vm<64><<<dim3((cnt + 1) / 2, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);
         else k_fk20_msm_vm<16><<<dim3((cnt + 7) / 8, ngroups), fpvm::NT, fpvm::SMEM_BYTES, st>>>(scalars, pts, T, B, b0, b0 + cnt);

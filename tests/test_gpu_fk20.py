@@ -182,6 +182,28 @@ def test_k5_radix4_equals_radix2(vec_ctx, pkg, n, coop, monkeypatch):
         assert got[1][i * 6144:(i + 1) * 6144] == b"".join(op)
 
 
+@pytest.mark.parametrize("n", [2, 5, 16])
+def test_k4_one_point_per_thread_form(vec_ctx, pkg, n, monkeypatch):
+    """small batches run the fixed-base MSM with ONE point per thread (64 slices); on tables with a merged top window the digits of a
+    merge group are then gathered across neighbouring threads -- against the 16-slice form, the register form and the oracle"""
+    syn = _synth(pkg)
+    blobs = [syn.blob(8800 + i) for i in range(n)]
+    if n >= 5:
+        blobs[1:5] = list(syn.edge_blobs())[:4]
+    flat = b"".join(blobs)
+    monkeypatch.setenv("EKZG_DIRECT_MAX", "0")
+    got = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
+    monkeypatch.setenv("EKZG_K4_NO_TINY", "1")
+    want = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
+    monkeypatch.setenv("EKZG_K4", "r")
+    want_r = vec_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
+    assert got[2] == want[2] == [0] * n
+    assert got[1] == want[1] == want_r[1]
+    from oracle import cref
+    oc, op = cref.compute_cells_and_kzg_proofs(blobs[0])
+    assert got[1][:6144] == b"".join(op) and got[0][:262144] == b"".join(oc)
+
+
 @pytest.mark.parametrize("form", ["r", "a"], ids=["register_xyzz", "batched_affine"])
 def test_k4_alternative_forms_equal_default(vec_ctx, pkg, form, monkeypatch):
     """the A/B forms of the fixed-base MSM kernel that stay in the tree (EKZG_K4: register XYZZ of round 1; batched affine with a
