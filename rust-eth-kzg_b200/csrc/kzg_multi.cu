@@ -75,16 +75,19 @@ const Context* DeviceSet::owner_of(const void* device_ptr) const {
 }
 
 void DeviceSet::shard_bounds(uint64_t n, size_t parts, size_t i, uint64_t* lo, uint64_t* cnt) {
-    const uint64_t groups = (n + 31) / 32;
+    // whole blob groups of the G1-NTT kernels: 32 blobs per warp, or 8 where a device's share is small enough for the cooperative
+    // latency-mode kernel (four lanes per field element, up to 80 blobs) -- 64 blobs on eight devices are eight shards of 8, not two of 32
+    const uint64_t gw = (n + parts - 1) / parts <= 80 ? 8 : 32;
+    const uint64_t groups = (n + gw - 1) / gw;
     const uint64_t g0 = groups * i / parts, g1 = groups * (i + 1) / parts;
-    const uint64_t a = std::min<uint64_t>(n, g0 * 32), b = std::min<uint64_t>(n, g1 * 32);
+    const uint64_t a = std::min<uint64_t>(n, g0 * gw), b = std::min<uint64_t>(n, g1 * gw);
     *lo = a;
     *cnt = b - a;
 }
 
 Status DeviceSet::fan_out(uint64_t n, const std::function<Status(const Context&, uint64_t, uint64_t)>& fn) const {
     const size_t D = ctx_.size();
-    if (D == 1 || n <= 32) return fn(*ctx_[0], 0, n);
+    if (D == 1 || n <= 8) return fn(*ctx_[0], 0, n);
     std::vector<Status> st(D);
     std::vector<std::thread> th;
     uint64_t lo0 = 0, cnt0 = 0;
@@ -133,7 +136,7 @@ Status DeviceSet::compute_blob_kzg_proof_batch(uint64_t n, const uint8_t* blobs,
 
 Status DeviceSet::recover_cells_and_kzg_proofs_batch(uint64_t n, const uint64_t* counts, const uint64_t* indices, const uint8_t* cells,
                                                      uint8_t* out_cells, uint8_t* out_proofs, uint8_t* item_status) const {
-    if (ctx_.size() == 1 || n <= 32) return ctx_[0]->recover_cells_and_kzg_proofs_batch(n, counts, indices, cells, out_cells, out_proofs, item_status);
+    if (ctx_.size() == 1 || n <= 8) return ctx_[0]->recover_cells_and_kzg_proofs_batch(n, counts, indices, cells, out_cells, out_proofs, item_status);
     constexpr size_t CELLS_PER_BLOB = (size_t)N_EXT * 32, PROOFS_PER_BLOB = (size_t)N_CELLS * BYTES_PER_G1;
     std::vector<uint64_t> offset(n + 1, 0);   // blob i's cells and indices start at offset[i] in the concatenated inputs
     for (uint64_t i = 0; i < n; i++) offset[i + 1] = offset[i] + counts[i];

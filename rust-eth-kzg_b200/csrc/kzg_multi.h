@@ -27,8 +27,8 @@ public:
     // the member whose device owns this device pointer (nullptr if none does)
     const Context* owner_of(const void* device_ptr) const;
 
-    // shard i of a batch of n items over `parts` devices: whole 32-item groups (a K5 work unit is 32 blobs wide), sizes
-    // differing by at most one group
+    // shard i of a batch of n items over `parts` devices: whole blob groups of the G1-NTT kernels (32 items, or 8 where a device's
+    // share is at most 80 items: the cooperative latency-mode kernel), sizes differing by at most one group
     static void shard_bounds(uint64_t n, size_t parts, size_t i, uint64_t* lo, uint64_t* cnt);
 
     // Runs fn(context, first item, item count) once per non-empty shard, shard 0 on the calling thread and the others on

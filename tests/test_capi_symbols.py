@@ -84,12 +84,14 @@ def test_c_consumer_on_gpu(lib, pkg):
 
 
 def test_device_shard_bounds(lib):
-    """csrc/kzg_multi.cu: the shards of a multi-device batch cover every item once, in order, in whole 32-item groups"""
+    """csrc/kzg_multi.cu: the shards of a multi-device batch cover every item once, in order, in whole blob groups (32 items; 8 where
+    a device's share is at most 80 items, the range of the cooperative latency-mode G1-NTT kernel)"""
     f = lib.eth_kzg_b200_debug_shard_bounds
     f.argtypes = [ctypes.c_uint64] * 3 + [ctypes.POINTER(ctypes.c_uint64)] * 2
     f.restype = None
-    for n in (0, 1, 31, 32, 33, 100, 128, 1000, 1024, 4097):
+    for n in (0, 1, 8, 9, 31, 32, 33, 64, 100, 128, 640, 641, 1000, 1024, 4097):
         for parts in (1, 2, 3, 4, 8):
+            gw = 8 if -(-n // parts) <= 80 else 32
             spans = []
             for i in range(parts):
                 lo, cnt = ctypes.c_uint64(), ctypes.c_uint64()
@@ -99,7 +101,9 @@ def test_device_shard_bounds(lib):
             for (lo, c), (lo2, _) in zip(spans, spans[1:]):
                 assert lo + c == lo2
             for lo, c in spans[:-1]:
-                assert lo % 32 == 0
-            full = [c for _, c in spans if c and c % 32 == 0]
+                assert lo % gw == 0
+            full = [c for _, c in spans if c and c % gw == 0]
             if full:
-                assert max(full) - min(full) <= 32
+                assert max(full) - min(full) <= gw
+            if n == 64 and parts == 8:
+                assert [c for _, c in spans] == [8] * 8

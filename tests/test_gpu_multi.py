@@ -1,5 +1,5 @@
 """One DASContext over several devices (csrc/kzg_multi.cu, EKZG_DEVICES): a batch is cut into contiguous shards of whole
-32-blob groups, one per member context, each on a host thread of its own, results written straight into the caller's
+blob groups (32 blobs, or 8 where a share is small), one per member context, each on a host thread of its own, results written straight into the caller's
 buffers.  On a one-GPU box the member contexts share device 0 (EKZG_DEVICES=0,0 -- same code path, two sets of tables and
 queues); with two or more GPUs visible the same tests also run on devices 0,1.  Everything is compared with the
 single-device session context, which the consensus vectors pin."""
@@ -55,7 +55,7 @@ def test_sharded_batch_equals_single_device(das_ctx, multi_ctx, pkg):
     import torch
     syn = _synth(pkg)
     before = torch.cuda.current_device()
-    for n in (33, 100, 64 * len(multi_ctx.devices) + 5):
+    for n in (12, 33, 100, 64 * len(multi_ctx.devices) + 5, 170):
         flat = b"".join(syn.blob(3000 + i) for i in range(n))
         want = das_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
         got = multi_ctx.compute_cells_and_kzg_proofs_batch(flat, n)
