@@ -23,6 +23,8 @@ def main():
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--mixed", type=int, default=1, help="cycle the batch size through 1024 / 256 / 96 / 33 / 512 / 7 (the latency-mode "
                     "G1-NTT kernel on context A below 257 blobs, the wide kernel forced on context B) instead of --batch every round")
+    ap.add_argument("--small", type=int, default=0, help="cycle the batch size through 3 / 5 / 8 / 13 / 16 / 24 / 40 / 64 / 80 instead: context A runs "
+                    "its defaults (one-point-per-thread MSM, cooperative latency-mode G1 NTTs), context B the 16-slice MSM and the radix-2 kernel")
     args = ap.parse_args()
     pkg = __graft_entry__.load_package()
     import importlib
@@ -45,13 +47,18 @@ def main():
         arr = base_arr.copy()
         arr[:, 1:] ^= key
         n = (1024, 256, 96, 33, 512, 7)[rnd % 6] if args.mixed else args.batch
+        if args.small:
+            n = (3, 5, 8, 13, 16, 24, 40, 64, 80)[rnd % 9]
         n = min(n, args.batch)
         flat = arr[:n * 4096].tobytes()
         os.environ.pop("EKZG_K5_R4_MAX", None)
+        os.environ.pop("EKZG_K4_NO_TINY", None)
         ca, pa, _ = a.compute_cells_and_kzg_proofs_batch(flat, n)
-        os.environ["EKZG_K5_R4_MAX"] = "0"      # context B: always the radix-2 G1-NTT kernel
+        os.environ["EKZG_K5_R4_MAX"] = "0"      # context B: always the radix-2 G1-NTT kernel (and never the 64-slice MSM)
+        os.environ["EKZG_K4_NO_TINY"] = "1"
         cb, pb, _ = b.compute_cells_and_kzg_proofs_batch(flat, n)
         os.environ.pop("EKZG_K5_R4_MAX", None)
+        os.environ.pop("EKZG_K4_NO_TINY", None)
         ka, _ = a.blob_to_kzg_commitment_batch(flat, n)
         kb, _ = b.blob_to_kzg_commitment_batch(flat, n)
         qa, _ = a.compute_blob_kzg_proof_batch(flat, ka, n)
@@ -63,7 +70,8 @@ def main():
             mism["blob_proofs"] += qa[i * 48:(i + 1) * 48] != qb[i * 48:(i + 1) * 48]
         done += n
         rnd += 1
-    print(json.dumps({"check": "two table layouts, identical outputs", "blobs": done, "windows": [[14, 13], [10, 9]], "mismatches": mism,
+    print(json.dumps({"check": "two table layouts, identical outputs", "blobs": done, "rounds": rnd, "batch_sizes": "small (3..80)" if args.small else ("mixed" if args.mixed else args.batch),
+                      "windows": [[14, 13], [10, 9]], "mismatches": mism,
                       "fp_multiplications_per_context": "~%.1e" % (done * 2.6e6), "seconds": round(time.time() - t0, 1)}))
     a.close()
     b.close()
