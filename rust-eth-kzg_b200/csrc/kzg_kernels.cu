@@ -835,8 +835,9 @@ k_fk20_g1_ntts(G1Jac* __restrict__ pts, int B, int G, int ph0, int ph1, unsigned
 // queue[0] = ticket counter, queue[1 + (g*7 + sp)*2 + kind] = finished multiplication (0) / combination (1) units of blob group g
 // in super-phase sp; zeroed by the launcher.  Tickets: super-phase major, then all multiplication units, then all combinations.
 // GW = blobs per blob group (= per warp): 32, one lane per blob; or 8 (COOP), where a multiplication unit spreads every field element
-// of a blob over four lanes (r4_mul_unit_coop) and a combination unit simply uses 8 of its 32 lanes -- for batches so small that the
-// machine is mostly idle and only the latency of the dependent products counts (launch_g1_ntt_phases picks).
+// of a blob over four lanes (r4_mul_unit_coop) and a combination unit spreads its independent additions over the four lanes of a
+// blob (r4_combine_unit_par) -- for batches so small that the machine is mostly idle and only the latency of the dependent
+// products counts (launch_g1_ntt_phases picks; a queue of 1 + 14 ceil(B/8) counters, well inside g1_ntt_queue_words(B)).
 template <int GW>
 __global__ void __launch_bounds__(NTT_THREADS, 2)
 k_fk20_g1_ntts_r4(G1Jac* __restrict__ pts, G1Jac* __restrict__ tmp, int B, int G, int sp_end, unsigned* __restrict__ queue) {
