@@ -431,7 +431,10 @@ def main():
         ach5 = ntt_imad / (stages["K5_g1_ntt"] / 1000) if stages["K5_g1_ntt"] else 0.0
         roofline = {"bound": "imad", "kernel": "k_fk20_msm (K4, %s form)" % {"r": "register XYZZ", "a": "batched affine, global scratch", "b": "batched affine, shared memory"}.get(os.environ.get("EKZG_K4", "v")[:1], "shared-memory-operand XYZZ"),
                     "achieved": ach / 1e12, "peak": imad_peak / 1e12, "unit": "T IMAD.WIDE/s", "frac": ach / imad_peak,
-                    "peak_source": peak_source, "traffic": None,
+                    "peak_source": peak_source,
+                    # DRAM bytes of that kernel per launch (ncu --set full, profiles/r2_p_prof_k4_k5_raw.csv: 26.97 GB read + 0.15 GB written at
+                    # 1024 blobs, w = 14); the HBM view with the algorithmic bytes is in roofline_hbm
+                    "traffic": (27.12e9 * n / 1024 if w == 14 else None), "traffic_unit": "bytes per launch",
                     "algorithmic_imad_per_launch": msm_imad, "kernel_ms": msm_ms,
                     "model": "%d blobs x 8192 scalars x %.2f table additions x %d multiply-adds (XYZZ mixed addition 8M+2S, one fused reduction)" % (n, adds_per_scalar, OP_XYZZ_MADD),
                     "k_fk20_g1_ntts": {"imad_per_launch": ntt_imad, "scalar_muls_per_blob": k5_heavy, "achieved": ach5 / 1e12, "frac": ach5 / imad_peak, "kernel_ms": stages["K5_g1_ntt"]},
@@ -444,10 +447,10 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         msm_bytes = int(n * (128 * 64 * adds_per_scalar * 96 + 128 * 64 * 32 + 128 * 144))
         hbm_ach = msm_bytes / (msm_ms / 1000) / 1e9 if msm_ms else 0.0
-        traffic = 27.08e9 * n / 1024 if w == 14 else None
+        traffic = 27.12e9 * n / 1024 if w == 14 else None
         roofline_hbm = {"bound": "hbm (NOT binding)", "kernel": "k_fk20_msm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "algorithmic_bytes": msm_bytes, "traffic": traffic, "traffic_over_algorithmic": traffic / msm_bytes if traffic else None,
-                        "traffic_source": "ncu --set full, dram__bytes_read+write per launch at 1024 blobs, w=14 (profiles/r1_v4_prof_k4_k5_raw.csv)",
+                        "traffic_source": "ncu --set full, dram__bytes_read+write per launch of k_fk20_msm_vm<4> at 1024 blobs, w=14 (profiles/r2_p_prof_k4_k5_raw.csv)",
                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                         "note": "1.8x the algorithmic bytes: 96-byte table entries straddle 64-byte DRAM atoms; at ~8 % of HBM peak it costs nothing -- the kernel is bound by the fmaheavy pipe"}
         line = {
