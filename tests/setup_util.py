@@ -100,3 +100,58 @@ def g2_compress(pt):
     out = bytearray(x1.to_bytes(48, "big") + x0.to_bytes(48, "big"))
     out[0] |= 0x80 | (0x20 if _larger(y) else 0)
     return bytes(out)
+
+
+# ---- G2 affine arithmetic over Fp2 (test-side derivation of a rotated setup; slow and simple) ----------------------------------
+def f2_sub(a, b):
+    return ((a[0] - b[0]) % P, (a[1] - b[1]) % P)
+
+
+def f2_inv(a):
+    n = pow((a[0] * a[0] + a[1] * a[1]) % P, P - 2, P)
+    return (a[0] * n % P, -a[1] * n % P)
+
+
+def g2_add(p1, p2):
+    """affine addition on y^2 = x^3 + 4(1 + u); None is the identity"""
+    if p1 is None:
+        return p2
+    if p2 is None:
+        return p1
+    (x1, y1), (x2, y2) = p1, p2
+    if x1 == x2:
+        if f2_add(y1, y2) == (0, 0):
+            return None
+        lam = f2_mul(f2_mul((3, 0), f2_mul(x1, x1)), f2_inv(f2_add(y1, y1)))
+    else:
+        lam = f2_mul(f2_sub(y2, y1), f2_inv(f2_sub(x2, x1)))
+    x3 = f2_sub(f2_sub(f2_mul(lam, lam), x1), x2)
+    return x3, f2_sub(f2_mul(lam, f2_sub(x1, x3)), y1)
+
+
+def g2_mul(pt, k):
+    acc = None
+    for bit in bin(k)[2:]:
+        acc = g2_add(acc, acc)
+        if bit == "1":
+            acc = g2_add(acc, pt)
+    return acc
+
+
+R_ORDER = 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001
+
+
+def brp12(k):
+    return int(format(k, "012b")[::-1], 2)
+
+
+def rotated_setup(g1_monomial, g2_monomial, s, g1_mul):
+    """the setup of secret s * tau: point i scaled by s^i (g1_mul: compressed G1 point x integer -> compressed point, the oracle's)"""
+    g1 = [g1_mul(pt, pow(s, i, R_ORDER)) if i else pt for i, pt in enumerate(g1_monomial)]
+    g2 = [g2_compress(g2_mul(g2_decompress(pt), pow(s, i, R_ORDER))) if pow(s, i, R_ORDER) != 1 else pt for i, pt in enumerate(g2_monomial)]
+    return g1, g2
+
+
+def rotate_blob(blob, shift):
+    """evaluation form of p(w^shift X) for the blob of p: the domain in natural order moves by `shift` places"""
+    return b"".join(blob[32 * brp12((brp12(k) + shift) % 4096):32 * brp12((brp12(k) + shift) % 4096) + 32] for k in range(4096))

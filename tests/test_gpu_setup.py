@@ -117,6 +117,46 @@ def test_negated_setup_against_mainnet_oracle(pkg, das_ctx, neg_ctx):
     assert neg_ctx.verify_blob_kzg_proof_batch([blob, blob], [commitment] * 2, [bproof] * 2) is True
 
 
+def test_rotated_setup_against_mainnet_oracle(pkg, das_ctx):
+    """a setup whose points are all NEW ones (not sign flips): secret s * tau with s = w_4096^64, a 64th root of unity.  p(s X) is the blob
+    with its domain rotated by 64 places; s^64 = 1 keeps every cell's coset and X^64 - c_k in place, so commitment and cell proofs under
+    s * tau are the mainnet ones of the rotated blob, and a point proof at z is s^-1 times the mainnet proof of the rotated blob at z / s.
+    G1 points scaled by the oracle's curve arithmetic, G2 points by the affine arithmetic of tests/setup_util.py."""
+    g1m, _, g2m = su.mainnet_points()
+    w4096 = pow(7, (R - 1) // 4096, R)
+    s_ = pow(w4096, 64, R)
+    assert pow(s_, 64, R) == 1 and pow(s_, 32, R) != 1
+    g1, g2 = su.rotated_setup(g1m, g2m, s_, cref.g1_mul)
+    assert g2[64] == g2m[64] and g2[1] != g2m[1] and g1[1] != g1m[1]
+    ctx = pkg.DASContext.from_json(su.setup_json(g1, g2), use_precomp=False)
+    try:
+        rng = random.Random(79)
+        blob = b"".join(rng.randrange(R).to_bytes(32, "big") for _ in range(4096))
+        rot = su.rotate_blob(blob, 64)
+        commitment = ctx.blob_to_kzg_commitment(blob)
+        assert commitment == cref.blob_to_kzg_commitment(rot)
+        cells, proofs = ctx.compute_cells_and_kzg_proofs(blob)
+        want_cells, _ = cref.compute_cells_and_kzg_proofs(blob)
+        _, want_proofs = cref.compute_cells_and_kzg_proofs(rot)
+        assert cells == want_cells and proofs == want_proofs
+        bc, bp, _ = ctx.compute_cells_and_kzg_proofs_batch(blob * 2, 2)        # FK20 route
+        assert bytes(bp[:128 * 48]) == b"".join(want_proofs) and bytes(bp[128 * 48:]) == b"".join(want_proofs)
+        idx = list(range(128))
+        assert ctx.verify_cell_kzg_proof_batch([commitment] * 128, idx, cells, proofs) is True
+        assert das_ctx.verify_cell_kzg_proof_batch([commitment] * 128, idx, cells, proofs) is False
+        z = rng.randrange(R)
+        proof, y = ctx.compute_kzg_proof(blob, z.to_bytes(32, "big"))
+        s_inv = pow(s_, R - 2, R)
+        mp, my = cref.compute_kzg_proof(rot, (z * s_inv % R).to_bytes(32, "big"))
+        assert y == my and proof == cref.g1_mul(mp, s_inv)
+        assert ctx.verify_kzg_proof(commitment, z.to_bytes(32, "big"), y, proof) is True       # e(.., [s tau]_2): a G2 point the loader decompressed
+        assert das_ctx.verify_kzg_proof(commitment, z.to_bytes(32, "big"), y, proof) is False
+        bproof = ctx.compute_blob_kzg_proof(blob, commitment)
+        assert ctx.verify_blob_kzg_proof(blob, commitment, bproof) is True
+    finally:
+        ctx.close()
+
+
 def test_custom_setup_on_wide_windows(pkg, das_ctx, neg_ctx, monkeypatch):
     """use_precomp = true with a caller's setup: merged top window + the wider SRS tables built from the custom points"""
     monkeypatch.setenv("EKZG_FK20_WINDOW", "10")
